@@ -1,0 +1,776 @@
+/* TEST INFRASTRUCTURE ONLY -- CPU restatement (plain C) of the reference PopSift
+ * default hot path: image -> Gaussian pyramid -> DoG extrema + refine ->
+ * orientation -> 128-D descriptor -> normalisation -> Feature records.
+ *
+ * Every function cites the reference file:line it follows (paths relative to
+ * /root/reference/src/popsift/).  Compile with -ffp-contract=off: fused
+ * multiply-adds are written explicitly (fmaf) exactly where the reference's
+ * sm_100 SASS has FFMA (checked with cuobjdump on oracle/_ref/libpopsift_ref.so).
+ *
+ * Parity pin: tests/golden/ (outputs of the unmodified reference on a B200).
+ * Not shipped, not linked by the product.
+ */
+#define _GNU_SOURCE
+#include "sift_oracle.h"
+
+#include <fenv.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORI_NBINS 36              /* sift_constants.h:41 */
+#define ORI_WINFACTOR 1.5f        /* sift_constants.h:42 */
+#define DESC_MAGNIFY 3.0f         /* sift_constants.h:45 */
+#define ORIENTATION_MAX_COUNT 4   /* sift_constants.h:54 */
+static const float F_PI  = 3.14159265358979323846f;        /* sift_constants.h:23 */
+static const float F_PI2 = 2.0f * 3.14159265358979323846f; /* sift_constants.h:29 */
+
+typedef struct { float x, y, sigma; int lpos; int octave; } iext_t;
+typedef struct { float x, y, sigma; int lpos, octave, num_ori, idx_ori; float ori[4]; } ext_t;
+
+struct orc_ctx {
+    orc_config cfg;
+    orc_tables tab;
+    int w, h;               /* input size */
+    int noct, nlev;         /* octaves, L+3 */
+    int32_t W[ORC_MAX_OCTAVES], H[ORC_MAX_OCTAVES];
+    float* gauss[ORC_MAX_OCTAVES];
+    float* dog[ORC_MAX_OCTAVES];
+    iext_t* iext; int n_iext, cap_iext;
+    ext_t*  ext;  int n_ext;
+    float*  desc; int n_desc;
+};
+
+void orc_default_config(orc_config* c)
+{   /* sift_conf.cu:18-41 */
+    c->octaves = -1; c->levels = 3; c->sigma = 1.6f; c->edge_limit = 10.0f; c->threshold = 0.04f;
+    c->upscale = 1.0f; c->initial_blur = 0.5f; c->has_initial_blur = 1;
+    c->sift_mode = ORC_MODE_POPSIFT; c->norm_mode = ORC_NORM_ROOTSIFT; c->norm_multi = 0;
+    c->max_extrema = 100000;
+}
+
+int orc_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n; return 1;
+#endif
+}
+
+/* ------------------------------------------------------------------ tables */
+
+/* gauss_filter.cu:301-307 (VLFeat_Compute span) */
+static int vlfeat_span(float sigma)
+{
+    int s = (int)(ceilf(4.0f * sigma) + 1);
+    return s < ORC_GAUSS_ALIGN - 1 ? s : ORC_GAUSS_ALIGN - 1;
+}
+
+/* gauss_filter.cu:341-371 (computeBlurTable): taps in double, stored float,
+ * normalised by a double sum that accumulates 2.0f*val of the *float* tap. */
+static void blur_row(float sig, int* span_out, float* f)
+{
+    int spn = vlfeat_span(sig);
+    if (spn > ORC_GAUSS_ALIGN - 1) spn = ORC_GAUSS_ALIGN - 1;
+    double sum = 1.0;
+    f[0] = 1.0f;
+    for (int x = 1; x < spn; x++) {
+        const float val = (float)exp(-0.5 * pow((double)x / (double)sig, 2.0));
+        f[x] = val;
+        sum += (double)(2.0f * val);
+    }
+    for (int x = 0; x < spn; x++) f[x] = (float)((double)f[x] / sum);
+    for (int x = spn; x < ORC_GAUSS_ALIGN; x++) f[x] = 0.0f;
+    *span_out = spn;
+}
+
+int orc_compute_tables(const orc_config* c, orc_tables* t)
+{
+    memset(t, 0, sizeof(*t));
+    const int levels = c->levels < 2 ? 2 : c->levels;      /* popsift.cpp:86 */
+    const float sigma0 = c->sigma;
+    if (sigma0 > 2.0f) return -1;                           /* gauss_filter.cu:131 */
+    if (levels > ORC_GAUSS_LEVELS) return -2;               /* gauss_filter.cu:138 */
+    const int stages = levels + 3;
+    /* gauss_filter.cu:169-171: float pow overload */
+    const float initial_blur = c->has_initial_blur ? c->initial_blur * powf(2.0f, c->upscale) : 0.0f;
+    /* gauss_filter.cu:177-186 */
+    t->inc.sigma[0] = c->has_initial_blur ? sqrtf(fabsf(sigma0 * sigma0 - initial_blur * initial_blur)) : sigma0;
+    for (int lvl = 1; lvl < stages; lvl++) {
+        const float sigmaP = sigma0 * powf(2.0f, (float)(lvl - 1) / (float)levels);
+        const float sigmaS = sigma0 * powf(2.0f, (float)(lvl) / (float)levels);
+        t->inc.sigma[lvl] = sqrtf(sigmaS * sigmaS - sigmaP * sigmaP);
+    }
+    /* rows beyond `stages` have sigma 0 in the reference (cleared struct): span = 1 */
+    for (int lvl = 0; lvl < ORC_GAUSS_LEVELS; lvl++)
+        blur_row(t->inc.sigma[lvl], &t->inc.span[lvl], &t->inc.filter[lvl * ORC_GAUSS_ALIGN]);
+    /* gauss_filter.cu:227-238, octave 0 row */
+    {
+        float oct_sigma = scalbnf(sigma0, 0);
+        float b = sqrtf(fabsf(oct_sigma * oct_sigma - initial_blur * initial_blur));
+        t->dd_sigma0 = scalbnf(b, 0);
+        blur_row(t->dd_sigma0, &t->dd_span0, t->dd_filter0);
+    }
+    t->peak_threshold = c->threshold * 0.5f * 255.0f / (float)levels; /* sift_conf.cu:276-279 */
+    t->sigma_k = powf(2.0f, 1.0f / (float)levels);                    /* sift_constants.cu:27 */
+    return 0;
+}
+
+/* popsift.cpp:109-126 + sift_pyramid.cu:129-134 */
+int orc_geometry(const orc_config* c, int w, int h, int32_t* W, int32_t* H)
+{
+    const float up = c->upscale;
+    const float scale = 1.0f / powf(2.0f, -up);
+    int oct = c->octaves;
+    if (oct < 0) {
+        int mn = w < h ? w : h;
+        oct = (int)(floorf(logf((float)mn) / logf(2.0f)) - 3.0f + scale);
+        if (oct < 1) oct = 1;
+    }
+    if (oct > ORC_MAX_OCTAVES) oct = ORC_MAX_OCTAVES;
+    int ww = (int)ceilf(w * scale), hh = (int)ceilf(h * scale);
+    for (int o = 0; o < oct; o++) {
+        W[o] = ww; H[o] = hh;
+        ww = (int)ceilf(ww / 2.0f); hh = (int)ceilf(hh / 2.0f);
+    }
+    return oct;
+}
+
+/* ------------------------------------------------------------ texture model */
+
+static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* What tex2D<float> returns for the reference's input texture
+ * (s_image.cu:138-167: pitch2D u8, normalized coords, linear filter, clamp,
+ * cudaReadModeNormalizedFloat).  MEASURED on a B200 with oracle/texprobe.cu
+ * (all 65536 (a,b) pairs at fraction 0.5 in x and in y, 2x2 blends, and the
+ * reference's own coordinate arithmetic at 640x480, 641x479, 3840x2160):
+ *   - texel-space coordinate xB = rx*w - 0.5, clamped to [-0.5, w-0.5];
+ *     fraction rounded to nearest 1/256;
+ *   - texels widened u8 -> unorm16 (x257); 2x2 blend in integer arithmetic,
+ *     rounded half-up to a 16-bit value r16;
+ *   - returned float = (float)r16 / 65535.0f (correctly rounded).
+ * 0 mismatches over 6.4 M probed samples (tools/analyze_texprobe.py). */
+float orc_tex_u8(const uint8_t* img, int w, int h, float rx, float ry)
+{
+    float fx = rx * (float)w - 0.5f;
+    float fy = ry * (float)h - 0.5f;
+    if (fx < -0.5f) fx = -0.5f;
+    if (fx > (float)w - 0.5f) fx = (float)w - 0.5f;
+    if (fy < -0.5f) fy = -0.5f;
+    if (fy > (float)h - 0.5f) fy = (float)h - 0.5f;
+    float flx = floorf(fx), fly = floorf(fy);
+    int ix = (int)flx, iy = (int)fly;
+    int ax = (int)floorf((fx - flx) * 256.0f + 0.5f);   /* 8-bit fraction, round to nearest */
+    int ay = (int)floorf((fy - fly) * 256.0f + 0.5f);
+    if (ax == 256) { ax = 0; ix += 1; }
+    if (ay == 256) { ay = 0; iy += 1; }
+    int x0 = clampi(ix, 0, w - 1), x1 = clampi(ix + 1, 0, w - 1);
+    int y0 = clampi(iy, 0, h - 1), y1 = clampi(iy + 1, 0, h - 1);
+    const int64_t t00 = img[(size_t)y0 * w + x0], t10 = img[(size_t)y0 * w + x1];
+    const int64_t t01 = img[(size_t)y1 * w + x0], t11 = img[(size_t)y1 * w + x1];
+    const int64_t num = (256 - ax) * (256 - ay) * t00 + ax * (256 - ay) * t10
+                      + (256 - ax) * ay * t01 + ax * ay * t11;   /* weights sum to 65536 */
+    const int64_t r16 = (num * 257 + 32768) >> 16;
+    return (float)r16 / 65535.0f;
+}
+
+/* ----------------------------------------------------------------- pyramid */
+
+/* s_pyramid_build_ra.cu:17-55 (normalizedSource::horiz): octave 0, level 0,
+ * rows, straight from the input texture; output x255. */
+static void level0_rows(const orc_ctx* c, const uint8_t* img, float* dst)
+{
+    const int W0 = c->W[0], H0 = c->H[0];
+    const int span = c->tab.dd_span0;
+    const float* g = c->tab.dd_filter0;
+    float shift = 0.5f;   /* s_pyramid_build.cu:108-114 */
+    if (c->cfg.sift_mode == ORC_MODE_POPSIFT || c->cfg.sift_mode == ORC_MODE_VLFEAT)
+        shift = 0.5f * powf(2.0f, c->cfg.upscale - 0);
+    #pragma omp parallel for schedule(static)
+    for (int Y = 0; Y < H0; Y++) {
+        const float read_y = ((float)Y + shift) / (float)H0;
+        for (int X = 0; X < W0; X++) {
+            const float read_x = ((float)X + shift) / (float)W0;
+            float out = 0.0f;
+            for (int off = span; off > 0; off--) {
+                const float offrel = (float)off / (float)W0;
+                const float v1 = orc_tex_u8(img, c->w, c->h, read_x - offrel, read_y);
+                const float v2 = orc_tex_u8(img, c->w, c->h, read_x + offrel, read_y);
+                out = fmaf(v1 + v2, g[off], out);
+            }
+            out = fmaf(orc_tex_u8(img, c->w, c->h, read_x, read_y), g[0], out);
+            dst[(size_t)Y * W0 + X] = out * 255.0f;
+        }
+    }
+}
+
+/* s_pyramid_build_aa.cu:17-50 (absoluteSource::horiz): rows of level l-1 ->
+ * intermediate.  acc = C*g0 ; += (A+B)*g[span] ; then off = span-1..1. */
+static void rows_pass(const float* src, float* dst, int W, int H, const float* g, int span)
+{
+    #pragma omp parallel for schedule(static)
+    for (int y = 0; y < H; y++) {
+        const float* s = src + (size_t)y * W;
+        float* d = dst + (size_t)y * W;
+        for (int x = 0; x < W; x++) {
+            float out = fmaf(s[x], g[0], 0.0f);
+            out = fmaf(s[clampi(x - span, 0, W - 1)] + s[clampi(x + span, 0, W - 1)], g[span], out);
+            for (int off = span - 1; off > 0; off--)
+                out = fmaf(s[clampi(x - off, 0, W - 1)] + s[clampi(x + off, 0, W - 1)], g[off], out);
+            d[x] = out;
+        }
+    }
+}
+
+/* s_pyramid_build_aa.cu:52-86 (absoluteSource::vert): columns of the
+ * intermediate -> level l.  off = span..1: += v(-off)*g ; += v(+off)*g ; centre last. */
+static void cols_pass(const float* src, float* dst, int W, int H, const float* g, int span)
+{
+    #pragma omp parallel for schedule(static)
+    for (int y = 0; y < H; y++) {
+        float* d = dst + (size_t)y * W;
+        for (int x = 0; x < W; x++) {
+            float out = 0.0f;
+            for (int off = span; off > 0; off--) {
+                out = fmaf(src[(size_t)clampi(y - off, 0, H - 1) * W + x], g[off], out);
+                out = fmaf(src[(size_t)clampi(y + off, 0, H - 1) * W + x], g[off], out);
+            }
+            out = fmaf(src[(size_t)y * W + x], g[0], out);
+            d[x] = out;
+        }
+    }
+}
+
+/* s_pyramid_build.cu:460-594, default arm :547-575, then make_dog :74-92 */
+static void build_pyramid(orc_ctx* c, const uint8_t* img)
+{
+    const int L = c->nlev - 3;
+    for (int o = 0; o < c->noct; o++) {
+        const int W = c->W[o], H = c->H[o];
+        const size_t P = (size_t)W * H;
+        float* interm = (float*)malloc(P * sizeof(float));
+        for (int l = 0; l < c->nlev; l++) {
+            float* dstp = c->gauss[o] + P * l;
+            const float* g = &c->tab.inc.filter[l * ORC_GAUSS_ALIGN];
+            const int span = c->tab.inc.span[l];
+            if (l == 0) {
+                if (o == 0) {
+                    level0_rows(c, img, interm);
+                    cols_pass(interm, dstp, W, H, g, span);
+                } else {
+                    /* s_pyramid_build.cu:50-71 get_by_2_pick_every_second from level L of o-1 */
+                    const int Wp = c->W[o - 1], Hp = c->H[o - 1];
+                    const float* srcp = c->gauss[o - 1] + (size_t)Wp * Hp * L;
+                    for (int y = 0; y < H; y++)
+                        for (int x = 0; x < W; x++) {
+                            int rx = clampi(x << 1, 0, Wp), ry = clampi(y << 1, 0, Hp);
+                            rx = clampi(rx, 0, Wp - 1); ry = clampi(ry, 0, Hp - 1);   /* texture clamp */
+                            dstp[(size_t)y * W + x] = srcp[(size_t)ry * Wp + rx];
+                        }
+                }
+            } else {
+                rows_pass(c->gauss[o] + P * (l - 1), interm, W, H, g, span);
+                cols_pass(interm, dstp, W, H, g, span);
+            }
+        }
+        free(interm);
+        for (int l = 0; l < c->nlev - 1; l++) {
+            const float* a = c->gauss[o] + P * l;
+            const float* b = c->gauss[o] + P * (l + 1);
+            float* d = c->dog[o] + P * l;
+            for (size_t i = 0; i < P; i++) d[i] = b[i] - a[i];
+        }
+    }
+}
+
+/* ----------------------------------------------------------------- extrema */
+
+typedef struct { const float* dog; int W, H, nd; } dogv_t;
+static inline float DG(const dogv_t* v, int x, int y, int z)
+{   /* clamp addressing in x, y and layer (sift_octave.cu:313-315) */
+    x = clampi(x, 0, v->W - 1); y = clampi(y, 0, v->H - 1); z = clampi(z, 0, v->nd - 1);
+    return v->dog[((size_t)z * v->H + y) * v->W + x];
+}
+
+/* s_extrema.cu:56-120: strict 26-neighbour extremum */
+static int is_extremum(const dogv_t* v, int x, int y, int z)
+{
+    const float val = DG(v, x, y, z);
+    int gt = 1, lt = 1;
+    for (int dz = -1; dz <= 1; dz++)
+        for (int dy = -1; dy <= 1; dy++)
+            for (int dx = -1; dx <= 1; dx++) {
+                if (!dx && !dy && !dz) continue;
+                const float f = DG(v, x + dx, y + dy, z + dz);
+                if (!(val > f)) gt = 0;
+                if (!(val < f)) lt = 0;
+            }
+    return gt || lt;
+}
+
+/* s_solve.h:25-86 with the FFMA pattern of the sm_100 build:
+ * detK = fma(a1,a2, -(b1*b2)) ; det = fma(i02,det2, fma(i00,det0, i01*det1)) ;
+ * rows: fma(i[y][2],b.z, fma(i[y][1],b.y, fma(i[y][0],b.x, 0))) */
+static int solve3(float i00, float i01, float i02, float i11, float i12, float i22, float* bx, float* by, float* bz)
+{
+    const float det0 = fmaf(i11, i22, -(i12 * i12));
+    const float det1 = fmaf(i12, i02, -(i01 * i22));
+    const float det2 = fmaf(i01, i12, -(i11 * i02));
+    const float det3 = fmaf(i00, i22, -(i02 * i02));
+    const float det4 = fmaf(i01, i02, -(i00 * i12));
+    const float det5 = fmaf(i00, i11, -(i01 * i01));
+    float det = i01 * det1;
+    det = fmaf(i00, det0, det);
+    det = fmaf(i02, det2, det);
+    if (det == 0.0f) return 0;
+    const float rsd = 1.0f / det;   /* __frcp_rn */
+    const float a00 = det0 * rsd, a10 = det1 * rsd, a20 = det2 * rsd;
+    const float a11 = det3 * rsd, a12 = det4 * rsd, a22 = det5 * rsd;
+    const float X = *bx, Y = *by, Z = *bz;
+    *bx = fmaf(a20, Z, fmaf(a10, Y, fmaf(a00, X, 0.0f)));
+    *by = fmaf(a12, Z, fmaf(a11, Y, fmaf(a10, X, 0.0f)));
+    *bz = fmaf(a22, Z, fmaf(a12, Y, fmaf(a20, X, 0.0f)));
+    return 1;
+}
+
+/* s_extrema.cu:300-503 find_extrema_in_dog_sub, all three ModeFunctions (:122-298) */
+static int refine_extremum(const orc_ctx* c, const dogv_t* v, int x, int y, int level, iext_t* out)
+{
+    const int mode = c->cfg.sift_mode;
+    const int width = v->W, height = v->H;
+    const int maxlevel = c->nlev - 1;
+    const float thr = c->tab.peak_threshold;
+
+    if (mode == ORC_MODE_OPENCV)
+        if (x < 5 || y < 5 || x >= width - 5 || y >= height - 5) return 0;
+
+    const float val = DG(v, x, y, level);
+    if (mode == ORC_MODE_OPENCV) { if (!(fabsf(val) >= floorf(thr))) return 0; }
+    else if (mode == ORC_MODE_VLFEAT) { if (!(fabsf(val) >= 0.8f * 2.0f * thr)) return 0; }
+    else { if (!(fabsf(val) >= 1.6f * thr)) return 0; }
+
+    if (!is_extremum(v, x, y, level)) return 0;
+
+    float Dx = 0, Dy = 0, Dz = 0, DDx = 0, DDy = 0, DDz = 0, DXx = 0, DXy = 0, DXz = 0;
+    float dx = 0, dy = 0, dz = 0;
+    int nx = x, ny = y, nz = level;
+    int iter = 0;
+    do {
+        iter++;
+        const float x2y1z1 = DG(v, nx + 1, ny, nz), x0y1z1 = DG(v, nx - 1, ny, nz);
+        const float x1y2z1 = DG(v, nx, ny + 1, nz), x1y0z1 = DG(v, nx, ny - 1, nz);
+        const float x1y1z2 = DG(v, nx, ny, nz + 1), x1y1z0 = DG(v, nx, ny, nz - 1);
+        Dx = (x2y1z1 - x0y1z1) * 0.5f;
+        Dy = (x1y2z1 - x1y0z1) * 0.5f;
+        Dz = (x1y1z2 - x1y1z0) * 0.5f;
+        const float x1y1z1 = DG(v, nx, ny, nz);
+        const float c2 = x1y1z1 * 2.0f;
+        DDx = (x2y1z1 + x0y1z1) - c2;
+        DDy = (x1y2z1 + x1y0z1) - c2;
+        DDz = (x1y1z2 + x1y1z0) - c2;
+        const float x0y0z1 = DG(v, nx - 1, ny - 1, nz), x0y1z0 = DG(v, nx - 1, ny, nz - 1);
+        const float x0y1z2 = DG(v, nx - 1, ny, nz + 1), x0y2z1 = DG(v, nx - 1, ny + 1, nz);
+        const float x1y0z0 = DG(v, nx, ny - 1, nz - 1), x1y0z2 = DG(v, nx, ny - 1, nz + 1);
+        const float x1y2z0 = DG(v, nx, ny + 1, nz - 1), x1y2z2 = DG(v, nx, ny + 1, nz + 1);
+        const float x2y0z1 = DG(v, nx + 1, ny - 1, nz), x2y1z0 = DG(v, nx + 1, ny, nz - 1);
+        const float x2y1z2 = DG(v, nx + 1, ny, nz + 1), x2y2z1 = DG(v, nx + 1, ny + 1, nz);
+        DXx = (((x2y2z1 + x0y0z1) - x0y2z1) - x2y0z1) * 0.25f;
+        DXy = (((x2y1z2 + x0y1z0) - x0y1z2) - x2y1z0) * 0.25f;
+        DXz = (((x1y2z2 + x1y0z0) - x1y2z0) - x1y0z2) * 0.25f;
+
+        float bx = -Dx, by = -Dy, bz = -Dz;
+        /* A[0][0]=DDx A[1][1]=DDy A[2][2]=DDz A[0][1]=DXx A[0][2]=DXy A[1][2]=DXz */
+        if (!solve3(DDx, DXx, DXy, DDy, DXz, DDz, &bx, &by, &bz)) { dx = dy = dz = 0.0f; break; }
+        dx = bx; dy = by; dz = bz;
+
+        const int last_it = (iter == 5);
+        int retval;
+        if (mode == ORC_MODE_OPENCV) {
+            if (fabsf(dx) < 0.5f && fabsf(dy) < 0.5f && fabsf(dz) < 0.5f) retval = 1;
+            else {
+                nx += (int)roundf(dx); ny += (int)roundf(dy); nz += (int)roundf(dz);
+                retval = (nx < 5 || nx >= width - 5 || ny < 5 || ny >= height - 5 || nz < 1 || nz > maxlevel - 2) ? -1 : 0;
+            }
+        } else if (last_it) {
+            retval = 0;
+        } else {
+            int tx = ((dx >= 0.6f && nx < width - 2) ? 1 : 0) + ((dx <= -0.6f && nx > 1) ? -1 : 0);
+            int ty = ((dy >= 0.6f && ny < height - 2) ? 1 : 0) + ((dy <= -0.6f && ny > 1) ? -1 : 0);
+            int tz = 0;
+            if (mode == ORC_MODE_POPSIFT)
+                tz = ((dz >= 0.6f && nz < maxlevel - 1) ? 1 : 0) + ((dz <= -0.6f && nz > 1) ? -1 : 0);
+            if (tx == 0 && ty == 0 && tz == 0) retval = 1;
+            else { nx += tx; ny += ty; nz += tz; retval = 0; }
+        }
+        if (retval == -1) return 0;
+        if (retval == 1) break;
+    } while (iter < 5);
+
+    if (iter >= 5 && mode == ORC_MODE_OPENCV) return 0;
+    if (mode != ORC_MODE_OPENCV)
+        if (dx >= 1.5f || dy >= 1.5f || dz >= 1.5f) return 0;
+
+    const float xn = (float)nx + dx, yn = (float)ny + dy, sn = (float)nz + dz;
+    if (mode != ORC_MODE_OPENCV)
+        if (xn < 0.0f || xn > (float)width - 1.0f || yn < 0.0f || yn > (float)height - 1.0f ||
+            sn < 0.0f || sn > (float)maxlevel) return 0;
+
+    const float contr = val + fmaf(dz, Dz, fmaf(dy, Dy, dx * Dx)) * 0.5f;
+    const float tr = DDx + DDy;
+    const float det = fmaf(DDx, DDy, -(DXx * DXx));
+    const float edgeval = tr * tr / det;
+    if (!(det > 0.0f)) return 0;
+    if (fabsf(contr) < thr * 2.0f) return 0;
+    const float el = c->cfg.edge_limit;
+    if (edgeval >= (el + 1.0f) * (el + 1.0f) / el) return 0;
+
+    out->x = xn; out->y = yn; out->lpos = (int)roundf(sn);
+    out->sigma = c->cfg.sigma * powf(c->tab.sigma_k, sn);
+    return 1;
+}
+
+static void find_extrema(orc_ctx* c)
+{
+    const int L = c->nlev - 3;
+    c->n_iext = 0;
+    for (int o = 0; o < c->noct; o++) {
+        dogv_t v = { c->dog[o], c->W[o], c->H[o], c->nlev - 1 };
+        int count_o = 0;
+        for (int level = 1; level <= L; level++)
+            for (int y = 1; y <= v.H - 2; y++)
+                for (int x = 1; x <= v.W - 2; x++) {
+                    iext_t e;
+                    if (!refine_extremum(c, &v, x, y, level, &e)) continue;
+                    if (count_o >= c->cfg.max_extrema) continue;
+                    e.octave = o;
+                    if (c->n_iext == c->cap_iext) {
+                        c->cap_iext = c->cap_iext ? 2 * c->cap_iext : 4096;
+                        c->iext = (iext_t*)realloc(c->iext, sizeof(iext_t) * c->cap_iext);
+                    }
+                    c->iext[c->n_iext++] = e; count_o++;
+                }
+    }
+}
+
+/* -------------------------------------------------------------- orientation */
+
+static inline float GP(const float* pl, int W, int H, int x, int y)
+{
+    x = clampi(x, 0, W - 1); y = clampi(y, 0, H - 1);
+    return pl[(size_t)y * W + x];
+}
+
+/* s_gradiant.h:55-69 */
+static inline void get_gradiant(float* grad, float* theta, int x, int y, const float* pl, int W, int H)
+{
+    const float dx = GP(pl, W, H, x + 1, y) - GP(pl, W, H, x - 1, y);
+    const float dy = GP(pl, W, H, x, y + 1) - GP(pl, W, H, x, y - 1);
+    *grad = hypotf(dx, dy);
+    *theta = atan2f(dy, dx);
+}
+
+static void box3(const float* src, float* dst)
+{   /* s_orientation.cu:58-68 */
+    for (int b = 0; b < ORI_NBINS; b++) {
+        const int prev = b == 0 ? ORI_NBINS - 1 : b - 1;
+        const int next = b == ORI_NBINS - 1 ? 0 : b + 1;
+        dst[b] = (src[prev] + src[b] + src[next]) / 3.0f;
+    }
+}
+
+/* s_orientation.cu:75-259 ori_par */
+static void orientation_one(const orc_ctx* c, const iext_t* ie, ext_t* e)
+{
+    const int o = ie->octave;
+    const int W = c->W[o], H = c->H[o];
+    const int lvl = clampi(ie->lpos, 0, c->nlev - 1);
+    const float* pl = c->gauss[o] + (size_t)W * H * lvl;
+    float hist[ORI_NBINS], sm[ORI_NBINS];
+    memset(hist, 0, sizeof(hist));
+    const float x = ie->x, y = ie->y, sig = ie->sigma;
+    const float sigw = ORI_WINFACTOR * sig;
+    const int rad = (int)roundf(3.0f * sigw);
+    const float factor = -0.5f / (sigw * sigw);
+    const int sq_thres = rad * rad;
+    int xmin = (int)roundf(x) - rad; if (xmin < 1) xmin = 1;
+    int xmax = (int)roundf(x) + rad; if (xmax > W - 2) xmax = W - 2;
+    int ymin = (int)roundf(y) - rad; if (ymin < 1) ymin = 1;
+    int ymax = (int)roundf(y) + rad; if (ymax > H - 2) ymax = H - 2;
+    for (int yy = ymin; yy <= ymax; yy++)
+        for (int xx = xmin; xx <= xmax; xx++) {
+            float grad, theta;
+            get_gradiant(&grad, &theta, xx, yy, pl, W, H);
+            const float ddx = (float)xx - x, ddy = (float)yy - y;
+            const int sq_dist = (int)(ddx * ddx + ddy * ddy);
+            if (sq_dist <= sq_thres) {
+                const float weight = grad * expf((float)sq_dist * factor);
+                int bidx = (int)roundf((float)ORI_NBINS * (theta + F_PI) / F_PI2);
+                if (bidx == ORI_NBINS) bidx = 0;
+                if (bidx < 0 || bidx > ORI_NBINS) continue;
+                hist[bidx] += weight;
+            }
+        }
+    for (int i = 0; i < 3; i++) { box3(hist, sm); box3(sm, hist); }
+    memcpy(sm, hist, sizeof(sm));
+
+    float refined[ORI_NBINS], yval[ORI_NBINS];
+    for (int b = 0; b < ORI_NBINS; b++) {
+        const int prev = b == 0 ? ORI_NBINS - 1 : b - 1;
+        const int next = b == ORI_NBINS - 1 ? 0 : b + 1;
+        int pred = sm[b] > fmaxf(sm[prev], sm[next]);
+        const float num = pred ? 3.0f * sm[prev] - 4.0f * sm[b] + 1.0f * sm[next] : 0.0f;
+        const float denB = pred ? 2.0f * (sm[prev] - 2.0f * sm[b] + sm[next]) : 1.0f;
+        const float newbin = num / denB;
+        pred = pred && newbin >= 0.0f && newbin <= 2.0f;
+        refined[b] = pred ? (float)prev + newbin : -1.0f;
+        yval[b] = pred ? -(num * num) / (4.0f * denB) + sm[prev] : -INFINITY;
+    }
+    /* descending sort by yval (common/warp_bitonic_sort.h), top 4 with yval >= 0.8*best */
+    int idx[ORI_NBINS];
+    for (int b = 0; b < ORI_NBINS; b++) idx[b] = b;
+    for (int i = 1; i < ORI_NBINS; i++) {   /* stable insertion sort */
+        int k = idx[i], j = i - 1;
+        while (j >= 0 && yval[idx[j]] < yval[k]) { idx[j + 1] = idx[j]; j--; }
+        idx[j + 1] = k;
+    }
+    const float best = yval[idx[0]];
+    const float yref = 0.8f * best;
+    int n = 0;
+    for (int k = 0; k < ORIENTATION_MAX_COUNT; k++) {
+        /* quirk 2: best = -inf => -inf >= -inf is true for all 4 lanes */
+        if (yval[idx[k]] >= yref) {
+            float chosen = refined[idx[k]];
+            if (chosen >= ORI_NBINS) chosen -= ORI_NBINS;
+            e->ori[n++] = fmaf(F_PI2 * chosen, 1.0f / ORI_NBINS, -F_PI);
+        }
+    }
+    e->x = ie->x; e->y = ie->y; e->lpos = ie->lpos; e->sigma = ie->sigma; e->octave = o; e->num_ori = n;
+}
+
+/* -------------------------------------------------------------- descriptors */
+
+static float fma_ru(float a, float b, float c)
+{   /* __fmaf_ru: exact under FE_UPWARD (double product is exact) */
+    volatile double p = (double)a * (double)b;
+    volatile double s = p + (double)c;
+    volatile float r = (float)s;
+    return r;
+}
+static float fmul_ru(float a, float b)
+{
+    volatile double p = (double)a * (double)b;
+    volatile float r = (float)p;
+    return r;
+}
+
+/* s_desc_loop.cu:19-139 ext_desc_loop_sub: 16 cells x 32 lanes, per-lane
+ * partial sums, shuffle-down tree 16,8,4,2,1. */
+static void descriptor_one(const orc_ctx* c, const ext_t* e, float ang, float* feat)
+{
+    const int o = e->octave;
+    const int W = c->W[o], H = c->H[o];
+    const int lvl = clampi(e->lpos, 0, c->nlev - 1);
+    const float* pl = c->gauss[o] + (size_t)W * H * lvl;
+    const float x = e->x, y = e->y, sig = e->sigma;
+    const float SBP = fabsf(DESC_MAGNIFY * sig);
+    memset(feat, 0, 128 * sizeof(float));
+    if (SBP == 0.0f) return;
+    const float cos_t = cosf(ang), sin_t = sinf(ang);   /* __sincosf */
+    const float csbp = cos_t * SBP, ssbp = sin_t * SBP;
+    const float crsbp = cos_t / SBP, srsbp = sin_t / SBP;
+    const float M_4RPI = 4.0f / F_PI;
+    for (int iy = 0; iy < 4; iy++)
+        for (int ix = 0; ix < 4; ix++) {
+            const float ox = (float)ix - 1.5f, oy = (float)iy - 1.5f;
+            const float ptx = fmaf(csbp, ox, fmaf(-ssbp, oy, x));
+            const float pty = fmaf(csbp, oy, fmaf(ssbp, ox, y));
+            const float bsz = fabsf(csbp) + fabsf(ssbp);
+            int xmin = (int)floorf(ptx - bsz); if (xmin < 1) xmin = 1;
+            int ymin = (int)floorf(pty - bsz); if (ymin < 1) ymin = 1;
+            int xmax = (int)floorf(ptx + bsz); if (xmax > W - 2) xmax = W - 2;
+            int ymax = (int)floorf(pty + bsz); if (ymax > H - 2) ymax = H - 2;
+            const int wx = xmax - xmin + 1, hy = ymax - ymin + 1;
+            const int loops = wx * hy;
+            float lane[32][9];
+            memset(lane, 0, sizeof(lane));
+            if (wx > 0 && hy > 0) {
+                fesetround(FE_UPWARD);
+                for (int i = 0; i < loops; i++) {
+                    float* dpt = lane[i & 31];
+                    const int ii = i / wx + ymin, jj = i % wx + xmin;
+                    fesetround(FE_TONEAREST);
+                    const float ddx = (float)jj - ptx, ddy = (float)ii - pty;
+                    const float nx = fmaf(crsbp, ddx, srsbp * ddy);
+                    const float ny = fmaf(crsbp, ddy, -srsbp * ddx);
+                    const float nnx = fabsf(nx), nny = fabsf(ny);
+                    if (nnx < 1.0f && nny < 1.0f) {
+                        float mod, th;
+                        get_gradiant(&mod, &th, jj, ii, pl, W, H);
+                        const float dnx = nx + ox, dny = ny + oy;
+                        const float ww = expf(-((dnx * dnx + dny * dny) * 0.125f));   /* __expf */
+                        const float wgt = ww * (1.0f - nnx) * (1.0f - nny) * mod;
+                        th -= ang;
+                        th += (th < 0.0f ? F_PI2 : 0.0f);
+                        th -= (th >= F_PI2 ? F_PI2 : 0.0f);
+                        fesetround(FE_UPWARD);
+                        const float tth = fmul_ru(th, M_4RPI);
+                        fesetround(FE_TONEAREST);
+                        const int fo0 = (int)floorf(tth);
+                        const float do0 = tth - (float)fo0;
+                        const float wgt1 = 1.0f - do0, wgt2 = do0;
+                        const int fo = fo0 % 8;
+                        fesetround(FE_UPWARD);
+                        dpt[fo] = fma_ru(wgt1, wgt, dpt[fo]);
+                        dpt[fo + 1] = fma_ru(wgt2, wgt, dpt[fo + 1]);
+                    }
+                    fesetround(FE_UPWARD);
+                }
+                fesetround(FE_TONEAREST);
+            }
+            for (int l = 0; l < 32; l++) lane[l][0] += lane[l][8];
+            for (int b = 0; b < 8; b++) {
+                float vv[32];
+                for (int l = 0; l < 32; l++) vv[l] = lane[l][b];
+                for (int d = 16; d >= 1; d >>= 1)
+                    for (int l = 0; l < 32; l++) vv[l] += (l + d < 32) ? vv[l + d] : vv[l]; /* shfl_down keeps own value when out of range */
+                feat[((iy << 2) + ix) * 8 + b] = vv[0];
+            }
+        }
+}
+
+/* s_desc_norm_rs.h:41-77 and s_desc_norm_l2.h:46-135: lane k holds floats 4k..4k+3 */
+static float tree32(float* v)
+{
+    for (int d = 16; d >= 1; d >>= 1)
+        for (int l = 0; l < 32; l++) v[l] += (l + d < 32) ? v[l + d] : v[l];
+    return v[0];
+}
+static void normalize_desc(const orc_ctx* c, float* f)
+{
+    float v[32];
+    const int nm = c->cfg.norm_multi;
+    if (c->cfg.norm_mode == ORC_NORM_ROOTSIFT) {
+        for (int l = 0; l < 32; l++) v[l] = f[4 * l] + f[4 * l + 1] + f[4 * l + 2] + f[4 * l + 3];
+        const float sum = tree32(v);
+        for (int i = 0; i < 128; i++) f[i] = scalbnf(sqrtf(f[i] / sum), nm);
+    } else {
+        for (int l = 0; l < 32; l++)
+            v[l] = fmaf(f[4*l+3], f[4*l+3], fmaf(f[4*l+2], f[4*l+2], fmaf(f[4*l+1], f[4*l+1], f[4*l] * f[4*l])));
+        float norm = sqrtf(tree32(v));
+        for (int i = 0; i < 128; i++) f[i] = fminf(f[i], 0.2f * norm);
+        for (int l = 0; l < 32; l++)
+            v[l] = fmaf(f[4*l+3], f[4*l+3], fmaf(f[4*l+2], f[4*l+2], fmaf(f[4*l+1], f[4*l+1], f[4*l] * f[4*l])));
+        norm = scalbnf(1.0f / sqrtf(tree32(v)), nm);
+        for (int i = 0; i < 128; i++) f[i] = f[i] * norm;
+    }
+}
+
+/* ---------------------------------------------------------------- pipeline */
+
+orc_ctx* orc_create(const orc_config* cfg, int w, int h)
+{
+    orc_ctx* c = (orc_ctx*)calloc(1, sizeof(orc_ctx));
+    c->cfg = *cfg;
+    if (c->cfg.levels < 2) c->cfg.levels = 2;
+    if (orc_compute_tables(&c->cfg, &c->tab) != 0) { free(c); return NULL; }
+    c->w = w; c->h = h;
+    c->noct = orc_geometry(&c->cfg, w, h, c->W, c->H);
+    c->nlev = c->cfg.levels + 3;
+    for (int o = 0; o < c->noct; o++) {
+        const size_t P = (size_t)c->W[o] * c->H[o];
+        c->gauss[o] = (float*)malloc(P * c->nlev * sizeof(float));
+        c->dog[o] = (float*)malloc(P * (c->nlev - 1) * sizeof(float));
+    }
+    return c;
+}
+
+void orc_destroy(orc_ctx* c)
+{
+    if (!c) return;
+    for (int o = 0; o < c->noct; o++) { free(c->gauss[o]); free(c->dog[o]); }
+    free(c->iext); free(c->ext); free(c->desc); free(c);
+}
+
+int orc_run_u8(orc_ctx* c, const uint8_t* img, int stages)
+{
+    if (stages & 1) build_pyramid(c, img);
+    if (stages & 2) find_extrema(c);
+    if (stages & 4) {
+        free(c->ext);
+        c->ext = (ext_t*)calloc(c->n_iext ? c->n_iext : 1, sizeof(ext_t));
+        c->n_ext = c->n_iext;
+        #pragma omp parallel for schedule(dynamic, 16)
+        for (int i = 0; i < c->n_iext; i++) orientation_one(c, &c->iext[i], &c->ext[i]);
+        int total = 0;
+        for (int i = 0; i < c->n_ext; i++) { c->ext[i].idx_ori = total; total += c->ext[i].num_ori; }
+        c->n_desc = total;
+    }
+    if (stages & 8) {
+        free(c->desc);
+        c->desc = (float*)calloc((size_t)(c->n_desc ? c->n_desc : 1) * 128, sizeof(float));
+        #pragma omp parallel for schedule(dynamic, 8)
+        for (int i = 0; i < c->n_ext; i++)
+            for (int k = 0; k < c->ext[i].num_ori; k++) {
+                float* f = c->desc + (size_t)(c->ext[i].idx_ori + k) * 128;
+                descriptor_one(c, &c->ext[i], c->ext[i].ori[k], f);
+                normalize_desc(c, f);
+            }
+    }
+    return 0;
+}
+
+int orc_num_octaves(const orc_ctx* c) { return c->noct; }
+int orc_octave_dims(const orc_ctx* c, int o, int32_t* W, int32_t* H)
+{
+    if (o < 0 || o >= c->noct) return -1;
+    *W = c->W[o]; *H = c->H[o]; return 0;
+}
+const float* orc_gauss_plane(const orc_ctx* c, int o, int l)
+{
+    if (o < 0 || o >= c->noct || l < 0 || l >= c->nlev) return NULL;
+    return c->gauss[o] + (size_t)c->W[o] * c->H[o] * l;
+}
+const float* orc_dog_plane(const orc_ctx* c, int o, int l)
+{
+    if (o < 0 || o >= c->noct || l < 0 || l >= c->nlev - 1) return NULL;
+    return c->dog[o] + (size_t)c->W[o] * c->H[o] * l;
+}
+const orc_tables* orc_get_tables(const orc_ctx* c) { return &c->tab; }
+int orc_num_extrema(const orc_ctx* c) { return c->n_iext; }
+int orc_get_extrema(const orc_ctx* c, float* out5)
+{
+    for (int i = 0; i < c->n_iext; i++) {
+        out5[5 * i + 0] = c->iext[i].x; out5[5 * i + 1] = c->iext[i].y; out5[5 * i + 2] = c->iext[i].sigma;
+        out5[5 * i + 3] = (float)c->iext[i].lpos; out5[5 * i + 4] = (float)c->iext[i].octave;
+    }
+    return c->n_iext;
+}
+int orc_counts(const orc_ctx* c, int32_t* nf, int32_t* nd) { *nf = c->n_ext; *nd = c->n_desc; return 0; }
+
+/* sift_pyramid.cu:250-280 prep_features (up_fac is an int kernel parameter) */
+int orc_download(const orc_ctx* c, orc_feature* feat, float* desc128)
+{
+    const int up_fac = (int)c->cfg.upscale;
+    for (int i = 0; i < c->n_ext; i++) {
+        const ext_t* e = &c->ext[i];
+        const float s = powf(2.0f, (float)(e->octave - up_fac));
+        orc_feature* f = &feat[i];
+        memset(f, 0, sizeof(*f));
+        f->debug_octave = e->octave;
+        f->xpos = e->x * s; f->ypos = e->y * s; f->sigma = e->sigma * s;
+        f->num_ori = e->num_ori;
+        for (int k = 0; k < 4; k++) {
+            f->orientation[k] = k < e->num_ori ? e->ori[k] : 0.0f;
+            f->desc_idx[k] = k < e->num_ori ? e->idx_ori + k : -1;
+        }
+    }
+    if (desc128 && c->desc) memcpy(desc128, c->desc, (size_t)c->n_desc * 128 * sizeof(float));
+    return 0;
+}
