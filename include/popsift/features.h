@@ -1,0 +1,91 @@
+// Result containers of the drop-in (reference src/popsift/features.h:23-122,
+// src/popsift/sift_extremum.h:69-72).  Byte layouts are the reference's: Descriptor = 128 floats,
+// Feature = 72 bytes with host pointers into the owning FeaturesHost's descriptor array.
+#pragma once
+
+#include <iostream>
+
+#define ORIENTATION_MAX_COUNT 4
+
+namespace popsift {
+
+struct Descriptor
+{
+    float features[128];   // index (iy*4+ix)*8 + bin
+};
+
+struct Feature
+{
+    int         debug_octave;
+    float       xpos;
+    float       ypos;
+    float       sigma;
+    int         num_ori;
+    float       orientation[ORIENTATION_MAX_COUNT];
+    Descriptor* desc[ORIENTATION_MAX_COUNT];
+
+    void print(std::ostream& ostr, bool write_as_uchar) const;
+};
+
+std::ostream& operator<<(std::ostream& ostr, const Feature& feature);
+
+class FeaturesBase
+{
+    int _num_ext;
+    int _num_ori;
+
+public:
+    FeaturesBase();
+    virtual ~FeaturesBase();
+
+    int  size() const { return _num_ext; }
+    int  getFeatureCount() const { return _num_ext; }
+    int  getDescriptorCount() const { return _num_ori; }
+    void setFeatureCount(int n) { _num_ext = n; }
+    void setDescriptorCount(int n) { _num_ori = n; }
+};
+
+class FeaturesHost : public FeaturesBase
+{
+    Feature*    _ext;
+    Descriptor* _ori;
+
+public:
+    FeaturesHost();
+    FeaturesHost(int num_ext, int num_ori);
+    ~FeaturesHost() override;
+
+    typedef Feature*       F_iterator;
+    typedef const Feature* F_const_iterator;
+
+    F_iterator       begin() { return _ext; }
+    F_const_iterator begin() const { return _ext; }
+    F_iterator       end() { return _ext + size(); }
+    F_const_iterator end() const { return _ext + size(); }
+
+    void reset(int num_ext, int num_ori);
+    void pin();     // no-op here: results arrive through the library's own pinned staging
+    void unpin();
+
+    Feature*    getFeatures() { return _ext; }
+    Descriptor* getDescriptors() { return _ori; }
+
+    void print(std::ostream& ostr, bool write_as_uchar) const;
+};
+
+using Features = FeaturesHost;
+
+std::ostream& operator<<(std::ostream& ostr, const FeaturesHost& feature);
+
+/// Device-resident results (Config::MatchingMode).  Not part of this round's hot path
+/// (SURVEY.md 8f rank 1): the type exists so that callers compile; getDev() reports an error.
+class FeaturesDev : public FeaturesBase
+{
+public:
+    FeaturesDev() = default;
+    Feature*    getFeatures() { return nullptr; }
+    Descriptor* getDescriptors() { return nullptr; }
+    int*        getReverseMap() { return nullptr; }
+};
+
+} // namespace popsift

@@ -1,0 +1,264 @@
+// PopSift / SiftJob -- the reference's job pipeline (reference src/popsift/popsift.cpp:25-503)
+// re-designed for many images in flight:
+//
+//   caller thread --enqueue--> job queue --> ONE worker thread per PopSift:
+//        slot = next in round robin; if that slot still holds a job: finish it
+//        (ps_counts + ps_download -> promise); ps_submit_* the new job (asynchronous: H2D + all
+//        kernels on the slot's stream); when the queue runs dry, finish the remaining slots in order.
+//
+// Jobs therefore complete in FIFO order like the reference's, but `slots` images overlap on the
+// GPU (upload of n+1 and kernels of n+1 run while the results of n are downloaded), where the
+// reference has one image on the device at a time and >= 8 host synchronisations per image.
+// The device context is created on the first image (or re-created when a larger image arrives),
+// and the octave count is fixed by the first image exactly like the reference
+// (popsift.cpp:118-122 writes it back into the stored Config).
+#include "popsift/popsift.h"
+#include "popsift_b200.h"
+
+#include <algorithm>
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <iostream>
+#include <mutex>
+#include <sstream>
+#include <thread>
+#include <vector>
+
+using popsift::Config;
+
+// ---------------------------------------------------------------- SiftJob
+
+SiftJob::SiftJob(int w, int h, const unsigned char* imageData) : _w(w), _h(h), _isFloat(false)
+{
+    _f = _p.get_future();
+    const size_t n = (size_t)w * h;
+    _imageData = static_cast<unsigned char*>(std::malloc(n ? n : 1));
+    if (!_imageData) throw std::runtime_error("Memory limitation\nE    Failed to allocate memory for SiftJob");
+    std::memcpy(_imageData, imageData, n);
+}
+
+SiftJob::SiftJob(int w, int h, const float* imageData) : _w(w), _h(h), _isFloat(true)
+{
+    _f = _p.get_future();
+    const size_t n = (size_t)w * h * sizeof(float);
+    _imageData = static_cast<unsigned char*>(std::malloc(n ? n : 1));
+    if (!_imageData) throw std::runtime_error("Memory limitation\nE    Failed to allocate memory for SiftJob");
+    std::memcpy(_imageData, imageData, n);
+}
+
+SiftJob::~SiftJob() { std::free(_imageData); }
+
+void SiftJob::setFeatures(popsift::FeaturesBase* f) { _p.set_value(f); }
+void SiftJob::setError(std::exception_ptr ptr) { _err = ptr; }
+
+popsift::FeaturesBase* SiftJob::getBase()
+{
+    popsift::FeaturesBase* f = _f.get();
+    if (_err) std::rethrow_exception(_err);
+    return f;
+}
+popsift::FeaturesHost* SiftJob::getHost() { return dynamic_cast<popsift::FeaturesHost*>(getBase()); }
+popsift::FeaturesHost* SiftJob::get() { return getHost(); }
+popsift::FeaturesDev* SiftJob::getDev()
+{
+    getBase();
+    throw std::runtime_error("popsift_b200: device-resident results (Config::MatchingMode) are not implemented yet");
+}
+
+// ---------------------------------------------------------------- PopSift::Pipe
+
+struct PopSift::Pipe
+{
+    std::mutex                mu;
+    std::condition_variable   cv;
+    std::deque<SiftJob*>      queue;
+    bool                      stop = false;
+    std::thread               worker;
+
+    ps_ctx*                   ctx = nullptr;
+    int                       ctx_w = 0, ctx_h = 0;
+    int                       slots = 4;
+    std::vector<SiftJob*>     in_slot;
+    int                       next_slot = 0;
+    bool                      octaves_fixed = false;
+};
+
+namespace {
+
+void fail_job(SiftJob* job, const std::string& msg)
+{
+    job->setError(std::make_exception_ptr(std::runtime_error(msg)));
+    job->setFeatures(nullptr);
+}
+
+} // namespace
+
+PopSift::PopSift(ImageMode imode, int device) : _pipe(new Pipe), _image_mode(imode), _device(device)
+{
+    Pipe* p = _pipe.get();
+    p->worker = std::thread([this, p] {
+        auto finish = [&](int s) {
+            SiftJob* job = p->in_slot[s];
+            if (!job) return;
+            p->in_slot[s] = nullptr;
+            int32_t nf = 0, nd = 0;
+            int rc = ps_counts(p->ctx, s, &nf, &nd);
+            if (rc != PS_OK && rc != PS_ERR_OVERFLOW) { fail_job(job, ps_last_error(p->ctx)); return; }
+            if (rc == PS_ERR_OVERFLOW) std::cerr << "popsift_b200 warning: " << ps_last_error(p->ctx) << std::endl;
+            popsift::FeaturesHost* fh = nullptr;
+            try {
+                fh = new popsift::FeaturesHost(nf, nd);
+                rc = ps_download(p->ctx, s, reinterpret_cast<ps_feature*>(fh->getFeatures()),
+                                 reinterpret_cast<ps_descriptor*>(fh->getDescriptors()));
+                if (rc != PS_OK) { delete fh; fail_job(job, ps_last_error(p->ctx)); return; }
+            } catch (const std::exception& e) { delete fh; fail_job(job, e.what()); return; }
+            job->setFeatures(fh);
+        };
+        auto finish_all = [&] {
+            if (!p->ctx) return;
+            for (int i = 0; i < (int)p->in_slot.size(); ++i) finish((p->next_slot + i) % (int)p->in_slot.size());
+        };
+        for (;;) {
+            SiftJob* job = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(p->mu);
+                if (p->queue.empty() && !p->stop) {
+                    // nothing to submit: drain what is in flight, then sleep
+                    lk.unlock();
+                    finish_all();
+                    lk.lock();
+                    p->cv.wait(lk, [&] { return !p->queue.empty() || p->stop; });
+                }
+                if (p->queue.empty() && p->stop) break;
+                job = p->queue.front();
+                p->queue.pop_front();
+            }
+            const int w = job->width(), h = job->height();
+            if (!p->ctx || w > p->ctx_w || h > p->ctx_h) {
+                finish_all();
+                if (p->ctx) { ps_destroy(p->ctx); p->ctx = nullptr; }
+                if (!p->octaves_fixed) {
+                    // first image fixes the octave count (reference popsift.cpp:118-122)
+                    ps_config c; _config.toC(c);
+                    if (c.octaves < 0) { const int n = ps_geometry(&c, w, h, nullptr, nullptr); if (n > 0) _config.octaves = n; }
+                    p->octaves_fixed = true;
+                }
+                ps_config c; _config.toC(c);
+                p->ctx_w = std::max(w, p->ctx_w); p->ctx_h = std::max(h, p->ctx_h);
+                p->ctx = ps_create(_device, &c, p->ctx_w, p->ctx_h, p->slots);
+                p->in_slot.assign(p->slots, nullptr);
+                p->next_slot = 0;
+                if (!p->ctx) { fail_job(job, ps_last_error(nullptr)); p->ctx_w = p->ctx_h = 0; continue; }
+            }
+            const int s = p->next_slot;
+            finish(s);
+            const int rc = job->isFloat() ? ps_submit_f32(p->ctx, s, reinterpret_cast<const float*>(job->pixels()), w, h)
+                                          : ps_submit_u8(p->ctx, s, job->pixels(), w, h);
+            if (rc != PS_OK) { fail_job(job, ps_last_error(p->ctx)); continue; }
+            p->in_slot[s] = job;
+            p->next_slot = (s + 1) % p->slots;
+        }
+        finish_all();
+        if (p->ctx) { ps_destroy(p->ctx); p->ctx = nullptr; }
+    });
+}
+
+PopSift::PopSift(const Config& config, Config::ProcessingMode mode, ImageMode imode, int device)
+    : PopSift(imode, device)
+{
+    if (mode != Config::ExtractingMode)
+        std::cerr << "popsift_b200 warning: MatchingMode is not implemented; running in ExtractingMode" << std::endl;
+    configure(config);
+}
+
+PopSift::~PopSift()
+{
+    if (_isInit) uninit();
+}
+
+bool PopSift::configure(const Config& config, bool /*force*/)
+{
+    Pipe* p = _pipe.get();
+    std::lock_guard<std::mutex> lk(p->mu);
+    if (p->ctx != nullptr) return false;     // like the reference: not after the pyramid exists
+    _config = config;
+    _config.levels = std::max(2, config.levels);
+    return true;
+}
+
+void PopSift::setSlots(int n)
+{
+    Pipe* p = _pipe.get();
+    std::lock_guard<std::mutex> lk(p->mu);
+    if (p->ctx == nullptr && n >= 1 && n <= 64) p->slots = n;
+}
+
+void PopSift::uninit()
+{
+    if (!_isInit) {
+        std::cerr << "[warning] Attempt to release resources from an uninitialized instance" << std::endl;
+        return;
+    }
+    Pipe* p = _pipe.get();
+    {
+        std::lock_guard<std::mutex> lk(p->mu);
+        p->stop = true;
+    }
+    p->cv.notify_all();
+    if (p->worker.joinable()) p->worker.join();
+    _isInit = false;
+}
+
+PopSift::AllocTest PopSift::testTextureFit(int width, int height)
+{
+    // linear HBM planes: no texture or surface limits; only absurd sizes are refused
+    if (width < 1 || height < 1 || (long long)width * height > (1LL << 30)) return ImageExceedsLinearTextureLimit;
+    return Ok;
+}
+
+std::string PopSift::testTextureFitErrorString(AllocTest err, int width, int height)
+{
+    std::ostringstream o;
+    switch (err) {
+        case Ok: o << "?    No error." << std::endl; break;
+        case ImageExceedsLinearTextureLimit:
+            o << "E    Cannot load unscaled image. " << std::endl
+              << "E    Size (" << width << "," << height << ") is not supported." << std::endl; break;
+        default: o << "E    Programming error, please report." << std::endl; break;
+    }
+    return o.str();
+}
+
+SiftJob* PopSift::enqueue(int w, int h, const unsigned char* imageData)
+{
+    if (_image_mode != ByteImages)
+        throw std::runtime_error("Image mode error\nE    Cannot load byte images into a PopSift pipeline configured for float images");
+    const AllocTest a = testTextureFit(w, h);
+    if (a != Ok) {
+        std::cerr << __FILE__ << ":" << __LINE__ << " Image too large" << std::endl << testTextureFitErrorString(a, w, h);
+        return nullptr;
+    }
+    SiftJob* job = new SiftJob(w, h, imageData);
+    Pipe* p = _pipe.get();
+    { std::lock_guard<std::mutex> lk(p->mu); p->queue.push_back(job); }
+    p->cv.notify_all();
+    return job;
+}
+
+SiftJob* PopSift::enqueue(int w, int h, const float* imageData)
+{
+    if (_image_mode != FloatImages)
+        throw std::runtime_error("Image mode error\nE    Cannot load float images into a PopSift pipeline configured for byte images");
+    const AllocTest a = testTextureFit(w, h);
+    if (a != Ok) {
+        std::cerr << __FILE__ << ":" << __LINE__ << " Image too large" << std::endl << testTextureFitErrorString(a, w, h);
+        return nullptr;
+    }
+    SiftJob* job = new SiftJob(w, h, imageData);
+    Pipe* p = _pipe.get();
+    { std::lock_guard<std::mutex> lk(p->mu); p->queue.push_back(job); }
+    p->cv.notify_all();
+    return job;
+}

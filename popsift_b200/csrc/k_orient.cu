@@ -1,0 +1,253 @@
+// Stage 3a -- dominant orientations, hand-written for sm_100a.
+//
+// Replaces ori_par + ori_prefix_sum (reference src/popsift/s_orientation.cu:75-362,
+// s_gradiant.h:55-69, common/warp_bitonic_sort.h, common/excl_blk_prefix_sum.h).
+// Differences in structure (not in arithmetic):
+//   * no host round trip: the reference reads the extrema counters back to size its grid
+//     (s_orientation.cu:364-441); here a fixed grid of warps walks the device-side counters;
+//   * all octaves in one launch, 4 keypoints (warps) per CTA instead of 1;
+//   * lane-private histogram bins in shared memory, reduced in lane order -> deterministic
+//     (the reference's shared-memory atomicAdd order is not);
+//   * top-4 selection by four warp arg-max rounds instead of a 64-wide bitonic sort.
+// Per-sample math is the reference's: hypotf/atan2f gradients of the data plane lpos,
+// weight = grad*expf(int(sq_dist)*__fdividef(-0.5, sigw^2)), bin = round(36*(theta+pi)/2pi),
+// 3x(box3, box3) smoothing, parabola refinement, peaks >= 0.8*best, theta = fma(2pi*bin, 1/36, -pi).
+#include "ps_internal.h"
+
+namespace psb {
+
+namespace {
+
+constexpr int WARPS = 4;
+constexpr int HSTRIDE = 33;     // skewed so that the lane-order reduction is conflict-free
+__device__ const float kPi  = 3.14159265358979323846f;
+__device__ const float kPi2 = 2.0f * 3.14159265358979323846f;
+
+__device__ __forceinline__ float plane_at(const float* pl, int w, int h, int pitch, int x, int y)
+{
+    x = min(max(x, 0), w - 1);
+    y = min(max(y, 0), h - 1);
+    return __ldg(pl + (size_t)y * pitch + x);
+}
+
+// total number of extrema and the octave prefix, from the raw per-octave counters
+__device__ __forceinline__ int octave_prefix(const Counters* ct, const Consts& k, int num_octaves, int* ps /*[kMaxOctaves+1]*/)
+{
+    int total = 0;
+    for (int o = 0; o < num_octaves; ++o) {
+        ps[o] = total;
+        int c = min(ct->ext_ct[o], k.max_extrema);
+        if (total + c > k.ext_capacity) c = k.ext_capacity - total;
+        total += c;
+    }
+    ps[num_octaves] = total;
+    return total;
+}
+
+__global__ void __launch_bounds__(WARPS * 32)
+orientation_kernel(PyramidView pyr, Consts k, const InitialExtremum* __restrict__ iext,
+                   ps_extremum* __restrict__ ext, Counters* ct)
+{
+    __shared__ float hist[WARPS][kOriBins * HSTRIDE];
+    __shared__ float sm_a[WARPS][kOriBins];
+    __shared__ float sm_b[WARPS][kOriBins];
+    __shared__ int   ps[kMaxOctaves + 1];
+
+    if (threadIdx.x == 0) octave_prefix(ct, k, pyr.num_octaves, ps);
+    __syncthreads();
+    const int total = ps[pyr.num_octaves];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    float* H = hist[warp];
+    float* A = sm_a[warp];
+    float* B = sm_b[warp];
+
+    for (int item = blockIdx.x * WARPS + warp; item < total; item += gridDim.x * WARPS) {
+        int o = 0;
+        while (o + 1 < pyr.num_octaves && item >= ps[o + 1]) ++o;
+        const InitialExtremum ie = iext[(size_t)o * k.max_extrema + (item - ps[o])];
+        const OctaveView& ov = pyr.oct[o];
+        const int w = ov.w, h = ov.h;
+        const int lvl = min(max(ie.lpos, 0), pyr.levels + 2);
+        const float* pl = ov.gauss + (size_t)lvl * ov.plane;
+
+        for (int b = 0; b < kOriBins; ++b) H[b * HSTRIDE + lane] = 0.0f;
+
+        const float x = ie.xpos, y = ie.ypos, sig = ie.sigma;
+        const float sigw = __fmul_rn(1.5f, sig);
+        const int rad = (int)roundf(__fmul_rn(3.0f, sigw));
+        const float factor = __fdividef(-0.5f, __fmul_rn(sigw, sigw));
+        const int sq_thres = rad * rad;
+        const int xmin = max(1, (int)roundf(x) - rad);
+        const int xmax = min(w - 2, (int)roundf(x) + rad);
+        const int ymin = max(1, (int)roundf(y) - rad);
+        const int ymax = min(h - 2, (int)roundf(y) + rad);
+        const int wx = xmax - xmin + 1;
+        const int hy = ymax - ymin + 1;
+        const int loops = (wx > 0 && hy > 0) ? wx * hy : 0;
+
+        for (int i = lane; i < loops; i += 32) {
+            const int yy = i / wx + ymin;
+            const int xx = i - (i / wx) * wx + xmin;
+            const float gdx = __fsub_rn(plane_at(pl, w, h, ov.pitch, xx + 1, yy), plane_at(pl, w, h, ov.pitch, xx - 1, yy));
+            const float gdy = __fsub_rn(plane_at(pl, w, h, ov.pitch, xx, yy + 1), plane_at(pl, w, h, ov.pitch, xx, yy - 1));
+            const float grad = hypotf(gdx, gdy);
+            const float theta = atan2f(gdy, gdx);
+            const float ddx = __fsub_rn((float)xx, x), ddy = __fsub_rn((float)yy, y);
+            const int sq_dist = (int)__fmaf_rn(ddx, ddx, __fmul_rn(ddy, ddy));
+            if (sq_dist <= sq_thres) {
+                const float weight = __fmul_rn(grad, expf(__fmul_rn((float)sq_dist, factor)));
+                int bidx = (int)roundf(__fdividef(__fmul_rn((float)kOriBins, __fadd_rn(theta, kPi)), kPi2));
+                if (bidx == kOriBins) bidx = 0;
+                if (bidx >= 0 && bidx < kOriBins) H[bidx * HSTRIDE + lane] += weight;
+            }
+        }
+        __syncwarp();
+        // reduce the 32 lane-private copies of each bin, lanes in order
+        for (int b = lane; b < kOriBins; b += 32) {
+            float s = 0.0f;
+            for (int l = 0; l < 32; ++l) s = __fadd_rn(s, H[b * HSTRIDE + l]);
+            A[b] = s;
+        }
+        __syncwarp();
+        // 3 x (box3 ; box3), circular over 36 bins (reference s_orientation.cu:58-68,166-174)
+        for (int it = 0; it < 3; ++it) {
+            for (int b = lane; b < kOriBins; b += 32) {
+                const int pv = b == 0 ? kOriBins - 1 : b - 1, nx = b == kOriBins - 1 ? 0 : b + 1;
+                B[b] = __fdiv_rn(__fadd_rn(__fadd_rn(A[pv], A[b]), A[nx]), 3.0f);
+            }
+            __syncwarp();
+            for (int b = lane; b < kOriBins; b += 32) {
+                const int pv = b == 0 ? kOriBins - 1 : b - 1, nx = b == kOriBins - 1 ? 0 : b + 1;
+                A[b] = __fdiv_rn(__fadd_rn(__fadd_rn(B[pv], B[b]), B[nx]), 3.0f);
+            }
+            __syncwarp();
+        }
+        // peaks + parabola refinement; lane holds bins `lane` and `lane+32`
+        float yv[2], ra[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int b = lane + 32 * s;
+            yv[s] = -INFINITY; ra[s] = -1.0f;
+            if (b < kOriBins) {
+                const int pv = b == 0 ? kOriBins - 1 : b - 1, nx = b == kOriBins - 1 ? 0 : b + 1;
+                const float hp = A[pv], hc = A[b], hn = A[nx];
+                bool pred = hc > fmaxf(hp, hn);
+                const float num = pred ? 3.0f * hp - 4.0f * hc + 1.0f * hn : 0.0f;
+                const float den = pred ? 2.0f * (hp - 2.0f * hc + hn) : 1.0f;
+                const float newbin = __fdividef(num, den);
+                pred = pred && newbin >= 0.0f && newbin <= 2.0f;
+                if (pred) { ra[s] = (float)pv + newbin; yv[s] = -(num * num) / (4.0f * den) + hp; }
+            }
+        }
+        // four arg-max rounds (descending yval; ties -> lower bin)
+        float best_y[PS_MAX_ORI], best_r[PS_MAX_ORI];
+#pragma unroll
+        for (int r = 0; r < PS_MAX_ORI; ++r) {
+            float cy; int cb;
+            if (yv[0] >= yv[1] || !(yv[1] == yv[1])) { cy = yv[0]; cb = lane; } else { cy = yv[1]; cb = lane + 32; }
+            float wy = cy; int wb = cb;
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+                const float oy = __shfl_xor_sync(0xffffffffu, wy, d);
+                const int ob = __shfl_xor_sync(0xffffffffu, wb, d);
+                if (oy > wy || (oy == wy && ob < wb)) { wy = oy; wb = ob; }
+            }
+            // owner publishes its refined angle and retires the bin
+            const int owner = wb & 31, slot = wb >> 5;
+            const float rr = __shfl_sync(0xffffffffu, slot ? ra[1] : ra[0], owner);
+            best_y[r] = wy; best_r[r] = rr;
+            if (lane == owner) { if (slot) yv[1] = -INFINITY; else yv[0] = -INFINITY; }
+        }
+        const float yref = __fmul_rn(0.8f, best_y[0]);
+        if (lane == 0) {
+            ps_extremum e;
+            e.xpos = ie.xpos; e.ypos = ie.ypos; e.lpos = ie.lpos; e.sigma = ie.sigma;
+            e.octave = o; e.idx_ori = 0;
+            int n = 0;
+#pragma unroll
+            for (int r = 0; r < PS_MAX_ORI; ++r) {
+                e.orientation[r] = 0.0f;
+            }
+#pragma unroll
+            for (int r = 0; r < PS_MAX_ORI; ++r) {
+                // best_y[0] == -inf (no peak at all): -inf >= -inf holds for all four (reference quirk)
+                if (best_y[r] >= yref) {
+                    float chosen = best_r[r];
+                    if (chosen >= (float)kOriBins) chosen -= (float)kOriBins;
+                    e.orientation[n++] = __fmaf_rn(__fmul_rn(kPi2, chosen), 1.0f / kOriBins, -kPi);
+                }
+            }
+            e.num_ori = n;
+            ext[item] = e;
+        }
+        __syncwarp();
+    }
+}
+
+// Exclusive prefix sum of num_ori over all extrema (single CTA), reverse map, totals.
+__global__ void __launch_bounds__(1024)
+ori_prefix_kernel(int num_octaves, Consts k, ps_extremum* __restrict__ ext, int* __restrict__ feat_to_ext, Counters* ct)
+{
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    __shared__ int ps[kMaxOctaves + 1];
+    if (threadIdx.x == 0) { octave_prefix(ct, k, num_octaves, ps); carry = 0; }
+    __syncthreads();
+    const int total = ps[num_octaves];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    bool overflow = false;
+    for (int base = 0; base < total; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int n = i < total ? ext[i].num_ori : 0;
+        int v = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane >= d) v += t;
+        }
+        if (lane == 31) warp_sums[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            int s = warp_sums[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, s, d);
+                if (lane >= d) s += t;
+            }
+            warp_sums[lane] = s;
+        }
+        __syncthreads();
+        const int excl = carry + (warp ? warp_sums[warp - 1] : 0) + v - n;
+        if (i < total) {
+            int nn = n;
+            if (excl + nn > k.desc_capacity) { nn = max(0, k.desc_capacity - excl); overflow = true; ext[i].num_ori = nn; }
+            ext[i].idx_ori = min(excl, k.desc_capacity);
+            for (int r = 0; r < nn; ++r) feat_to_ext[excl + r] = i;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry += warp_sums[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        ct->ext_total = total;
+        ct->ori_total = min(carry, k.desc_capacity);
+        int raw = 0;
+        for (int o = 0; o < num_octaves; ++o) raw += min(ct->ext_ct[o], k.max_extrema);
+        if (raw > total) atomicOr(&ct->overflow, 1);
+    }
+    if (overflow) atomicOr(&ct->overflow, 2);
+}
+
+} // namespace
+
+int launch_orientation(const PyramidView& pyr, const Consts& k, const InitialExtremum* iext, ps_extremum* ext,
+                       int* feat_to_ext, Counters* ct, cudaStream_t st)
+{
+    // fixed grid: 148 SMs x 8 resident CTAs of 4 warps; warps stride over the device-side count
+    orientation_kernel<<<148 * 8, WARPS * 32, 0, st>>>(pyr, k, iext, ext, ct);
+    ori_prefix_kernel<<<1, 1024, 0, st>>>(pyr.num_octaves, k, ext, feat_to_ext, ct);
+    return 2;
+}
+
+} // namespace psb

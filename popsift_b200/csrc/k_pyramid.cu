@@ -1,0 +1,348 @@
+// Stage 1 -- Gaussian scale-space pyramid + DoG, hand-written for sm_100a.
+//
+// What the reference does with 13 launches per octave through textures and surfaces
+// (normalizedSource::horiz, absoluteSource::horiz/vert, get_by_2_pick_every_second, make_dog;
+// reference src/popsift/s_pyramid_build_ra.cu:17-55, s_pyramid_build_aa.cu:17-86,
+// s_pyramid_build.cu:50-92,547-586) is done here with ONE kernel per level on linear HBM planes:
+//   source tile (+halo, clamp-to-edge) -> shared memory -> row pass -> shared memory ->
+//   column pass in registers -> level l, DoG[l-1] = G[l] - G[l-1] and (for level L) the
+//   2:1 decimated level 0 of the next octave, all written from the same registers.
+//
+// Parity contract (tests/test_gpu_parity.py): every plane is BIT-IDENTICAL to the reference's.
+// That fixes the floating-point evaluation order, taken from the reference's sm_100 SASS:
+//   rows    (levels >= 1): acc = fma(C, g0, 0); for off = span-1..1: acc = fma(v(-off)+v(+off), g[off], acc)
+//   rows    (level 0)    : acc = 0; for off = span-1..1: acc = fma(v(-off)+v(+off), g[off], acc);
+//                          acc = fma(C, g0, acc); out = acc*255
+//   columns (all levels) : acc = 0; for off = span-1..1: acc = fma(v(-off), g[off], acc);
+//                          acc = fma(v(+off), g[off], acc); then acc = fma(C, g0, acc)
+// (the reference also adds the +/-span taps, whose weight is exactly 0).
+// All intrinsics are explicit (__fmaf_rn/__fadd_rn/__fmul_rn) so nvcc cannot re-associate.
+#include "ps_internal.h"
+
+namespace psb {
+
+namespace {
+
+constexpr int TW = 64;          // output tile width
+constexpr int TH = 32;          // output tile height
+constexpr int NT = 256;         // threads per CTA
+
+struct Taps { float g[PS_GAUSS_ALIGN]; };
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+// ---- row pass / column pass over shared-memory tiles ---------------------------------------
+
+// s  : source tile, (TH+2R) rows x SW floats, column c <-> image x = x0 - R + c
+// m  : row-filtered tile, (TH+2R) rows x TW floats
+template <int R, bool LEVEL0>
+__device__ __forceinline__ void row_pass(const float* __restrict__ s, float* __restrict__ m, int SW,
+                                         const Taps& t)
+{
+    constexpr int ROWS = TH + 2 * R;
+    for (int idx = threadIdx.x; idx < ROWS * TW; idx += NT) {
+        const int j = idx / TW;
+        const int i = idx - j * TW;
+        const float* p = s + j * SW + i + R;     // centre
+        float acc;
+        if (LEVEL0) {
+            acc = 0.0f;
+#pragma unroll
+            for (int off = R; off > 0; --off)
+                acc = __fmaf_rn(__fadd_rn(p[-off], p[off]), t.g[off], acc);
+            acc = __fmaf_rn(p[0], t.g[0], acc);
+            acc = __fmul_rn(acc, 255.0f);
+        } else {
+            acc = __fmaf_rn(p[0], t.g[0], 0.0f);
+#pragma unroll
+            for (int off = R; off > 0; --off)
+                acc = __fmaf_rn(__fadd_rn(p[-off], p[off]), t.g[off], acc);
+        }
+        m[j * TW + i] = acc;
+    }
+}
+
+template <int R>
+__device__ __forceinline__ float col_at(const float* __restrict__ m, int y, int x, const Taps& t)
+{
+    const float* p = m + (y + R) * TW + x;
+    float acc = 0.0f;
+#pragma unroll
+    for (int off = R; off > 0; --off) {
+        acc = __fmaf_rn(p[-off * TW], t.g[off], acc);
+        acc = __fmaf_rn(p[off * TW], t.g[off], acc);
+    }
+    return __fmaf_rn(p[0], t.g[0], acc);
+}
+
+// ---- level l >= 1 ---------------------------------------------------------------------------
+
+template <int R>
+__global__ void __launch_bounds__(NT)
+blur_level_kernel(const float* __restrict__ src, float* __restrict__ dst, float* __restrict__ dog,
+                  float* __restrict__ next0, int W, int H, int pitch, int next_pitch, Taps taps)
+{
+    extern __shared__ float smem[];
+    constexpr int SW = TW + 2 * R;
+    constexpr int ROWS = TH + 2 * R;
+    float* s = smem;                 // ROWS x SW
+    float* m = smem + ROWS * SW;     // ROWS x TW
+
+    const int x0 = blockIdx.x * TW;
+    const int y0 = blockIdx.y * TH;
+
+    for (int idx = threadIdx.x; idx < ROWS * SW; idx += NT) {
+        const int j = idx / SW;
+        const int i = idx - j * SW;
+        const int gx = clampi(x0 - R + i, 0, W - 1);
+        const int gy = clampi(y0 - R + j, 0, H - 1);
+        s[idx] = __ldg(src + (size_t)gy * pitch + gx);
+    }
+    __syncthreads();
+    row_pass<R, false>(s, m, SW, taps);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < TH * TW; idx += NT) {
+        const int y = idx / TW;
+        const int x = idx - y * TW;
+        const int gx = x0 + x, gy = y0 + y;
+        if (gx >= W || gy >= H) continue;
+        const float v = col_at<R>(m, y, x, taps);
+        const size_t o = (size_t)gy * pitch + gx;
+        dst[o] = v;
+        dog[o] = __fsub_rn(v, s[(y + R) * SW + x + R]);
+        if (next0 != nullptr && !((gx | gy) & 1))
+            next0[(size_t)(gy >> 1) * next_pitch + (gx >> 1)] = v;
+    }
+}
+
+// generic-radius fallback (any span up to 31): same arithmetic, run-time loops
+__global__ void __launch_bounds__(NT)
+blur_level_generic_kernel(const float* __restrict__ src, float* __restrict__ dst, float* __restrict__ dog,
+                          float* __restrict__ next0, int W, int H, int pitch, int next_pitch, Taps taps, int R)
+{
+    extern __shared__ float smem[];
+    const int SW = TW + 2 * R;
+    const int ROWS = TH + 2 * R;
+    float* s = smem;
+    float* m = smem + ROWS * SW;
+    const int x0 = blockIdx.x * TW;
+    const int y0 = blockIdx.y * TH;
+    for (int idx = threadIdx.x; idx < ROWS * SW; idx += NT) {
+        const int j = idx / SW;
+        const int i = idx - j * SW;
+        const int gx = clampi(x0 - R + i, 0, W - 1);
+        const int gy = clampi(y0 - R + j, 0, H - 1);
+        s[idx] = __ldg(src + (size_t)gy * pitch + gx);
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < ROWS * TW; idx += NT) {
+        const int j = idx / TW;
+        const int i = idx - j * TW;
+        const float* p = s + j * SW + i + R;
+        float acc = __fmaf_rn(p[0], taps.g[0], 0.0f);
+        for (int off = R; off > 0; --off)
+            acc = __fmaf_rn(__fadd_rn(p[-off], p[off]), taps.g[off], acc);
+        m[j * TW + i] = acc;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < TH * TW; idx += NT) {
+        const int y = idx / TW;
+        const int x = idx - y * TW;
+        const int gx = x0 + x, gy = y0 + y;
+        if (gx >= W || gy >= H) continue;
+        const float* p = m + (y + R) * TW + x;
+        float acc = 0.0f;
+        for (int off = R; off > 0; --off) {
+            acc = __fmaf_rn(p[-off * TW], taps.g[off], acc);
+            acc = __fmaf_rn(p[off * TW], taps.g[off], acc);
+        }
+        const float v = __fmaf_rn(p[0], taps.g[0], acc);
+        const size_t o = (size_t)gy * pitch + gx;
+        dst[o] = v;
+        dog[o] = __fsub_rn(v, s[(y + R) * SW + x + R]);
+        if (next0 != nullptr && !((gx | gy) & 1))
+            next0[(size_t)(gy >> 1) * next_pitch + (gx >> 1)] = v;
+    }
+}
+
+// ---- octave 0, level 0: straight from the input image ----------------------------------------
+//
+// The reference samples a normalized-coordinate, bilinear, clamp, u8->unorm-float texture at
+// ((X+shift)/W0 -/+ off/W0, (Y+shift)/H0).  What the B200 texture unit returns for that was
+// measured (oracle/texprobe.cu, tests/golden/texture_pairs.npz): texel coordinate rx*w-0.5 with the
+// fraction rounded to 1/256, texels widened to unorm16 (x257), integer 2x2 blend rounded half-up
+// to 16 bits, result (float)r16/65535.  virt_axis() + sample below restate exactly that.
+
+struct AxisTap { int i0, i1, a; };   // two source indices and the 8-bit fraction of the second
+
+__device__ __forceinline__ AxisTap virt_axis(int X, float shift, int N0, int n)
+{
+    float f = __fmul_rn(__fdiv_rn(__fadd_rn((float)X, shift), (float)N0), (float)n) - 0.5f;
+    f = fminf(fmaxf(f, -0.5f), (float)n - 0.5f);
+    const float fl = floorf(f);
+    int i = (int)fl;
+    int a = (int)floorf(__fmaf_rn(f - fl, 256.0f, 0.5f));
+    if (a == 256) { a = 0; i += 1; }
+    AxisTap t;
+    t.i0 = clampi(i, 0, n - 1);
+    t.i1 = clampi(i + 1, 0, n - 1);
+    t.a = a;
+    return t;
+}
+
+template <int R, typename PIX>
+__global__ void __launch_bounds__(NT)
+level0_kernel(const PIX* __restrict__ img, size_t img_pitch, int w, int h, float shift,
+              float* __restrict__ dst, int W, int H, int pitch, Taps dd, Taps inc0)
+{
+    extern __shared__ float smem[];
+    constexpr int SW = TW + 2 * R;
+    constexpr int ROWS = TH + 2 * R;
+    float* s = smem;                 // ROWS x SW : virtual up-scaled image (normalised floats)
+    float* m = smem + ROWS * SW;     // ROWS x TW
+    __shared__ AxisTap ax[SW];
+    __shared__ AxisTap ay[ROWS];
+
+    const int x0 = blockIdx.x * TW;
+    const int y0 = blockIdx.y * TH;
+    // rows/columns outside the octave clamp to the border pixel of the *virtual* image first
+    // (intermediate-plane clamp for rows; for columns the texture clamp is equivalent).
+    for (int i = threadIdx.x; i < SW; i += NT) ax[i] = virt_axis(x0 - R + i, shift, W, w);
+    for (int j = threadIdx.x; j < ROWS; j += NT) ay[j] = virt_axis(clampi(y0 - R + j, 0, H - 1), shift, H, h);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < ROWS * SW; idx += NT) {
+        const int j = idx / SW;
+        const int i = idx - j * SW;
+        const AxisTap tx = ax[i], ty = ay[j];
+        const PIX* r0 = img + (size_t)ty.i0 * img_pitch;
+        const PIX* r1 = img + (size_t)ty.i1 * img_pitch;
+        if (sizeof(PIX) == 1) {
+            const unsigned t00 = (unsigned)r0[tx.i0], t10 = (unsigned)r0[tx.i1];
+            const unsigned t01 = (unsigned)r1[tx.i0], t11 = (unsigned)r1[tx.i1];
+            const unsigned wx1 = tx.a, wx0 = 256u - wx1, wy1 = ty.a, wy0 = 256u - wy1;
+            const unsigned num = wx0 * wy0 * t00 + wx1 * wy0 * t10 + wx0 * wy1 * t01 + wx1 * wy1 * t11;
+            const unsigned r16 = (num * 257u + 32768u) >> 16;
+            s[idx] = __fdiv_rn((float)r16, 65535.0f);
+        } else {
+            // float images: fp32 blend with 8-bit weights (texture arithmetic not probed)
+            const float fx = (float)tx.a * (1.0f / 256.0f), fy = (float)ty.a * (1.0f / 256.0f);
+            const float top = __fmaf_rn(fx, (float)r0[tx.i1] - (float)r0[tx.i0], (float)r0[tx.i0]);
+            const float bot = __fmaf_rn(fx, (float)r1[tx.i1] - (float)r1[tx.i0], (float)r1[tx.i0]);
+            s[idx] = __fmaf_rn(fy, bot - top, top);
+        }
+    }
+    __syncthreads();
+    row_pass<R, true>(s, m, SW, dd);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < TH * TW; idx += NT) {
+        const int y = idx / TW;
+        const int x = idx - y * TW;
+        const int gx = x0 + x, gy = y0 + y;
+        if (gx >= W || gy >= H) continue;
+        dst[(size_t)gy * pitch + gx] = col_at<R>(m, y, x, inc0);
+    }
+}
+
+template <int R>
+constexpr size_t tile_smem() { return sizeof(float) * ((TH + 2 * R) * (TW + 2 * R) + (TH + 2 * R) * TW); }
+
+template <int R>
+int run_blur(const OctaveView& o, int level, const Taps& t, float* next0, int next_pitch, cudaStream_t st)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(blur_level_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem<R>());
+        attr_set = true;
+    }
+    dim3 grid((o.w + TW - 1) / TW, (o.h + TH - 1) / TH);
+    blur_level_kernel<R><<<grid, NT, tile_smem<R>(), st>>>(
+        o.gauss + o.plane * (level - 1), o.gauss + o.plane * level, o.dog + o.plane * (level - 1),
+        next0, o.w, o.h, o.pitch, next_pitch, t);
+    return 1;
+}
+
+template <int R, typename PIX>
+int run_level0(const PIX* img, size_t img_pitch, int w, int h, float shift, const OctaveView& o0,
+               const Taps& dd, const Taps& inc0, cudaStream_t st)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(level0_kernel<R, PIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem<R>());
+        attr_set = true;
+    }
+    dim3 grid((o0.w + TW - 1) / TW, (o0.h + TH - 1) / TH);
+    level0_kernel<R, PIX><<<grid, NT, tile_smem<R>(), st>>>(img, img_pitch, w, h, shift, o0.gauss, o0.w, o0.h,
+                                                            o0.pitch, dd, inc0);
+    return 1;
+}
+
+Taps make_taps(const GaussRow& g)
+{
+    Taps t;
+    for (int i = 0; i < PS_GAUSS_ALIGN; ++i) t.g[i] = g.tap[i];
+    return t;
+}
+
+template <typename PIX>
+int launch_level0_any(const PIX* img, size_t img_pitch, int w, int h, float upscale, int sift_mode,
+                      const OctaveView& o0, const GaussRow& dd, const GaussRow& inc0, cudaStream_t st)
+{
+    // reference s_pyramid_build.cu:108-114
+    float shift = 0.5f;
+    if (sift_mode == PS_MODE_POPSIFT || sift_mode == PS_MODE_VLFEAT) shift = 0.5f * powf(2.0f, upscale);
+    // both passes use sigma_inc[0]; the two tables have the same span by construction
+    const int R = (dd.span > inc0.span ? dd.span : inc0.span) - 1;
+    const Taps a = make_taps(dd), b = make_taps(inc0);
+    switch (R) {
+#define PSB_CASE(N) case N: return run_level0<N, PIX>(img, img_pitch, w, h, shift, o0, a, b, st);
+        PSB_CASE(1) PSB_CASE(2) PSB_CASE(3) PSB_CASE(4) PSB_CASE(5) PSB_CASE(6) PSB_CASE(7) PSB_CASE(8)
+        PSB_CASE(9) PSB_CASE(10)
+#undef PSB_CASE
+        default: return -1;   // sigma0 <= 2.0 bounds the level-0 span at 10 (R <= 9) for any initial blur
+    }
+}
+
+} // namespace
+
+int launch_level0_u8(const uint8_t* img, size_t img_pitch, int w, int h, float upscale, int sift_mode,
+                     const OctaveView& o0, const GaussRow& dd, const GaussRow& inc0, cudaStream_t st)
+{
+    return launch_level0_any<uint8_t>(img, img_pitch, w, h, upscale, sift_mode, o0, dd, inc0, st);
+}
+
+int launch_level0_f32(const float* img, size_t img_pitch_floats, int w, int h, float upscale, int sift_mode,
+                      const OctaveView& o0, const GaussRow& dd, const GaussRow& inc0, cudaStream_t st)
+{
+    return launch_level0_any<float>(img, img_pitch_floats, w, h, upscale, sift_mode, o0, dd, inc0, st);
+}
+
+int launch_blur_level(const OctaveView& o, int level, const GaussRow& g, const OctaveView* next, cudaStream_t st)
+{
+    const int R = g.span - 1;
+    const Taps t = make_taps(g);
+    float* next0 = next ? next->gauss : nullptr;
+    const int next_pitch = next ? next->pitch : 0;
+    switch (R) {
+        case 5:  return run_blur<5>(o, level, t, next0, next_pitch, st);
+        case 7:  return run_blur<7>(o, level, t, next0, next_pitch, st);
+        case 8:  return run_blur<8>(o, level, t, next0, next_pitch, st);
+        case 10: return run_blur<10>(o, level, t, next0, next_pitch, st);
+        case 13: return run_blur<13>(o, level, t, next0, next_pitch, st);
+        default: break;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        const int Rm = PS_GAUSS_ALIGN - 2;
+        cudaFuncSetAttribute(blur_level_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(sizeof(float) * ((TH + 2 * Rm) * (TW + 2 * Rm) + (TH + 2 * Rm) * TW)));
+        attr_set = true;
+    }
+    const size_t sm = sizeof(float) * ((TH + 2 * R) * (TW + 2 * R) + (TH + 2 * R) * TW);
+    dim3 grid((o.w + TW - 1) / TW, (o.h + TH - 1) / TH);
+    blur_level_generic_kernel<<<grid, NT, sm, st>>>(o.gauss + o.plane * (level - 1), o.gauss + o.plane * level,
+                                                    o.dog + o.plane * (level - 1), next0, o.w, o.h, o.pitch,
+                                                    next_pitch, t, R);
+    return 1;
+}
+
+} // namespace psb

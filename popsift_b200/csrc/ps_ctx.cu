@@ -1,0 +1,480 @@
+// C-ABI layer: contexts, slots (one CUDA stream + one set of HBM buffers per in-flight image),
+// kernel choreography.  See include/popsift_b200.h for the contract and the reference interfaces
+// each entry point replaces.
+//
+// HBM layout of a slot (all float32, linear, row pitch = multiple of 32 floats):
+//   for each octave o: [ (L+3) Gaussian planes | (L+2) DoG planes ], octaves back to back;
+//   InitialExtremum[octaves][max_extrema], ps_extremum[ext_cap], ps_feature[ext_cap],
+//   ps_descriptor[desc_cap], int feat_to_ext[desc_cap], Counters.
+// There is no intermediate (row-filtered) plane in HBM: the row pass lives in shared memory.
+#include "ps_internal.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace psb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    // input
+    uint8_t* d_img = nullptr;      // max_w*max_h*4 bytes (u8 or f32 images)
+    uint8_t* h_img = nullptr;      // pinned staging, same size
+    // pyramid
+    float*  d_planes = nullptr;
+    size_t  planes_floats = 0;
+    PyramidView view{};
+    // detections
+    InitialExtremum* d_iext = nullptr;
+    ps_extremum*     d_ext = nullptr;
+    ps_feature*      d_feat = nullptr;
+    ps_descriptor*   d_desc = nullptr;
+    int*             d_f2e = nullptr;
+    Counters*        d_ct = nullptr;
+    Counters*        h_ct = nullptr;   // pinned
+    // pinned result staging (grown on demand)
+    ps_feature*    h_feat = nullptr;  size_t h_feat_cap = 0;
+    ps_descriptor* h_desc = nullptr;  size_t h_desc_cap = 0;
+    cudaEvent_t ev[PS_NUM_STAGES + 1] = {};
+    cudaEvent_t done = nullptr;
+    bool submitted = false;
+    bool is_float = false;
+    int w = 0, h = 0;
+    int32_t W[kMaxOctaves] = {}, H[kMaxOctaves] = {};
+    int num_octaves = 0;
+};
+
+} // namespace
+
+struct ps_ctx {
+    int device = 0;
+    ps_config cfg{};
+    ps_gauss_tables tab{};
+    GaussRow rows[PS_GAUSS_LEVELS];
+    GaussRow dd0;
+    Consts k{};
+    int max_w = 0, max_h = 0;
+    int max_octaves = 0;
+    int levels = 3;
+    bool timing = false;
+    std::vector<Slot> slots;
+    std::atomic<int64_t> launches{0};
+    mutable std::mutex err_mu;
+    std::string err;
+
+    int fail(int code, const char* fmt, ...)
+    {
+        char buf[512];
+        va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+        std::lock_guard<std::mutex> g(err_mu);
+        err = buf;
+        return code;
+    }
+};
+
+#define PS_CUDA(ctx, call)                                                                   \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess)                                                               \
+            return (ctx)->fail(PS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+namespace {
+
+size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// floats needed for the planes of a w x h image
+size_t plane_budget(const ps_config& cfg, int w, int h, int levels)
+{
+    int32_t W[kMaxOctaves], H[kMaxOctaves];
+    const int n = ps_geometry(&cfg, w, h, W, H);
+    size_t total = 0;
+    for (int o = 0; o < n; ++o) total += round_up(W[o], 32) * (size_t)H[o] * (size_t)(2 * levels + 5);
+    return total;
+}
+
+int build_view(ps_ctx* ctx, Slot& s, int w, int h)
+{
+    s.num_octaves = ps_geometry(&ctx->cfg, w, h, s.W, s.H);
+    if (s.num_octaves < 1) return ctx->fail(PS_ERR_ARG, "bad geometry for %dx%d", w, h);
+    if (s.num_octaves > ctx->max_octaves)
+        return ctx->fail(PS_ERR_TOO_LARGE, "%dx%d needs %d octaves, context has %d", w, h, s.num_octaves, ctx->max_octaves);
+    const int L = ctx->levels;
+    size_t off = 0;
+    std::memset(&s.view, 0, sizeof(s.view));
+    for (int o = 0; o < s.num_octaves; ++o) {
+        OctaveView& v = s.view.oct[o];
+        v.w = s.W[o]; v.h = s.H[o];
+        v.pitch = (int)round_up(v.w, 32);
+        v.plane = (size_t)v.pitch * v.h;
+        v.gauss = s.d_planes + off;  off += v.plane * (L + 3);
+        v.dog = s.d_planes + off;    off += v.plane * (L + 2);
+    }
+    if (off > s.planes_floats) return ctx->fail(PS_ERR_TOO_LARGE, "%dx%d exceeds the slot's plane memory", w, h);
+    s.view.num_octaves = s.num_octaves;
+    s.view.levels = L;
+    s.w = w; s.h = h;
+    return PS_OK;
+}
+
+int run_pyramid(ps_ctx* ctx, Slot& s)
+{
+    const int L = ctx->levels;
+    int n = 0, r;
+    if (s.is_float)
+        r = launch_level0_f32(reinterpret_cast<const float*>(s.d_img), (size_t)s.w, s.w, s.h, ctx->cfg.upscale,
+                              ctx->cfg.sift_mode, s.view.oct[0], ctx->dd0, ctx->rows[0], s.stream);
+    else
+        r = launch_level0_u8(s.d_img, (size_t)s.w, s.w, s.h, ctx->cfg.upscale, ctx->cfg.sift_mode, s.view.oct[0],
+                             ctx->dd0, ctx->rows[0], s.stream);
+    if (r < 0) return ctx->fail(PS_ERR_ARG, "unsupported level-0 filter span %d", ctx->dd0.span);
+    n += r;
+    for (int o = 0; o < s.num_octaves; ++o)
+        for (int l = 1; l < L + 3; ++l) {
+            const OctaveView* next = (l == L && o + 1 < s.num_octaves) ? &s.view.oct[o + 1] : nullptr;
+            r = launch_blur_level(s.view.oct[o], l, ctx->rows[l], next, s.stream);
+            if (r < 0) return ctx->fail(PS_ERR_ARG, "unsupported filter span %d", ctx->rows[l].span);
+            n += r;
+        }
+    ctx->launches += n;
+    PS_CUDA(ctx, cudaGetLastError());
+    return PS_OK;
+}
+
+} // namespace
+
+static int submit_common(ps_ctx* ctx, Slot& s)
+{
+    const bool tm = ctx->timing;
+    int rc;
+    PS_CUDA(ctx, cudaMemsetAsync(s.d_ct, 0, sizeof(Counters), s.stream));
+    if (tm) PS_CUDA(ctx, cudaEventRecord(s.ev[1], s.stream));
+    if ((rc = run_pyramid(ctx, s)) != PS_OK) return rc;
+    if (tm) PS_CUDA(ctx, cudaEventRecord(s.ev[2], s.stream));
+    int n = launch_find_extrema(s.view, ctx->k, s.d_iext, s.d_ct, s.stream);
+    if (tm) PS_CUDA(ctx, cudaEventRecord(s.ev[3], s.stream));
+    n += launch_orientation(s.view, ctx->k, s.d_iext, s.d_ext, s.d_f2e, s.d_ct, s.stream);
+    if (tm) PS_CUDA(ctx, cudaEventRecord(s.ev[4], s.stream));
+    n += launch_descriptors(s.view, ctx->k, s.d_ext, s.d_f2e, s.d_desc, s.d_ct, s.stream);
+    n += launch_prep_features(ctx->k, s.d_ext, s.d_feat, s.d_ct, s.stream);
+    if (tm) PS_CUDA(ctx, cudaEventRecord(s.ev[5], s.stream));
+    ctx->launches += n;
+    PS_CUDA(ctx, cudaGetLastError());
+    PS_CUDA(ctx, cudaMemcpyAsync(s.h_ct, s.d_ct, sizeof(Counters), cudaMemcpyDeviceToHost, s.stream));
+    PS_CUDA(ctx, cudaEventRecord(s.done, s.stream));
+    s.submitted = true;
+    return PS_OK;
+}
+
+static Slot* get_slot(ps_ctx* ctx, int slot)
+{
+    if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return nullptr;
+    return &ctx->slots[slot];
+}
+
+extern "C" const char* ps_last_error(const ps_ctx* ctx)
+{
+    if (!ctx) return g_create_error.c_str();
+    std::lock_guard<std::mutex> g(ctx->err_mu);
+    return ctx->err.c_str();
+}
+
+extern "C" void ps_destroy(ps_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (Slot& s : ctx->slots) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        cudaFree(s.d_img); cudaFreeHost(s.h_img); cudaFree(s.d_planes); cudaFree(s.d_iext); cudaFree(s.d_ext);
+        cudaFree(s.d_feat); cudaFree(s.d_desc); cudaFree(s.d_f2e); cudaFree(s.d_ct); cudaFreeHost(s.h_ct);
+        cudaFreeHost(s.h_feat); cudaFreeHost(s.h_desc);
+        for (auto& e : s.ev) if (e) cudaEventDestroy(e);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    delete ctx;
+}
+
+extern "C" ps_ctx* ps_create(int device, const ps_config* cfg, int max_w, int max_h, int n_slots)
+{
+    auto bail = [&](const char* msg, cudaError_t e) -> ps_ctx* {
+        g_create_error = std::string(msg) + (e != cudaSuccess ? std::string(": ") + cudaGetErrorString(e) : std::string());
+        return nullptr;
+    };
+    if (!cfg || max_w < 1 || max_h < 1 || n_slots < 1 || n_slots > 64) return bail("ps_create: bad argument", cudaSuccess);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return bail("ps_create: no CUDA device (this library has no CPU fallback)", e);
+    if (device < 0 || device >= ndev) return bail("ps_create: bad device index", cudaSuccess);
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+
+    ps_ctx* ctx = new ps_ctx;
+    ctx->device = device;
+    ctx->cfg = *cfg;
+    ctx->cfg.levels = std::max(2, cfg->levels);       // reference popsift.cpp:86
+    ctx->levels = ctx->cfg.levels;
+    if (ctx->cfg.max_extrema < 1) ctx->cfg.max_extrema = 100000;
+    if (ps_gauss_tables_compute(&ctx->cfg, &ctx->tab) != PS_OK) {
+        delete ctx;
+        return bail("ps_create: unsupported configuration (sigma > 2.0, levels > 12 or gauss mode other than vlfeat)", cudaSuccess);
+    }
+    for (int l = 0; l < PS_GAUSS_LEVELS; ++l) {
+        std::memcpy(ctx->rows[l].tap, &ctx->tab.inc_filter[l * PS_GAUSS_ALIGN], sizeof(float) * PS_GAUSS_ALIGN);
+        ctx->rows[l].span = ctx->tab.inc_span[l];
+    }
+    std::memcpy(ctx->dd0.tap, ctx->tab.dd_filter0, sizeof(float) * PS_GAUSS_ALIGN);
+    ctx->dd0.span = ctx->tab.dd_span0;
+    ctx->max_w = max_w; ctx->max_h = max_h;
+    int32_t W[kMaxOctaves], H[kMaxOctaves];
+    ctx->max_octaves = ps_geometry(&ctx->cfg, max_w, max_h, W, H);
+    if (ctx->max_octaves < 1) { delete ctx; return bail("ps_create: bad geometry", cudaSuccess); }
+
+    Consts& k = ctx->k;
+    k.sigma0 = ctx->cfg.sigma;
+    k.sigma_k = ctx->tab.sigma_k;
+    k.edge_limit = ctx->cfg.edge_limit;
+    k.threshold = ctx->tab.peak_threshold;
+    k.max_extrema = ctx->cfg.max_extrema;
+    // capacity of one slot: the reference starts with max_extrema Extremum records and
+    // max(2*max_extrema, 1.25*max_extrema) descriptors and grows on demand (sift_pyramid.cu:136-209);
+    // here the capacity is fixed at create time and an overflow is reported by ps_counts.
+    k.ext_capacity = 2 * k.max_extrema;
+    k.desc_capacity = 2 * k.max_extrema;
+    k.norm_multi = ctx->cfg.norm_multi;
+    k.norm_mode = ctx->cfg.norm_mode;
+    k.sift_mode = ctx->cfg.sift_mode;
+    k.up_fac = (int)ctx->cfg.upscale;
+
+    const size_t planes = plane_budget(ctx->cfg, max_w, max_h, ctx->levels);
+    ctx->slots.resize(n_slots);
+    for (Slot& s : ctx->slots) {
+#define PS_TRY(call) if ((e = (call)) != cudaSuccess) { std::string m = #call; ps_destroy(ctx); return bail(m.c_str(), e); }
+        PS_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        PS_TRY(cudaMalloc(&s.d_img, (size_t)max_w * max_h * 4));
+        PS_TRY(cudaHostAlloc(&s.h_img, (size_t)max_w * max_h * 4, cudaHostAllocDefault));
+        PS_TRY(cudaMalloc(&s.d_planes, planes * sizeof(float)));
+        s.planes_floats = planes;
+        PS_TRY(cudaMalloc(&s.d_iext, sizeof(InitialExtremum) * (size_t)ctx->max_octaves * k.max_extrema));
+        PS_TRY(cudaMalloc(&s.d_ext, sizeof(ps_extremum) * (size_t)k.ext_capacity));
+        PS_TRY(cudaMalloc(&s.d_feat, sizeof(ps_feature) * (size_t)k.ext_capacity));
+        PS_TRY(cudaMalloc(&s.d_desc, sizeof(ps_descriptor) * (size_t)k.desc_capacity));
+        PS_TRY(cudaMalloc(&s.d_f2e, sizeof(int) * (size_t)k.desc_capacity));
+        PS_TRY(cudaMalloc(&s.d_ct, sizeof(Counters)));
+        PS_TRY(cudaHostAlloc(&s.h_ct, sizeof(Counters), cudaHostAllocDefault));
+        for (auto& ev : s.ev) PS_TRY(cudaEventCreate(&ev));
+        PS_TRY(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+#undef PS_TRY
+    }
+    return ctx;
+}
+
+static int stage_input(ps_ctx* ctx, Slot& s, const void* host_img, size_t bytes)
+{
+    // Pinned caller memory goes straight to the device; pageable memory is staged through the
+    // slot's pinned buffer (the reference always stages: popsift.cpp:392-395 + s_image.cu:75).
+    cudaPointerAttributes at{};
+    const bool pinned = cudaPointerGetAttributes(&at, host_img) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    const void* src = host_img;
+    if (!pinned) {
+        // the staging buffer may still be in flight for the previous image of this slot
+        PS_CUDA(ctx, cudaStreamSynchronize(s.stream));
+        std::memcpy(s.h_img, host_img, bytes);
+        src = s.h_img;
+    }
+    PS_CUDA(ctx, cudaMemcpyAsync(s.d_img, src, bytes, cudaMemcpyHostToDevice, s.stream));
+    return PS_OK;
+}
+
+extern "C" int ps_submit_u8(ps_ctx* ctx, int slot, const uint8_t* host_img, int w, int h)
+{
+    Slot* s = get_slot(ctx, slot);
+    if (!s || !host_img) return ctx ? ctx->fail(PS_ERR_ARG, "ps_submit_u8: bad argument") : PS_ERR_ARG;
+    if (w < 1 || h < 1 || w > ctx->max_w || h > ctx->max_h)
+        return ctx->fail(PS_ERR_TOO_LARGE, "image %dx%d exceeds context maximum %dx%d", w, h, ctx->max_w, ctx->max_h);
+    PS_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = build_view(ctx, *s, w, h);
+    if (rc != PS_OK) return rc;
+    s->is_float = false;
+    if (ctx->timing) PS_CUDA(ctx, cudaEventRecord(s->ev[0], s->stream));
+    if ((rc = stage_input(ctx, *s, host_img, (size_t)w * h)) != PS_OK) return rc;
+    return submit_common(ctx, *s);
+}
+
+extern "C" int ps_submit_f32(ps_ctx* ctx, int slot, const float* host_img, int w, int h)
+{
+    Slot* s = get_slot(ctx, slot);
+    if (!s || !host_img) return ctx ? ctx->fail(PS_ERR_ARG, "ps_submit_f32: bad argument") : PS_ERR_ARG;
+    if (w < 1 || h < 1 || w > ctx->max_w || h > ctx->max_h)
+        return ctx->fail(PS_ERR_TOO_LARGE, "image %dx%d exceeds context maximum %dx%d", w, h, ctx->max_w, ctx->max_h);
+    PS_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = build_view(ctx, *s, w, h);
+    if (rc != PS_OK) return rc;
+    s->is_float = true;
+    if (ctx->timing) PS_CUDA(ctx, cudaEventRecord(s->ev[0], s->stream));
+    if ((rc = stage_input(ctx, *s, host_img, (size_t)w * h * sizeof(float))) != PS_OK) return rc;
+    return submit_common(ctx, *s);
+}
+
+extern "C" int ps_submit_dev_u8(ps_ctx* ctx, int slot, const uint8_t* dev_img, size_t pitch, int w, int h)
+{
+    Slot* s = get_slot(ctx, slot);
+    if (!s || !dev_img) return ctx ? ctx->fail(PS_ERR_ARG, "ps_submit_dev_u8: bad argument") : PS_ERR_ARG;
+    if (w < 1 || h < 1 || w > ctx->max_w || h > ctx->max_h || pitch < (size_t)w)
+        return ctx->fail(PS_ERR_TOO_LARGE, "image %dx%d exceeds context maximum %dx%d", w, h, ctx->max_w, ctx->max_h);
+    PS_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = build_view(ctx, *s, w, h);
+    if (rc != PS_OK) return rc;
+    s->is_float = false;
+    if (ctx->timing) PS_CUDA(ctx, cudaEventRecord(s->ev[0], s->stream));
+    PS_CUDA(ctx, cudaMemcpy2DAsync(s->d_img, (size_t)w, dev_img, pitch, (size_t)w, (size_t)h, cudaMemcpyDeviceToDevice, s->stream));
+    return submit_common(ctx, *s);
+}
+
+extern "C" int ps_sync(ps_ctx* ctx, int slot)
+{
+    Slot* s = get_slot(ctx, slot);
+    if (!s) return PS_ERR_ARG;
+    PS_CUDA(ctx, cudaSetDevice(ctx->device));
+    PS_CUDA(ctx, cudaStreamSynchronize(s->stream));
+    return PS_OK;
+}
+
+extern "C" int ps_counts(ps_ctx* ctx, int slot, int32_t* n_feat, int32_t* n_desc)
+{
+    Slot* s = get_slot(ctx, slot);
+    if (!s) return PS_ERR_ARG;
+    if (!s->submitted) return ctx->fail(PS_ERR_STATE, "ps_counts: nothing submitted to slot %d", slot);
+    PS_CUDA(ctx, cudaSetDevice(ctx->device));
+    PS_CUDA(ctx, cudaEventSynchronize(s->done));
+    if (n_feat) *n_feat = s->h_ct->ext_total;
+    if (n_desc) *n_desc = s->h_ct->ori_total;
+    if (s->h_ct->overflow)
+        return ctx->fail(PS_ERR_OVERFLOW, "slot %d: capacity exceeded (flags %d); results truncated", slot, s->h_ct->overflow);
+    return PS_OK;
+}
+
+static int grow_pinned(ps_ctx* ctx, void** p, size_t* cap, size_t need, size_t elem)
+{
+    if (need <= *cap) return PS_OK;
+    size_t ncap = std::max(need, *cap * 2);
+    ncap = std::max<size_t>(ncap, 4096);
+    if (*p) PS_CUDA(ctx, cudaFreeHost(*p));
+    *p = nullptr; *cap = 0;
+    PS_CUDA(ctx, cudaHostAlloc(p, ncap * elem, cudaHostAllocDefault));
+    *cap = ncap;
+    return PS_OK;
+}
+
+extern "C" int ps_download(ps_ctx* ctx, int slot, ps_feature* feat, ps_descriptor* desc)
+{
+    Slot* s = get_slot(ctx, slot);
+    if (!s) return PS_ERR_ARG;
+    if (!s->submitted) return ctx->fail(PS_ERR_STATE, "ps_download: nothing submitted to slot %d", slot);
+    PS_CUDA(ctx, cudaSetDevice(ctx->device));
+    PS_CUDA(ctx, cudaEventSynchronize(s->done));
+    const size_t nf = (size_t)s->h_ct->ext_total, nd = (size_t)s->h_ct->ori_total;
+    if (nf == 0) return PS_OK;
+    if (!feat || (nd && !desc)) return ctx->fail(PS_ERR_ARG, "ps_download: null output array");
+    int rc;
+    if ((rc = grow_pinned(ctx, (void**)&s->h_feat, &s->h_feat_cap, nf, sizeof(ps_feature))) != PS_OK) return rc;
+    if ((rc = grow_pinned(ctx, (void**)&s->h_desc, &s->h_desc_cap, nd, sizeof(ps_descriptor))) != PS_OK) return rc;
+    PS_CUDA(ctx, cudaMemcpyAsync(s->h_feat, s->d_feat, nf * sizeof(ps_feature), cudaMemcpyDeviceToHost, s->stream));
+    if (nd) PS_CUDA(ctx, cudaMemcpyAsync(s->h_desc, s->d_desc, nd * sizeof(ps_descriptor), cudaMemcpyDeviceToHost, s->stream));
+    PS_CUDA(ctx, cudaStreamSynchronize(s->stream));
+    if (nd) std::memcpy(desc, s->h_desc, nd * sizeof(ps_descriptor));
+    for (size_t i = 0; i < nf; ++i) {
+        ps_feature f = s->h_feat[i];
+        const int first = f.pad_;
+        f.pad_ = 0;
+        for (int r = 0; r < PS_MAX_ORI; ++r) f.desc[r] = (r < f.num_ori) ? desc + first + r : nullptr;
+        feat[i] = f;
+    }
+    return PS_OK;
+}
+
+extern "C" int ps_debug_plane(ps_ctx* ctx, int slot, int octave, int level, int which, float* out)
+{
+    Slot* s = get_slot(ctx, slot);
+    if (!s || !out) return PS_ERR_ARG;
+    if (!s->submitted) return ctx->fail(PS_ERR_STATE, "ps_debug_plane: nothing submitted");
+    if (octave < 0 || octave >= s->num_octaves) return ctx->fail(PS_ERR_ARG, "bad octave %d", octave);
+    const int L = ctx->levels;
+    const int nl = which == PS_PLANE_DOG ? L + 2 : L + 3;
+    if (level < 0 || level >= nl) return ctx->fail(PS_ERR_ARG, "bad level %d", level);
+    PS_CUDA(ctx, cudaSetDevice(ctx->device));
+    PS_CUDA(ctx, cudaStreamSynchronize(s->stream));
+    const OctaveView& v = s->view.oct[octave];
+    const float* src = (which == PS_PLANE_DOG ? v.dog : v.gauss) + v.plane * level;
+    PS_CUDA(ctx, cudaMemcpy2D(out, (size_t)v.w * sizeof(float), src, (size_t)v.pitch * sizeof(float),
+                              (size_t)v.w * sizeof(float), v.h, cudaMemcpyDeviceToHost));
+    return PS_OK;
+}
+
+extern "C" int ps_debug_extrema(ps_ctx* ctx, int slot, ps_extremum* out, int cap)
+{
+    Slot* s = get_slot(ctx, slot);
+    if (!s) return PS_ERR_ARG;
+    if (!s->submitted) return ctx->fail(PS_ERR_STATE, "ps_debug_extrema: nothing submitted");
+    PS_CUDA(ctx, cudaSetDevice(ctx->device));
+    PS_CUDA(ctx, cudaEventSynchronize(s->done));
+    const int n = s->h_ct->ext_total;
+    const int m = std::min(n, cap);
+    if (m > 0 && out) PS_CUDA(ctx, cudaMemcpy(out, s->d_ext, sizeof(ps_extremum) * (size_t)m, cudaMemcpyDeviceToHost));
+    return n;
+}
+
+extern "C" int ps_slot_geometry(ps_ctx* ctx, int slot, int32_t* n_octaves, int32_t* W, int32_t* H)
+{
+    Slot* s = get_slot(ctx, slot);
+    if (!s) return PS_ERR_ARG;
+    if (n_octaves) *n_octaves = s->num_octaves;
+    for (int o = 0; o < s->num_octaves; ++o) { if (W) W[o] = s->W[o]; if (H) H[o] = s->H[o]; }
+    return PS_OK;
+}
+
+extern "C" int ps_set_timing(ps_ctx* ctx, int enable)
+{
+    if (!ctx) return PS_ERR_ARG;
+    ctx->timing = enable != 0;
+    return PS_OK;
+}
+
+extern "C" int ps_stage_ms(ps_ctx* ctx, int slot, float ms[PS_NUM_STAGES])
+{
+    Slot* s = get_slot(ctx, slot);
+    if (!s || !ms) return PS_ERR_ARG;
+    if (!ctx->timing || !s->submitted) return ctx->fail(PS_ERR_STATE, "ps_stage_ms: timing not enabled or nothing submitted");
+    PS_CUDA(ctx, cudaSetDevice(ctx->device));
+    PS_CUDA(ctx, cudaEventSynchronize(s->done));
+    PS_CUDA(ctx, cudaEventSynchronize(s->ev[5]));
+    for (int i = 0; i < 5; ++i) PS_CUDA(ctx, cudaEventElapsedTime(&ms[i], s->ev[i], s->ev[i + 1]));
+    PS_CUDA(ctx, cudaEventElapsedTime(&ms[PS_STAGE_TOTAL], s->ev[0], s->ev[5]));
+    return PS_OK;
+}
+
+extern "C" int64_t ps_launch_count(const ps_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+
+extern "C" void* ps_slot_stream(ps_ctx* ctx, int slot)
+{
+    Slot* s = get_slot(ctx, slot);
+    return s ? (void*)s->stream : nullptr;
+}
+
+extern "C" int ps_run_pyramid_only(ps_ctx* ctx, int slot)
+{
+    Slot* s = get_slot(ctx, slot);
+    if (!s) return PS_ERR_ARG;
+    if (!s->submitted) return ctx->fail(PS_ERR_STATE, "ps_run_pyramid_only: nothing submitted");
+    PS_CUDA(ctx, cudaSetDevice(ctx->device));
+    return run_pyramid(ctx, *s);
+}

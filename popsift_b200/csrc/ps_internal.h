@@ -1,0 +1,85 @@
+// Internal (device + host) structures shared by the kernels and the C-ABI layer.
+#pragma once
+#include "popsift_b200.h"
+
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace psb {
+
+constexpr int kMaxOctaves = PS_MAX_OCTAVES;
+constexpr int kMaxPlanes  = PS_GAUSS_LEVELS + 3;   // L+3 <= 15
+constexpr int kOriBins    = 36;                    // reference sift_constants.h:41
+
+// A candidate from the DoG scan (reference InitialExtremum, sift_extremum.h:25-39, without
+// the grid-filter fields).
+struct InitialExtremum {
+    float xpos, ypos;
+    int   lpos;
+    float sigma;
+};
+
+// Per-image device counters (reference ExtremaCounters, sift_pyramid.h:21-35).
+struct Counters {
+    int ext_ct[kMaxOctaves];   // extrema found per octave (may exceed max_extrema; clamp on use)
+    int ext_total;             // after clamping, written by the orientation-prefix kernel
+    int ori_total;
+    int overflow;              // bit 0: extrema capacity hit, bit 1: descriptor capacity hit
+    int work_ori;              // work-stealing cursors
+    int work_desc;
+    int pad_[3];
+};
+
+// One octave's planes in HBM: linear float32, row pitch a multiple of 32 floats (128 B).
+struct OctaveView {
+    float* gauss;       // (levels+3) planes, plane stride = plane
+    float* dog;         // (levels+2) planes
+    int    w, h;
+    int    pitch;       // floats per row
+    size_t plane;       // floats per plane = pitch * h
+};
+
+// Kernel-visible description of one slot's pyramid.
+struct PyramidView {
+    OctaveView oct[kMaxOctaves];
+    int        num_octaves;
+    int        levels;      // L
+};
+
+// Small constants consumed by the extrema / orientation / descriptor kernels
+// (reference ConstInfo, sift_constants.h:56-67).
+struct Consts {
+    float sigma0;
+    float sigma_k;
+    float edge_limit;
+    float threshold;        // peak threshold
+    int   max_extrema;      // per octave
+    int   ext_capacity;     // total Extremum records per slot
+    int   desc_capacity;    // total descriptors per slot
+    int   norm_multi;
+    int   norm_mode;
+    int   sift_mode;
+    int   up_fac;           // int(upscale), reference sift_pyramid.cu:297
+};
+
+// ---- launchers (defined in the k_*.cu files); all asynchronous on `st`, return #kernels launched
+
+struct GaussRow { float tap[PS_GAUSS_ALIGN]; int span; };
+
+// octave 0, level 0 from the 8-bit or float input image
+int launch_level0_u8(const uint8_t* img, size_t img_pitch, int w, int h, float upscale, int sift_mode,
+                     const OctaveView& o0, const GaussRow& dd, const GaussRow& inc0, cudaStream_t st);
+int launch_level0_f32(const float* img, size_t img_pitch_floats, int w, int h, float upscale, int sift_mode,
+                      const OctaveView& o0, const GaussRow& dd, const GaussRow& inc0, cudaStream_t st);
+// level l >= 1 of one octave: blur level l-1 -> level l, DoG[l-1] = G[l]-G[l-1]; if next0 != nullptr
+// also writes every second pixel into the next octave's level 0.
+int launch_blur_level(const OctaveView& o, int level, const GaussRow& g, const OctaveView* next, cudaStream_t st);
+
+int launch_find_extrema(const PyramidView& pyr, const Consts& k, InitialExtremum* iext, Counters* ct, cudaStream_t st);
+int launch_orientation(const PyramidView& pyr, const Consts& k, const InitialExtremum* iext, ps_extremum* ext,
+                       int* feat_to_ext, Counters* ct, cudaStream_t st);
+int launch_descriptors(const PyramidView& pyr, const Consts& k, const ps_extremum* ext, const int* feat_to_ext,
+                       ps_descriptor* desc, Counters* ct, cudaStream_t st);
+int launch_prep_features(const Consts& k, const ps_extremum* ext, ps_feature* feat, const Counters* ct, cudaStream_t st);
+
+} // namespace psb

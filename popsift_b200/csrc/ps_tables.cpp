@@ -1,0 +1,120 @@
+// Host-side tables and geometry of the SIFT pipeline (no CUDA needed).
+//
+// Restates, with bit-identical float/double mixing, what the reference computes in
+//   init_filter / GaussTable::computeBlurTable   (reference src/popsift/gauss_filter.cu:127-257,341-371)
+//   init_constants                               (reference src/popsift/sift_constants.cu:22-53)
+//   Config::getPeakThreshold                     (reference src/popsift/sift_conf.cu:276-279)
+//   PopSift::private_apply_scale_factor          (reference src/popsift/popsift.cpp:109-126)
+//   Pyramid ctor octave sizes                    (reference src/popsift/sift_pyramid.cu:129-134)
+#include "popsift_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace {
+
+// Half-width (including the centre tap) of the VLFeat-style kernel for one sigma.
+int kernel_span(float sigma)
+{
+    const int s = static_cast<int>(std::ceil(4.0f * sigma) + 1.0f);
+    return std::min(s, PS_GAUSS_ALIGN - 1);
+}
+
+// One normalised half-kernel.  The taps are evaluated in double, stored as float; the
+// normaliser is a double that accumulates twice the *stored float* tap.
+void fill_kernel(float sigma, float* taps, int32_t* span_out)
+{
+    const int span = kernel_span(sigma);
+    std::fill(taps, taps + PS_GAUSS_ALIGN, 0.0f);
+    taps[0] = 1.0f;
+    double norm = 1.0;
+    for (int k = 1; k < span; ++k) {
+        const double q = static_cast<double>(k) / static_cast<double>(sigma);
+        const float t = static_cast<float>(std::exp(-0.5 * std::pow(q, 2.0)));
+        taps[k] = t;
+        norm += static_cast<double>(2.0f * t);
+    }
+    for (int k = 0; k < span; ++k) taps[k] = static_cast<float>(static_cast<double>(taps[k]) / norm);
+    *span_out = span;
+}
+
+} // namespace
+
+extern "C" int ps_abi_version(void) { return PS_ABI_VERSION; }
+
+extern "C" void ps_config_default(ps_config* c)
+{
+    if (!c) return;
+    c->octaves = -1;
+    c->levels = 3;
+    c->sigma = 1.6f;
+    c->edge_limit = 10.0f;
+    c->threshold = 0.04f;
+    c->upscale = 1.0f;
+    c->initial_blur = 0.5f;
+    c->has_initial_blur = 1;
+    c->sift_mode = PS_MODE_POPSIFT;
+    c->gauss_mode = PS_GAUSS_VLFEAT_COMPUTE;
+    c->desc_mode = PS_DESC_LOOP;
+    c->norm_mode = PS_NORM_ROOTSIFT;
+    c->norm_multi = 0;
+    c->max_extrema = 100000;
+}
+
+extern "C" int ps_gauss_tables_compute(const ps_config* cfg, ps_gauss_tables* out)
+{
+    if (!cfg || !out) return PS_ERR_ARG;
+    std::memset(out, 0, sizeof(*out));
+    const int levels = std::max(2, cfg->levels);
+    const float s0 = cfg->sigma;
+    if (s0 > 2.0f) return PS_ERR_ARG;                 // reference gauss_filter.cu:131-137
+    if (levels > PS_GAUSS_LEVELS) return PS_ERR_ARG;  // reference gauss_filter.cu:138-144
+    if (cfg->gauss_mode != PS_GAUSS_VLFEAT_COMPUTE) return PS_ERR_ARG;
+    const int planes = levels + 3;
+    const float blur_in = cfg->has_initial_blur ? cfg->initial_blur * std::pow(2.0f, cfg->upscale) : 0.0f;
+
+    // incremental sigmas: level 0 closes the gap from the assumed input blur to sigma0,
+    // level l >= 1 goes from sigma0*2^((l-1)/L) to sigma0*2^(l/L); all in float.
+    out->inc_sigma[0] = cfg->has_initial_blur ? std::sqrt(std::fabs(s0 * s0 - blur_in * blur_in)) : s0;
+    for (int l = 1; l < planes; ++l) {
+        const float lo = s0 * std::pow(2.0f, static_cast<float>(l - 1) / static_cast<float>(levels));
+        const float hi = s0 * std::pow(2.0f, static_cast<float>(l) / static_cast<float>(levels));
+        out->inc_sigma[l] = std::sqrt(hi * hi - lo * lo);
+    }
+    for (int l = 0; l < PS_GAUSS_LEVELS; ++l)
+        fill_kernel(out->inc_sigma[l], &out->inc_filter[l * PS_GAUSS_ALIGN], &out->inc_span[l]);
+
+    // first horizontal pass over the input image (octave 0): sqrt(|sigma0^2 - blur_in^2|)
+    {
+        const float so = std::scalbn(s0, 0);
+        const float gap = std::sqrt(std::fabs(so * so - blur_in * blur_in));
+        out->dd_sigma0 = std::scalbn(gap, 0);
+        fill_kernel(out->dd_sigma0, out->dd_filter0, &out->dd_span0);
+    }
+    out->peak_threshold = cfg->threshold * 0.5f * 255.0f / static_cast<float>(levels);
+    out->sigma_k = std::pow(2.0f, 1.0f / static_cast<float>(levels));
+    return PS_OK;
+}
+
+extern "C" int ps_geometry(const ps_config* cfg, int w, int h, int32_t* W, int32_t* H)
+{
+    if (!cfg || w <= 0 || h <= 0) return PS_ERR_ARG;
+    const float scale = 1.0f / std::pow(2.0f, -cfg->upscale);
+    int n = cfg->octaves;
+    if (n < 0) {
+        const float lg = std::floor(std::log(static_cast<float>(std::min(w, h))) / std::log(2.0f));
+        n = std::max(static_cast<int>(lg - 3.0f + scale), 1);
+    }
+    n = std::min(n, PS_MAX_OCTAVES);
+    if (n < 1) return PS_ERR_ARG;
+    int ow = static_cast<int>(std::ceil(w * scale));
+    int oh = static_cast<int>(std::ceil(h * scale));
+    for (int o = 0; o < n; ++o) {
+        if (W) W[o] = ow;
+        if (H) H[o] = oh;
+        ow = static_cast<int>(std::ceil(ow / 2.0f));
+        oh = static_cast<int>(std::ceil(oh / 2.0f));
+    }
+    return n;
+}

@@ -1,0 +1,127 @@
+"""CPU-only checks of the product's host side: the C-ABI library loads, exports every symbol
+include/popsift_b200.h declares, and its GPU-free host logic (tables, geometry, Config) agrees with
+the oracle.  No compute call needs a GPU here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from popsift_b200 import api
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "popsift_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(ps_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    L = api.load_library()
+    for name in sorted(declared):
+        assert hasattr(L, name), "libpopsift_b200.so does not export %s" % name
+    assert declared == set(api.EXPORTS)
+    assert L.ps_abi_version() == 1
+
+
+def test_struct_sizes_match_reference_layouts():
+    # popsift::Feature is 72 bytes, Descriptor 512
+    assert api.FEATURE_DTYPE.itemsize == 72
+    assert api.EXTREMUM_DTYPE.itemsize == 44
+    assert C.sizeof(api.PsConfig) == 14 * 4
+
+
+CFGS = [dict(), dict(downsampling=0), dict(levels=4), dict(sigma=1.2, levels=5), dict(initial_blur=0.0),
+        dict(downsampling=-2), dict(levels=2, sigma=2.0)]
+
+
+def _mk(kw):
+    c = api.Config()
+    o = dict(kw)
+    if "downsampling" in o:
+        c.setDownsampling(o["downsampling"])
+    if "levels" in o:
+        c.setLevels(o["levels"])
+    if "sigma" in o:
+        c.setSigma(o["sigma"])
+    if "initial_blur" in o:
+        c.setInitialBlur(o["initial_blur"])
+    oc = ol.make_config(**{k: v for k, v in kw.items() if k != "initial_blur"})
+    if "initial_blur" in kw:
+        oc.initial_blur = kw["initial_blur"]
+        oc.has_initial_blur = 0 if kw["initial_blur"] == 0 else 1
+    return c, oc
+
+
+@pytest.mark.parametrize("kw", CFGS)
+def test_gauss_tables_bit_identical_to_oracle(kw):
+    c, oc = _mk(kw)
+    t = c.gauss_tables()
+    ot = ol.OrcTables()
+    assert ol.lib().orc_compute_tables(C.byref(oc), C.byref(ot)) == 0
+    assert list(t.inc_span) == list(ot.inc.span)
+    assert np.array_equal(np.frombuffer(t.inc_filter, np.uint32), np.frombuffer(ot.inc.filter, np.uint32))
+    assert np.array_equal(np.frombuffer(t.inc_sigma, np.uint32), np.frombuffer(ot.inc.sigma, np.uint32))
+    assert np.array_equal(np.frombuffer(t.dd_filter0, np.uint32), np.frombuffer(ot.dd_filter0, np.uint32))
+    assert t.dd_span0 == ot.dd_span0
+    assert t.peak_threshold == ot.peak_threshold and t.sigma_k == ot.sigma_k
+
+
+def test_default_tables_have_the_surveyed_spans():
+    t = api.Config().gauss_tables()
+    # taps 11,11,15,17,21,27 -> spans 6,6,8,9,11,14
+    assert list(t.inc_span)[:6] == [6, 6, 8, 9, 11, 14]
+    assert abs(t.peak_threshold - 1.7) < 1e-6
+
+
+@pytest.mark.parametrize("w,h,kw,expect", [
+    (640, 480, {}, [(1280, 960), (640, 480), (320, 240), (160, 120), (80, 60), (40, 30), (20, 15)]),
+    (1920, 1080, {}, [(3840, 2160), (1920, 1080), (960, 540), (480, 270), (240, 135), (120, 68), (60, 34), (30, 17), (15, 9)]),
+    (3840, 2160, {"downsampling": 0, "octaves": 5}, [(3840, 2160), (1920, 1080), (960, 540), (480, 270), (240, 135)]),
+    (641, 479, {}, None),
+    (17, 33, {}, None),
+])
+def test_geometry_matches_oracle_and_survey(w, h, kw, expect):
+    c = api.Config()
+    if "downsampling" in kw:
+        c.setDownsampling(kw["downsampling"])
+    if "octaves" in kw:
+        c.setOctaves(kw["octaves"])
+    g = c.geometry(w, h)
+    oc = ol.make_config(**kw)
+    W = (C.c_int32 * 20)()
+    H = (C.c_int32 * 20)()
+    n = ol.lib().orc_geometry(C.byref(oc), w, h, W, H)
+    assert g == [(W[i], H[i]) for i in range(n)]
+    if expect:
+        assert g == expect
+
+
+def test_config_mirrors_reference_semantics():
+    a, b = api.Config(), api.Config()
+    assert a == b
+    b.setDescMode("grid")          # not part of equal() (reference sift_conf.cu:286-304)
+    assert a == b
+    b.setNormMode("classic")
+    assert not (a == b)
+    with pytest.raises(api.PopSiftError):
+        a.setGaussMode("nonsense")
+    with pytest.raises(api.PopSiftError):
+        a.setNormMode("L2")
+    a.setInitialBlur(0.0)
+    assert not a.hasInitialBlur()
+    assert abs(api.Config().getPeakThreshold() - 1.7) < 1e-6
+    c = api.Config(); c.setSigma(2.5)
+    with pytest.raises(api.PopSiftError):
+        c.gauss_tables()           # reference gauss_filter.cu:131-137 rejects sigma > 2
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(api.PopSiftError) as ei:
+        api.PopSift(api.Config(), max_width=64, max_height=64)
+    assert "no CUDA device" in str(ei.value) or "CUDA" in str(ei.value)
