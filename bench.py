@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""Benchmark of the SIFT hot path on B200 (contract in the task description / SURVEY.md 8d).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nproc-per-node N bench.py --gpus N ...          (one rank per GPU, no data-path collective)
+
+Workload ("step") = one pass of the hot path over a batch of FRAMES_PER_STEP synthetic 3840x2160
+8-bit frames per GPU, popsift::Config defaults with octaves=5, levels=3 (BASELINE.json configs[2]:
+octave 0 is the 2x up-scaled 7680x4320 plane).  Frames are independent, so ranks shard them with
+no collective ("weak" scaling: per-GPU batch fixed).
+
+Printed JSON (rank 0, one line):
+  value     Mpixels/s of input pixels, whole job, inputs resident in HBM before the timed region
+            (ps_submit_dev_u8 -> ps_counts -> ps_download: all kernels + result download).
+  e2e       same metric through the public API (PopSift.enqueue -> SiftJob.get) from pinned HOST
+            buffers: host->device copy of every frame and device->host copy of every result inside
+            the timed region.
+  roofline  pyramid stage: algorithmic bytes per frame (68 B per octave-pixel) / CUDA-event
+            time of the pyramid launches of one frame, against the measured HBM peak
+            (MEASURED_PEAKS.json); `dominant_kernel` = the octave-0 fused blur+DoG launches alone.
+  cpu_baseline  the CPU oracle port (oracle/sift_oracle.c, OpenMP) timed on one frame of the workload;
+  opencv_cpu    cv2.SIFT on the same frame, all host cores (the CPU baseline north_star names).
+`--impl reference` times the UNMODIFIED reference PopSift (oracle/_ref, CUDA, built from
+/root/reference) on the same frames through its own public API (host buffers in, host features out).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 3840, 2160
+OCTAVES, LEVELS = 5, 3
+FRAMES_PER_STEP = 8
+SLOTS = 4
+BYTES_PER_OCTAVE_PIXEL = 4 * (3 * LEVELS + 8)     # 68 B
+METRIC = "Mpixels/s SIFT extract @ 3840x2160 gray"
+
+
+def synth_frames(n, rank):
+    """n distinct 4K frames: one generated frame (seed 7 + rank) and shifted/flipped variants."""
+    from popsift_b200.synth import make_frame
+    base = make_frame(W, H, 7 + rank)
+    out = [base]
+    for i in range(1, n):
+        f = np.roll(base, (37 * i, 91 * i), axis=(0, 1))
+        if i & 1:
+            f = f[:, ::-1]
+        if i & 2:
+            f = f[::-1, :]
+        out.append(np.ascontiguousarray(f))
+    return out
+
+
+def octave_pixels():
+    from popsift_b200 import api
+    c = api.Config()
+    c.setOctaves(OCTAVES)
+    return [(w, h) for (w, h) in c.geometry(W, H)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    from popsift_b200 import api
+
+    torch.cuda.set_device(local_rank)
+    L = api.load_library()
+    cfg = api.Config()
+    cfg.setOctaves(OCTAVES)
+    cfg.setLevels(LEVELS)
+    frames = synth_frames(FRAMES_PER_STEP, rank)
+    npix_step = FRAMES_PER_STEP * W * H
+
+    # ---------------- device-resident path (`value`) ----------------
+    ctx = L.ps_create(local_rank, C.byref(cfg._c), W, H, SLOTS)
+    if not ctx:
+        raise SystemExit("ps_create failed: " + L.ps_last_error(None).decode())
+    dev_frames = [torch.from_numpy(f).cuda() for f in frames]
+    feat_buf = np.zeros(200000, dtype=api.FEATURE_DTYPE)
+    desc_buf = np.zeros((200000, 128), dtype=np.float32)
+    nf, nd = C.c_int32(), C.c_int32()
+
+    def chk(rc):
+        if rc != 0:
+            raise SystemExit("popsift_b200 error %d: %s" % (rc, L.ps_last_error(ctx).decode()))
+
+    def step_dev():
+        """FRAMES_PER_STEP frames, SLOTS in flight; every job's features + descriptors land on the host."""
+        tot_f = tot_d = 0
+        inflight = []
+        for i, df in enumerate(dev_frames):
+            s = i % SLOTS
+            if len(inflight) == SLOTS:
+                s0 = inflight.pop(0)
+                chk(L.ps_counts(ctx, s0, C.byref(nf), C.byref(nd)))
+                chk(L.ps_download(ctx, s0, feat_buf.ctypes.data, desc_buf.ctypes.data))
+                tot_f += nf.value; tot_d += nd.value
+            chk(L.ps_submit_dev_u8(ctx, s, df.data_ptr(), W, W, H))
+            inflight.append(s)
+        for s0 in inflight:
+            chk(L.ps_counts(ctx, s0, C.byref(nf), C.byref(nd)))
+            chk(L.ps_download(ctx, s0, feat_buf.ctypes.data, desc_buf.ctypes.data))
+            tot_f += nf.value; tot_d += nd.value
+        return tot_f, tot_d
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.ps_launch_count(ctx)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    slot_streams = [torch.cuda.ExternalStream(L.ps_slot_stream(ctx, s)) for s in range(SLOTS)]
+    tstream = torch.cuda.Stream()
+    with torch.cuda.stream(tstream):
+        ev0.record(tstream)
+    for st in slot_streams:        # the slots' work is ordered after ev0
+        st.wait_event(ev0)
+    t0 = time.perf_counter()
+    counts = (0, 0)
+    for _ in range(args.steps):
+        counts = step_dev()
+    for st in slot_streams:        # ev1 after everything the slots did
+        e = torch.cuda.Event()
+        e.record(st)
+        tstream.wait_event(e)
+    ev1.record(tstream)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = L.ps_launch_count(ctx) - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---------------- roofline of the pyramid stage (same context, slot 0 holds the last frame) ----
+    chk(L.ps_submit_dev_u8(ctx, 0, dev_frames[0].data_ptr(), W, W, H))
+    chk(L.ps_counts(ctx, 0, C.byref(nf), C.byref(nd)))
+    s0 = slot_streams[0]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > L2 (126 MB)
+    pyr_ms, dom_ms = [], []
+    geo = octave_pixels()
+    for it in range(3 + 10):
+        with torch.cuda.stream(s0):
+            flush.fill_(it & 0xff)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(s0)
+        chk(L.ps_run_pyramid_only(ctx, 0))
+        b.record(s0)
+        b.synchronize()
+        if it >= 3:
+            pyr_ms.append(a.elapsed_time(b))
+    for it in range(3 + 10):
+        with torch.cuda.stream(s0):
+            flush.fill_(it & 0xff)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(s0)
+        for lvl in range(1, LEVELS + 3):
+            chk(L.ps_run_level_only(ctx, 0, 0, lvl))
+        b.record(s0)
+        b.synchronize()
+        if it >= 3:
+            dom_ms.append(a.elapsed_time(b) / (LEVELS + 2))
+    L.ps_destroy(ctx)
+    del dev_frames, flush
+    torch.cuda.empty_cache()
+
+    # ---------------- end-to-end path through the public API (host buffers) ----------------
+    pinned = [torch.from_numpy(f).pin_memory().numpy() for f in frames]
+    ps = api.PopSift(cfg, device=local_rank, max_width=W, max_height=H, slots=SLOTS)
+
+    def step_e2e():
+        jobs, tf, td = [], 0, 0
+        for f in pinned:
+            jobs.append(ps.enqueue(W, H, f))
+            if len(jobs) == SLOTS:
+                r = jobs.pop(0).get(); tf += r.getFeatureCount(); td += r.getDescriptorCount()
+        for j in jobs:
+            r = j.get(); tf += r.getFeatureCount(); td += r.getDescriptorCount()
+        return tf, td
+
+    for _ in range(args.warmup):
+        step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t0 = time.perf_counter()
+    ecounts = (0, 0)
+    for _ in range(args.steps):
+        ecounts = step_e2e()
+    e1.record()
+    barrier()
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+    ps.uninit()
+
+    # max over ranks (device-timed `value`; wall-clock for e2e, which includes host work by definition)
+    t = torch.tensor([dev_ms, wall_ms, e2e_wall_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    dev_ms, wall_ms, e2e_wall_ms = [float(x) for x in t.tolist()]
+    total_pix = npix_step * args.steps * world
+    if rank != 0:
+        return None
+
+    peak, peak_src = measured_peak()
+    sum_wh = sum(w * h for w, h in geo)
+    alg_bytes_frame = BYTES_PER_OCTAVE_PIXEL * sum_wh
+    pyr = statistics.median(pyr_ms)
+    dom = statistics.median(dom_ms)
+    dom_bytes = 12 * geo[0][0] * geo[0][1]       # read G[l-1], write G[l], write DoG[l-1]
+    out = {
+        "metric": METRIC, "value": total_pix / (dev_ms * 1e-3) / 1e6, "unit": "Mpixels/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "3840x2160 u8 gray, octaves=5 levels=3, default Config (upscale 2x: octave 0 = 7680x4320), "
+                               "RootSift, desc loop", "frames_per_step_per_gpu": FRAMES_PER_STEP, "slots": SLOTS,
+                   "sharding": "frames across ranks, no collective",
+                   "l2": "working set per frame 3.0 GB of planes >> 126 MB L2; L2 flushed (256 MB fill) before each roofline sample"},
+        "wall_ms_per_step": wall_ms / args.steps,
+        "features_per_step": counts[0], "descriptors_per_step": counts[1],
+        "gpu_launches": int(launches),
+        "e2e": {"value": total_pix / (e2e_wall_ms * 1e-3) / 1e6, "unit": "Mpixels/s",
+                "h2d_bytes_per_step": FRAMES_PER_STEP * W * H,
+                "d2h_bytes_per_step": int(ecounts[0] * 72 + ecounts[1] * 512 + FRAMES_PER_STEP * 128),
+                "api": "popsift_b200.api.PopSift.enqueue -> SiftJob.get (C ABI ps_submit_u8/ps_counts/ps_download), pinned host frames"},
+        "roofline": {"bound": "hbm", "stage": "pyramid (all launches of one frame)", "achieved": alg_bytes_frame / (pyr * 1e-3) / 1e9,
+                     "peak": peak, "unit": "GB/s", "frac": alg_bytes_frame / (pyr * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                     "algorithmic_bytes": alg_bytes_frame, "ms": pyr, "traffic": None,
+                     "dominant_kernel": {"name": "blur_level_kernel (octave 0, levels 1..5, avg per launch)",
+                                         "algorithmic_bytes": dom_bytes, "ms": dom,
+                                         "achieved": dom_bytes / (dom * 1e-3) / 1e9, "frac": dom_bytes / (dom * 1e-3) / 1e9 / peak}},
+        "clocks": clocks,
+    }
+    out.update(cpu_baselines(frames[0]))
+    return out
+
+
+def cpu_baselines(frame):
+    """CPU oracle port + OpenCV SIFT on ONE frame of the workload (bounded sample)."""
+    res = {}
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as ol
+        cores = ol.lib().orc_set_threads(0)
+        o = ol.Oracle(ol.make_config(octaves=OCTAVES), W, H)
+        t = time.perf_counter(); o.run(frame); dt = time.perf_counter() - t
+        nf, nd = o.features()[0].shape[0], o.features()[1].shape[0]
+        res["cpu_baseline"] = {"value": W * H / dt / 1e6, "unit": "Mpixels/s", "cores": cores, "kind": "port",
+                               "sample": "1 frame 3840x2160 of the same workload, oracle/sift_oracle.c (OpenMP), %.2f s, %d features" % (dt, nf)}
+        o.close()
+    except Exception as e:  # the oracle is test infrastructure; its absence must not hide the GPU numbers
+        res["cpu_baseline"] = {"value": None, "unit": "Mpixels/s", "cores": 0, "kind": "port", "sample": "unavailable: %s" % e}
+    try:
+        import cv2
+        n = os.cpu_count() or 1
+        cv2.setNumThreads(n)
+        sift = cv2.SIFT_create(nOctaveLayers=3, contrastThreshold=0.04, edgeThreshold=10, sigma=1.6)
+        sift.detectAndCompute(frame, None)
+        ts = []
+        kp = []
+        for _ in range(3):
+            t = time.perf_counter(); kp, _d = sift.detectAndCompute(frame, None); ts.append(time.perf_counter() - t)
+        dt = statistics.median(ts)
+        res["opencv_cpu"] = {"value": W * H / dt / 1e6, "unit": "Mpixels/s", "cores": n,
+                             "sample": "cv2 %s SIFT_create(3,0.04,10,1.6).detectAndCompute, 1 frame 3840x2160, median of 3, %d keypoints" % (cv2.__version__, len(kp))}
+    except Exception as e:
+        res["opencv_cpu"] = {"value": None, "unit": "Mpixels/s", "cores": 0, "sample": "unavailable: %s" % e}
+    return res
+
+
+def run_reference(args, rank, world, local_rank):
+    """The unmodified reference (CUDA) through its own API; rank 0 only."""
+    if rank != 0:
+        return None
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_dump")
+    if not os.path.exists(exe):
+        return {"impl": "reference", "unavailable": "oracle/_ref/ref_dump not built (needs /root/reference at build time)"}
+    from popsift_b200.synth import write_pgm
+    frames = synth_frames(FRAMES_PER_STEP, 0)
+    with tempfile.TemporaryDirectory() as td:
+        cmd = [exe, "--octaves", str(OCTAVES), "--levels", str(LEVELS), "--device", str(local_rank),
+               "--bench", str(args.steps), str(args.warmup)]
+        for i, f in enumerate(frames):
+            p = os.path.join(td, "f%d.pgm" % i)
+            write_pgm(p, f)
+            cmd += ["-i", p]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=1200)
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    if r.returncode != 0 or not line:
+        return {"impl": "reference", "unavailable": "ref_dump failed: %s" % (r.stderr.strip()[-200:])}
+    j = json.loads(line[-1])
+    v = j["mpix_per_s"]
+    return {"impl": "reference", "metric": METRIC, "value": v, "unit": "Mpixels/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": j["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "3840x2160 u8 gray, octaves=5 levels=3, default Config, RootSift, desc loop",
+                       "frames_per_step_per_gpu": FRAMES_PER_STEP,
+                       "note": "reference PopSift is CUDA-only (no CPU implementation exists); it runs on GPU 0 through "
+                               "PopSift::enqueue/SiftJob::get with host buffers; N>1 is not supported by this arm"},
+            "features_per_step": j["features_last_step"], "descriptors_per_step": j["descriptors_last_step"],
+            "cpu_baseline": {"value": v, "unit": "Mpixels/s", "cores": 2, "kind": "reference",
+                             "sample": "%d frames 3840x2160 per step, unmodified reference libpopsift (oracle/_ref) on the B200, "
+                                       "2 host threads" % FRAMES_PER_STEP},
+            "e2e": {"value": v, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        out = run_reference(args, rank, world, local_rank)
+        if out is not None:
+            print(json.dumps(out), flush=True)
+        return
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product has no CPU path")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        torch.distributed.init_process_group("nccl")
+    out = run_ours(args, rank, world, local_rank)
+    if out is not None:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

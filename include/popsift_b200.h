@@ -161,6 +161,9 @@ int64_t ps_launch_count(const ps_ctx* ctx);
 void* ps_slot_stream(ps_ctx* ctx, int slot);
 /* run only the pyramid stage on the slot's current input (benchmark / roofline hook) */
 int ps_run_pyramid_only(ps_ctx* ctx, int slot);
+/* run ONE pyramid launch on the slot's current planes (roofline hook): level 0 of octave 0 is the
+ * input-image kernel, any other (octave, level >= 1) the fused blur+DoG kernel of that level */
+int ps_run_level_only(ps_ctx* ctx, int slot, int octave, int level);
 
 #ifdef __cplusplus
 }

@@ -50,7 +50,7 @@ assert FEATURE_DTYPE.itemsize == 72 and EXTREMUM_DTYPE.itemsize == 44
 EXPORTS = ["ps_abi_version", "ps_config_default", "ps_gauss_tables_compute", "ps_geometry", "ps_create", "ps_destroy",
            "ps_last_error", "ps_submit_u8", "ps_submit_f32", "ps_submit_dev_u8", "ps_counts", "ps_download",
            "ps_sync", "ps_debug_plane", "ps_debug_extrema", "ps_slot_geometry", "ps_set_timing", "ps_stage_ms",
-           "ps_launch_count", "ps_slot_stream", "ps_run_pyramid_only"]
+           "ps_launch_count", "ps_slot_stream", "ps_run_pyramid_only", "ps_run_level_only"]
 
 _lib = None
 
@@ -89,6 +89,7 @@ def load_library():
     L.ps_slot_stream.restype = C.c_void_p
     L.ps_slot_stream.argtypes = [C.c_void_p, C.c_int]
     L.ps_run_pyramid_only.argtypes = [C.c_void_p, C.c_int]
+    L.ps_run_level_only.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     _lib = L
     return L
 

@@ -18,6 +18,9 @@
 // (the reference also adds the +/-span taps, whose weight is exactly 0).
 // All intrinsics are explicit (__fmaf_rn/__fadd_rn/__fmul_rn) so nvcc cannot re-associate.
 #include "ps_internal.h"
+#include "k_pyramid.h"
+
+#include <cstdlib>
 
 namespace psb {
 
@@ -26,8 +29,6 @@ namespace {
 constexpr int TW = 64;          // output tile width
 constexpr int TH = 32;          // output tile height
 constexpr int NT = 256;         // threads per CTA
-
-struct Taps { float g[PS_GAUSS_ALIGN]; };
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
@@ -276,6 +277,13 @@ int run_level0(const PIX* img, size_t img_pitch, int w, int h, float shift, cons
     return 1;
 }
 
+// POPSIFT_B200_TILE_KERNELS=1 forces the simple tile kernels (debugging / A-B timing)
+bool use_march()
+{
+    static const bool on = [] { const char* e = getenv("POPSIFT_B200_TILE_KERNELS"); return !(e && e[0] == '1'); }();
+    return on;
+}
+
 Taps make_taps(const GaussRow& g)
 {
     Taps t;
@@ -293,6 +301,12 @@ int launch_level0_any(const PIX* img, size_t img_pitch, int w, int h, float upsc
     // both passes use sigma_inc[0]; the two tables have the same span by construction
     const int R = (dd.span > inc0.span ? dd.span : inc0.span) - 1;
     const Taps a = make_taps(dd), b = make_taps(inc0);
+    if (use_march()) {
+        const int r = sizeof(PIX) == 1
+            ? march_level0_u8(reinterpret_cast<const uint8_t*>(img), img_pitch, w, h, shift, o0, a, b, R, st)
+            : march_level0_f32(reinterpret_cast<const float*>(img), img_pitch, w, h, shift, o0, a, b, R, st);
+        if (r >= 0) return r;
+    }
     switch (R) {
 #define PSB_CASE(N) case N: return run_level0<N, PIX>(img, img_pitch, w, h, shift, o0, a, b, st);
         PSB_CASE(1) PSB_CASE(2) PSB_CASE(3) PSB_CASE(4) PSB_CASE(5) PSB_CASE(6) PSB_CASE(7) PSB_CASE(8)
@@ -322,6 +336,10 @@ int launch_blur_level(const OctaveView& o, int level, const GaussRow& g, const O
     const Taps t = make_taps(g);
     float* next0 = next ? next->gauss : nullptr;
     const int next_pitch = next ? next->pitch : 0;
+    if (use_march()) {
+        const int r = march_blur_level(o, level, t, R, next0, next_pitch, st);
+        if (r >= 0) return r;
+    }
     switch (R) {
         case 5:  return run_blur<5>(o, level, t, next0, next_pitch, st);
         case 7:  return run_blur<7>(o, level, t, next0, next_pitch, st);

@@ -1,0 +1,16 @@
+// Shared between the two pyramid translation units.
+#pragma once
+#include "ps_internal.h"
+
+namespace psb {
+
+struct Taps { float g[PS_GAUSS_ALIGN]; };   // one half-kernel, passed by value (constant bank)
+
+// column-marching fast path (k_pyramid_march.cu); return -1 when the radius is not instantiated
+int march_blur_level(const OctaveView& o, int level, const Taps& t, int R, float* next0, int next_pitch, cudaStream_t st);
+int march_level0_u8(const uint8_t* img, size_t img_pitch, int w, int h, float shift, const OctaveView& o0,
+                    const Taps& dd, const Taps& inc0, int R, cudaStream_t st);
+int march_level0_f32(const float* img, size_t img_pitch, int w, int h, float shift, const OctaveView& o0,
+                     const Taps& dd, const Taps& inc0, int R, cudaStream_t st);
+
+} // namespace psb

@@ -1,0 +1,643 @@
+// Stage 1, fast path -- "column-marching" fused Gaussian level kernel for sm_100a.
+//
+// One CTA owns a strip of TW=128 output columns and marches down a segment of rows in chunks of
+// Q=16 rows.  Per chunk:
+//   1. the Q new source rows (+ horizontal halo, clamp-to-edge) are staged in shared memory; they
+//      were prefetched into registers with 128-bit loads while the previous chunk was computed;
+//   2. row pass: thread = (row, 16-column group); a 16+2R wide register window is loaded with
+//      conflict-free LDS.128 (row stride == 4 mod 32) and produces 16 outputs -> ring buffer HB of
+//      row-filtered lines (Q+2R lines);
+//   3. column pass: thread = column; the whole ring column (Q+2R values) is loaded once into
+//      registers and produces the Q output rows that lag the input by R rows: level l, DoG[l-1]
+//      (= out - centre source, still in the staging buffers) and, for level L, the 2:1 decimated
+//      level 0 of the next octave.
+// Every source row is read from HBM once (+2R warm-up rows per segment), every output written once;
+// the row-filtered intermediate never leaves shared memory.  Shared-memory traffic is ~11 floats
+// per pixel at R=13 instead of ~60 for a one-output-per-thread stencil, which is what keeps the
+// FP32 pipe (4R+2 dependent-order FMA/ADD per pixel, fixed by the parity contract) fed.
+//
+// The floating-point evaluation order is exactly the one documented in k_pyramid.cu (taken from the
+// reference's sm_100 SASS); results are bit-identical to the tile kernels and to the reference.
+#include "ps_internal.h"
+#include "k_pyramid.h"
+
+#include <cstdlib>
+#include <mutex>
+#include <set>
+#include <utility>
+
+namespace psb {
+
+namespace {
+
+constexpr int TW = 128;     // output columns per CTA
+constexpr int Q = 16;       // rows per chunk
+constexpr int NT = 128;     // threads per CTA
+constexpr int HBW = TW + 4; // ring-buffer row stride (== 4 mod 32: conflict-free 128-bit row-wise stores)
+
+constexpr int pad4mod32(int v) { return v + ((4 - (v % 32)) + 32) % 32; }
+
+template <int R>
+struct Geo {
+    static constexpr int RP = (R + 3) / 4 * 4;          // halo rounded to float4
+    static constexpr int SW = TW + 2 * RP;              // staged columns per row
+    static constexpr int SWP = pad4mod32(SW);           // stage row stride
+    static constexpr int RING = Q + 2 * R;              // lines in the ring buffer
+    static constexpr int V4 = Q * SW / 4;               // float4 per staged chunk
+    static constexpr int PF = (V4 + NT - 1) / NT;       // float4 prefetch registers per thread
+    static constexpr size_t smem = sizeof(float) * (3 * Q * SWP + RING * HBW);   // 3 staging buffers + ring
+    static_assert(R <= Q, "centre rows must still be in the two staging buffers");
+};
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+// ---- staging: source rows -> registers -> shared -------------------------------------------
+//
+// The float4 a thread moves in slot k of a chunk is the same (row j_k, column group i4_k) for every
+// chunk, so its global offset (relative to the chunk's first row) and its shared-memory offset are
+// computed once per CTA.
+
+template <int R>
+struct StageMap {
+    int goff[Geo<R>::PF];     // j*pitch + (x0 - RP + 4*i4)   (floats; used on the interior fast path)
+    int soff[Geo<R>::PF];     // j*SWP + 4*i4                 (floats)
+};
+
+template <int R>
+__device__ __forceinline__ void make_stage_map(StageMap<R>& m, int pitch, int x0)
+{
+    using G = Geo<R>;
+#pragma unroll
+    for (int k = 0; k < G::PF; ++k) {
+        const int e = threadIdx.x + k * NT;
+        const int j = e / (G::SW / 4);
+        const int i4 = e - j * (G::SW / 4);
+        m.goff[k] = j * pitch + (x0 - G::RP + 4 * i4);
+        m.soff[k] = j * G::SWP + 4 * i4;
+    }
+}
+
+// FASTX: the strip and its halo lie inside the image (aligned 128-bit loads, no column clamp)
+template <int R, bool FASTX>
+__device__ __forceinline__ void prefetch_f32(float4 (&pf)[Geo<R>::PF], const StageMap<R>& m,
+                                             const float* __restrict__ src, int W, int H, int pitch, int iy, int x0)
+{
+    using G = Geo<R>;
+    const bool rows_inside = (iy >= 0) && (iy + Q <= H);
+    if (FASTX && rows_inside) {
+        const float* base = src + (long long)iy * pitch;
+#pragma unroll
+        for (int k = 0; k < G::PF; ++k)
+            if ((k + 1) * NT <= G::V4 || threadIdx.x + k * NT < G::V4)
+                pf[k] = __ldg(reinterpret_cast<const float4*>(base + m.goff[k]));
+    } else {
+#pragma unroll
+        for (int k = 0; k < G::PF; ++k) {
+            if ((k + 1) * NT <= G::V4 || threadIdx.x + k * NT < G::V4) {
+                const int e = threadIdx.x + k * NT;
+                const int j = e / (G::SW / 4);
+                const int gy = clampi(iy + j, 0, H - 1);
+                const float* row = src + (size_t)gy * pitch;
+                const int gx = x0 - G::RP + 4 * (e - j * (G::SW / 4));
+                if (FASTX || (gx >= 0 && gx + 3 < W)) {
+                    pf[k] = __ldg(reinterpret_cast<const float4*>(row + gx));
+                } else {
+                    pf[k].x = __ldg(row + clampi(gx, 0, W - 1));
+                    pf[k].y = __ldg(row + clampi(gx + 1, 0, W - 1));
+                    pf[k].z = __ldg(row + clampi(gx + 2, 0, W - 1));
+                    pf[k].w = __ldg(row + clampi(gx + 3, 0, W - 1));
+                }
+            }
+        }
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void commit_stage(const float4 (&pf)[Geo<R>::PF], const StageMap<R>& m, float* __restrict__ S)
+{
+    using G = Geo<R>;
+#pragma unroll
+    for (int k = 0; k < G::PF; ++k)
+        if ((k + 1) * NT <= G::V4 || threadIdx.x + k * NT < G::V4)
+            *reinterpret_cast<float4*>(S + m.soff[k]) = pf[k];
+}
+
+// interior strip, but some rows of the chunk are outside the image: clamp rows, aligned 128-bit loads
+template <int R, bool FASTX>
+__device__ __forceinline__ void stage_sync(const StageMap<R>& m, const float* __restrict__ src, int W, int H, int pitch,
+                                           int iy, int x0, float* __restrict__ S)
+{
+    using G = Geo<R>;
+#pragma unroll
+    for (int k = 0; k < G::PF; ++k)
+        if ((k + 1) * NT <= G::V4 || threadIdx.x + k * NT < G::V4) {
+            const int e = threadIdx.x + k * NT;
+            const int j = e / (G::SW / 4);
+            const int gy = clampi(iy + j, 0, H - 1);
+            const int gx = x0 - G::RP + 4 * (e - j * (G::SW / 4));
+            *reinterpret_cast<float4*>(S + m.soff[k]) = __ldg(reinterpret_cast<const float4*>(src + (size_t)gy * pitch + gx));
+        }
+}
+
+// ---- row pass: stage -> ring ------------------------------------------------------------------
+
+template <int R, bool LEVEL0>
+__device__ __forceinline__ void row_pass(const float* __restrict__ S, float* __restrict__ HB, int slot0, const Taps& t)
+{
+    using G = Geo<R>;
+    const int j = threadIdx.x & (Q - 1);        // row of the chunk
+    const int g = threadIdx.x >> 4;             // 16-column group (0..7)
+    constexpr int WIN = 16 + 2 * G::RP;
+    float w[WIN];
+    const float* p = S + j * G::SWP + 16 * g;
+#pragma unroll
+    for (int m = 0; m < WIN / 4; ++m) {
+        const float4 v = *reinterpret_cast<const float4*>(p + 4 * m);
+        w[4 * m] = v.x; w[4 * m + 1] = v.y; w[4 * m + 2] = v.z; w[4 * m + 3] = v.w;
+    }
+    int slot = slot0 + j;
+    if (slot >= G::RING) slot -= G::RING;
+    float* o = HB + slot * HBW + 16 * g;
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+        float r[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int c = 4 * q4 + u + G::RP;       // centre index in the window
+            float acc;
+            if (LEVEL0) {
+                acc = 0.0f;
+#pragma unroll
+                for (int off = R; off > 0; --off) acc = __fmaf_rn(__fadd_rn(w[c - off], w[c + off]), t.g[off], acc);
+                acc = __fmaf_rn(w[c], t.g[0], acc);
+                acc = __fmul_rn(acc, 255.0f);
+            } else {
+                acc = __fmaf_rn(w[c], t.g[0], 0.0f);
+#pragma unroll
+                for (int off = R; off > 0; --off) acc = __fmaf_rn(__fadd_rn(w[c - off], w[c + off]), t.g[off], acc);
+            }
+            r[u] = acc;
+        }
+        *reinterpret_cast<float4*>(o + 4 * q4) = make_float4(r[0], r[1], r[2], r[3]);
+    }
+}
+
+// ---- column pass: ring -> outputs ------------------------------------------------------------
+//
+// Thread = (pair of adjacent columns, half of the chunk's rows).  Both columns ride in one 64-bit
+// register pair, so every tap is ONE packed FFMA2 (fma.rn.f32x2; the tap weight is a scalar
+// uniform-register operand): half the FP32 issue slots of the scalar form, identical IEEE results.
+
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+
+constexpr int QH = Q / 2;   // output rows per thread in the column pass
+
+template <int R, bool WRITE_DOG, bool NEXT, bool GUARD>
+__device__ __forceinline__ void col_emit(const f32x2 (&win)[QH + 2 * R], const float* __restrict__ Scur,
+                                         const float* __restrict__ Sprev, int jbase, int y_first, int ys, int ye,
+                                         float* __restrict__ pd, float* __restrict__ pg, float* __restrict__ pn,
+                                         int pitch, int next_pitch, const Taps& t)
+{
+    using G = Geo<R>;
+    const int c2 = 2 * (threadIdx.x & 63);
+    const int par = y_first & 1;
+#pragma unroll
+    for (int jj = 0; jj < QH; ++jj) {
+        f32x2 acc = pack2(0.0f, 0.0f);
+#pragma unroll
+        for (int off = R; off > 0; --off) {
+            const f32x2 g2 = pack2(t.g[off], t.g[off]);
+            acc = fma2(win[jj + R - off], g2, acc);
+            acc = fma2(win[jj + R + off], g2, acc);
+        }
+        acc = fma2(win[jj + R], pack2(t.g[0], t.g[0]), acc);
+        const int j = jbase + jj;                       // row of the chunk's output block (0..Q-1)
+        const bool ok = !GUARD || (y_first + j >= ys && y_first + j < ye);
+        if (ok) {
+            *reinterpret_cast<f32x2*>(pd) = acc;
+            float a0, a1;
+            unpack2(acc, a0, a1);
+            if (WRITE_DOG) {
+                // centre source row: chunk-relative row j-R lives in the current (j >= R) or previous buffer
+                const float* cp = (j >= R) ? Scur + (j - R) * G::SWP : Sprev + (j - R + Q) * G::SWP;
+                const float2 cs = *reinterpret_cast<const float2*>(cp + G::RP + c2);
+                *reinterpret_cast<float2*>(pg) = make_float2(__fsub_rn(a0, cs.x), __fsub_rn(a1, cs.y));
+            }
+            if (NEXT && ((j & 1) == par)) pn[(size_t)((y_first + j) >> 1) * next_pitch] = a0;
+        }
+        pd += pitch;
+        if (WRITE_DOG) pg += pitch;
+    }
+}
+
+template <int R, bool WRITE_DOG, bool NEXT>
+__device__ __forceinline__ void col_pass(const float* __restrict__ HB, const float* __restrict__ Scur,
+                                         const float* __restrict__ Sprev, int slot_oldest, int y_first,
+                                         int ys, int ye, int x0, int W, float* __restrict__ dst, float* __restrict__ dog,
+                                         float* __restrict__ next0, int pitch, int next_pitch, const Taps& t)
+{
+    using G = Geo<R>;
+    const int c2 = 2 * (threadIdx.x & 63);
+    const int jbase = (threadIdx.x >> 6) * QH;          // 0 or Q/2 (warp-uniform)
+    f32x2 win[QH + 2 * R];
+    int first = slot_oldest + jbase;                    // ring slot of the first window line (warp-uniform)
+    if (first >= G::RING) first -= G::RING;
+    // the window wraps around the ring at most once: lines before the wrap use base a0, the others a1,
+    // both with compile-time offsets
+    const int nw = G::RING - first;
+    const float* a0 = HB + first * HBW + c2;
+    const float* a1 = a0 - G::RING * HBW;
+#pragma unroll
+    for (int i = 0; i < QH + 2 * R; ++i)
+        win[i] = *reinterpret_cast<const f32x2*>((i < nw ? a0 : a1) + i * HBW);
+    const int x = x0 + c2;
+    if (x >= W) return;
+    const int yb = y_first + jbase;
+    if (yb + QH <= ys || yb >= ye) return;                     // nothing of this half-block is inside the segment
+    const long long o = (long long)yb * pitch + x;             // may be negative for guarded rows (never dereferenced)
+    float* pd = dst + o;
+    float* pg = WRITE_DOG ? dog + o : nullptr;
+    float* pn = NEXT ? next0 + (x >> 1) : nullptr;
+    if (yb >= ys && yb + QH <= ye)
+        col_emit<R, WRITE_DOG, NEXT, false>(win, Scur, Sprev, jbase, y_first, ys, ye, pd, pg, pn, pitch, next_pitch, t);
+    else
+        col_emit<R, WRITE_DOG, NEXT, true>(win, Scur, Sprev, jbase, y_first, ys, ye, pd, pg, pn, pitch, next_pitch, t);
+}
+
+// asynchronous global->shared copy of one chunk (interior strips, rows inside the image)
+template <int R>
+__device__ __forceinline__ void stage_async(const StageMap<R>& m, const float* __restrict__ src, int pitch, int iy,
+                                            float* __restrict__ S)
+{
+    using G = Geo<R>;
+    const float* base = src + (long long)iy * pitch;
+#pragma unroll
+    for (int k = 0; k < G::PF; ++k)
+        if ((k + 1) * NT <= G::V4 || threadIdx.x + k * NT < G::V4) {
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(S + m.soff[k]);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(base + m.goff[k]) : "memory");
+        }
+}
+
+template <int R, bool FASTX, bool NEXT, bool ASYNC>
+__device__ __forceinline__ void march_body(float* __restrict__ smem, const float* __restrict__ src, float* __restrict__ dst,
+                                           float* __restrict__ dog, float* __restrict__ next0, int W, int H, int pitch,
+                                           int next_pitch, int x0, int ys, int ye, const Taps& taps)
+{
+    using G = Geo<R>;
+    constexpr int SB = Q * G::SWP;         // floats per staging buffer (buffer b starts at smem + b*SB)
+    float* HB = smem + 3 * SB;
+    const int nchunks = (ye - ys + 2 * R + Q - 1) / Q;
+
+    StageMap<R> map;
+    make_stage_map<R>(map, pitch, x0);
+    // Staging of chunk k+1 overlaps the computation of chunk k.  Interior strips with all rows inside the
+    // image use cp.async straight into the third staging buffer; everything else (edge strips, clamped
+    // rows) goes through registers (prefetch -> commit).
+    auto rows_inside = [&](int iy) { return iy >= 0 && iy + Q <= H; };
+    constexpr bool REGS = !FASTX || !ASYNC;     // stage through registers (prefetch -> commit)
+    float4 pf[REGS ? G::PF : 1];
+    bool in_regs;
+    {
+        const int iy = ys - R;
+        if constexpr (!REGS) {
+            if (rows_inside(iy)) stage_async<R>(map, src, pitch, iy, smem);
+            else stage_sync<R, true>(map, src, W, H, pitch, iy, x0, smem);
+            in_regs = false;
+        } else { prefetch_f32<R, FASTX>(pf, map, src, W, H, pitch, iy, x0); in_regs = true; }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    int slot_in = 0;                     // ring slot of the chunk's first input row
+    int cur = 0;                         // staging buffer of chunk k
+    for (int k = 0; k < nchunks; ++k) {
+        float* Scur = smem + cur * SB;
+        float* Sprev = smem + (cur == 0 ? 2 : cur - 1) * SB;
+        const int nxt = cur == 2 ? 0 : cur + 1;
+        if constexpr (REGS) { if (in_regs) commit_stage<R>(pf, map, Scur); }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                  // chunk k staged; column pass k-1 finished (ring + buffer `nxt` are free)
+        if (k + 1 < nchunks) {
+            const int iy = ys - R + (k + 1) * Q;
+            if constexpr (!REGS) {
+                if (rows_inside(iy)) stage_async<R>(map, src, pitch, iy, smem + nxt * SB);
+                else stage_sync<R, true>(map, src, W, H, pitch, iy, x0, smem + nxt * SB);
+            } else { prefetch_f32<R, FASTX>(pf, map, src, W, H, pitch, iy, x0); in_regs = true; }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        row_pass<R, false>(Scur, HB, slot_in, taps);
+        __syncthreads();
+        int slot_old = slot_in + Q;       // oldest line = the one after the newest
+        if (slot_old >= G::RING) slot_old -= G::RING;
+        col_pass<R, true, NEXT>(HB, Scur, Sprev, slot_old, ys - 2 * R + k * Q, ys, ye, x0, W, dst, dog, next0, pitch, next_pitch, taps);
+        slot_in = slot_old;
+        cur = nxt;
+    }
+    __syncthreads();                      // the next sub-segment reuses the buffers
+}
+
+// Work partition: strips of TW columns x segments of whole chunk-rows (Q rows), ONE wave of CTAs
+// (148 SMs x 4 resident CTAs).  CTA b handles strip b % strips, segment b / strips: CTAs that run
+// side by side touch the same image rows, so every DRAM page of a row is streamed by neighbouring
+// CTAs at about the same time (a strip-major split of the same work measured ~30 % slower).
+struct Partition { int strips, C, seg_units, B; };
+
+template <int R, bool ASYNC, bool NEXT>
+__global__ void __launch_bounds__(NT, 4)
+march_level_kernel(const float* __restrict__ src, float* __restrict__ dst, float* __restrict__ dog,
+                   float* __restrict__ next0, int W, int H, int pitch, int next_pitch, Partition part, Taps taps)
+{
+    using G = Geo<R>;
+    extern __shared__ __align__(16) float smem[];
+    const int strip = blockIdx.x % part.strips;
+    const int seg = blockIdx.x / part.strips;
+    const int x0 = strip * TW;
+    const int ys = seg * part.seg_units * Q;
+    const int ye = min(H, ys + part.seg_units * Q);
+    const bool fast = (x0 - G::RP >= 0) && (x0 + TW + G::RP <= W);
+    if (fast) march_body<R, true, NEXT, ASYNC>(smem, src, dst, dog, next0, W, H, pitch, next_pitch, x0, ys, ye, taps);
+    else      march_body<R, false, NEXT, ASYNC>(smem, src, dst, dog, next0, W, H, pitch, next_pitch, x0, ys, ye, taps);
+}
+
+// ---- octave 0, level 0 from the input image -----------------------------------------------------
+
+struct AxisTap { int i0, i1, a; };
+
+__device__ __forceinline__ AxisTap virt_axis(int X, float shift, int N0, int n)
+{   // see k_pyramid.cu: the measured behaviour of the reference's input texture
+    float f = __fmul_rn(__fdiv_rn(__fadd_rn((float)X, shift), (float)N0), (float)n) - 0.5f;
+    f = fminf(fmaxf(f, -0.5f), (float)n - 0.5f);
+    const float fl = floorf(f);
+    int i = (int)fl;
+    int a = (int)floorf(__fmaf_rn(f - fl, 256.0f, 0.5f));
+    if (a == 256) { a = 0; i += 1; }
+    AxisTap t;
+    t.i0 = clampi(i, 0, n - 1);
+    t.i1 = clampi(i + 1, 0, n - 1);
+    t.a = a;
+    return t;
+}
+
+// unorm16 -> float exactly as the texture unit: (float)r16 / 65535.0f, correctly rounded.
+// int->float through the 2^23 trick and a 3-instruction division (q = x*c; q += c*fma(-q, 65535, x))
+// that is exact for every r16 in [0, 65535] (exhaustively checked, tests/test_host_cpu.py).
+__device__ __forceinline__ float unorm16_to_float(unsigned r16)
+{
+    const float x = __fsub_rn(__uint_as_float(0x4B000000u | r16), 8388608.0f);
+    const float c = __uint_as_float(0x37800080u);      // RN(1/65535)
+    const float q = __fmul_rn(x, c);
+    const float rem = __fmaf_rn(-q, 65535.0f, x);
+    return __fmaf_rn(rem, c, q);
+}
+
+constexpr int NS2 = Q / 2 + 2;   // source rows a chunk of Q virtual rows can touch in the exact-2x case
+
+// X2 = true: 8-bit input, octave 0 is exactly the 2x up-scaled image (default Config: W == 2w, H == 2h,
+// shift == 1).  The virtual texture sample then only depends on the SUM s4 of the 2x2 source texels
+// {r0,r1} x {c0,c1} (indices repeated when a fraction is 0): r16 = (257*s4 + 2) >> 2.  The sums are
+// built in two cheap steps (row sums Hs, then column sums) instead of a general bilinear blend.
+template <int R, typename PIX, bool X2>
+__device__ __forceinline__ void level0_body(float* __restrict__ smem, AxisTap* __restrict__ ax, AxisTap* __restrict__ ay,
+                                            unsigned short (* __restrict__ Hs)[Geo<R>::SW],
+                                            const PIX* __restrict__ img, size_t img_pitch, int w, int h, float shift,
+                                            float* __restrict__ dst, int W, int H, int pitch, int x0, int ys, int ye,
+                                            const Taps& dd, const Taps& inc0)
+{
+    using G = Geo<R>;
+    float* S0 = smem;
+    float* S1 = smem + Q * G::SWP;
+    float* HB = smem + 3 * Q * G::SWP;
+    const int nchunks = (ye - ys + 2 * R + Q - 1) / Q;
+    constexpr int TAIL = G::SW - NT;          // columns beyond the first NT (= 2*RP)
+
+    for (int i = threadIdx.x; i < G::SW; i += NT) {
+        const int X = x0 - G::RP + i;
+        if (X2) {
+            AxisTap t;
+            t.i0 = clampi(X >> 1, 0, w - 1);
+            t.i1 = clampi((X + 1) >> 1, 0, w - 1);
+            t.a = 0;
+            ax[i] = t;
+        } else {
+            ax[i] = virt_axis(X, shift, W, w);
+        }
+    }
+    __syncthreads();
+    // this thread's main column and (for X2) its two source columns
+    const int ci = threadIdx.x;
+    const int c0 = X2 ? ax[ci].i0 : 0, c1 = X2 ? ax[ci].i1 : 0;
+
+    int slot_in = 0;
+    for (int k = 0; k < nchunks; ++k) {
+        float* Scur = (k & 1) ? S1 : S0;
+        const int iy = ys - R + k * Q;
+        if (X2) {
+            // step A: row sums of the source rows this chunk touches (thread = column, rows unrolled)
+            const int vy0 = clampi(iy, 0, H - 1);
+            const int rmin = vy0 >> 1;
+#pragma unroll
+            for (int r = 0; r < NS2; ++r) {
+                const PIX* row = img + (size_t)min(rmin + r, h - 1) * img_pitch;
+                Hs[r][ci] = (unsigned short)((unsigned)row[c0] + (unsigned)row[c1]);
+            }
+            for (int e = threadIdx.x; e < NS2 * TAIL; e += NT) {
+                const int r = e / TAIL;
+                const int i = NT + (e - r * TAIL);
+                const PIX* row = img + (size_t)min(rmin + r, h - 1) * img_pitch;
+                const AxisTap tx = ax[i];
+                Hs[r][i] = (unsigned short)((unsigned)row[tx.i0] + (unsigned)row[tx.i1]);
+            }
+            __syncthreads();
+            // step B: column sums -> unorm16 -> float (row indices are warp-uniform)
+#pragma unroll
+            for (int j = 0; j < Q; ++j) {
+                const int vy = clampi(iy + j, 0, H - 1);
+                const int ra = (vy >> 1) - rmin;
+                const int rb = min((vy + 1) >> 1, h - 1) - rmin;
+                const unsigned s4 = (unsigned)Hs[ra][ci] + (unsigned)Hs[rb][ci];
+                Scur[j * G::SWP + ci] = unorm16_to_float((257u * s4 + 2u) >> 2);
+            }
+            for (int e = threadIdx.x; e < Q * TAIL; e += NT) {
+                const int j = e / TAIL;
+                const int i = NT + (e - j * TAIL);
+                const int vy = clampi(iy + j, 0, H - 1);
+                const int ra = (vy >> 1) - rmin;
+                const int rb = min((vy + 1) >> 1, h - 1) - rmin;
+                const unsigned s4 = (unsigned)Hs[ra][i] + (unsigned)Hs[rb][i];
+                Scur[j * G::SWP + i] = unorm16_to_float((257u * s4 + 2u) >> 2);
+            }
+        } else {
+            // rows outside the octave clamp to the border row of the row-filtered plane
+            if (threadIdx.x < Q) ay[threadIdx.x] = virt_axis(clampi(iy + threadIdx.x, 0, H - 1), shift, H, h);
+            __syncthreads();
+            for (int e = threadIdx.x; e < Q * G::SW; e += NT) {
+                const int j = e / G::SW;
+                const int i = e - j * G::SW;
+                const AxisTap ty = ay[j];
+                const AxisTap tx = ax[i];
+                const PIX* r0 = img + (size_t)ty.i0 * img_pitch;
+                const PIX* r1 = img + (size_t)ty.i1 * img_pitch;
+                float v;
+                if (sizeof(PIX) == 1) {
+                    const unsigned t00 = (unsigned)r0[tx.i0], t10 = (unsigned)r0[tx.i1];
+                    const unsigned t01 = (unsigned)r1[tx.i0], t11 = (unsigned)r1[tx.i1];
+                    const unsigned wx1 = tx.a, wx0 = 256u - wx1, wy1 = ty.a, wy0 = 256u - wy1;
+                    const unsigned num = wx0 * wy0 * t00 + wx1 * wy0 * t10 + wx0 * wy1 * t01 + wx1 * wy1 * t11;
+                    v = unorm16_to_float((num * 257u + 32768u) >> 16);
+                } else {
+                    const float fx = (float)tx.a * (1.0f / 256.0f), fy = (float)ty.a * (1.0f / 256.0f);
+                    const float top = __fmaf_rn(fx, (float)r0[tx.i1] - (float)r0[tx.i0], (float)r0[tx.i0]);
+                    const float bot = __fmaf_rn(fx, (float)r1[tx.i1] - (float)r1[tx.i0], (float)r1[tx.i0]);
+                    v = __fmaf_rn(fy, bot - top, top);
+                }
+                Scur[j * G::SWP + i] = v;
+            }
+        }
+        __syncthreads();
+        row_pass<R, true>(Scur, HB, slot_in, dd);
+        __syncthreads();
+        int slot_old = slot_in + Q;
+        if (slot_old >= G::RING) slot_old -= G::RING;
+        col_pass<R, false, false>(HB, Scur, Scur, slot_old, ys - 2 * R + k * Q, ys, ye, x0, W, dst, nullptr, nullptr, pitch, 0, inc0);
+        slot_in = slot_old;
+        __syncthreads();
+    }
+}
+
+template <int R, typename PIX, bool X2>
+__global__ void __launch_bounds__(NT)
+march_level0_kernel(const PIX* __restrict__ img, size_t img_pitch, int w, int h, float shift,
+                    float* __restrict__ dst, int W, int H, int pitch, Partition part, Taps dd, Taps inc0)
+{
+    using G = Geo<R>;
+    extern __shared__ __align__(16) float smem[];
+    __shared__ AxisTap ax[G::SW];
+    __shared__ AxisTap ay[Q];
+    __shared__ unsigned short Hs[X2 ? NS2 : 1][G::SW];
+    const int strip = blockIdx.x % part.strips;
+    const int seg = blockIdx.x / part.strips;
+    const int ys = seg * part.seg_units * Q;
+    level0_body<R, PIX, X2>(smem, ax, ay, Hs, img, img_pitch, w, h, shift, dst, W, H, pitch, strip * TW, ys,
+                            min(H, ys + part.seg_units * Q), dd, inc0);
+}
+
+// ---- launch helpers ---------------------------------------------------------------------------
+
+Partition make_partition(int W, int H)
+{
+    Partition p;
+    p.strips = (W + TW - 1) / TW;
+    p.C = (H + Q - 1) / Q;
+    int segments = 592 / p.strips;                 // one wave: 148 SMs x 4 resident CTAs
+    if (segments < 1) segments = 1;
+    p.seg_units = (p.C + segments - 1) / segments;
+    if (p.seg_units < 4) p.seg_units = 4;          // keep the 2R-row warm-up a small fraction of the work
+    segments = (p.C + p.seg_units - 1) / p.seg_units;
+    p.B = p.strips * segments;
+    return p;
+}
+
+// opt in to > 48 KB dynamic shared memory once per (kernel, device)
+template <typename K>
+void ensure_smem(K kernel, size_t bytes)
+{
+    static std::mutex mu;
+    static std::set<std::pair<const void*, int>> done;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const std::pair<const void*, int> key(reinterpret_cast<const void*>(kernel), dev);
+    std::lock_guard<std::mutex> g(mu);
+    if (done.insert(key).second)
+        {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        }
+}
+
+// interior strips are staged with cp.async (default); POPSIFT_B200_ASYNC=0 selects the register
+// prefetch path for A/B timing
+bool async_choice()
+{
+    static const bool v = [] { const char* e = getenv("POPSIFT_B200_ASYNC"); return !(e && e[0] == '0'); }();
+    return v;
+}
+
+template <int R, bool ASYNC, bool NEXT>
+void launch_march(const Partition& part, const float* src, float* dst, float* dog, float* next0, const OctaveView& o,
+                  int next_pitch, const Taps& t, cudaStream_t st)
+{
+    ensure_smem(march_level_kernel<R, ASYNC, NEXT>, Geo<R>::smem);
+    march_level_kernel<R, ASYNC, NEXT><<<part.B, NT, Geo<R>::smem, st>>>(src, dst, dog, next0, o.w, o.h, o.pitch, next_pitch, part, t);
+}
+
+template <int R>
+int run_march(const OctaveView& o, int level, const Taps& t, float* next0, int next_pitch, cudaStream_t st)
+{
+    const Partition part = make_partition(o.w, o.h);
+    const float* src = o.gauss + o.plane * (level - 1);
+    float* dst = o.gauss + o.plane * level;
+    float* dog = o.dog + o.plane * (level - 1);
+    const bool as = async_choice();
+    if (next0) { if (as) launch_march<R, true, true>(part, src, dst, dog, next0, o, next_pitch, t, st);
+                 else    launch_march<R, false, true>(part, src, dst, dog, next0, o, next_pitch, t, st); }
+    else       { if (as) launch_march<R, true, false>(part, src, dst, dog, next0, o, next_pitch, t, st);
+                 else    launch_march<R, false, false>(part, src, dst, dog, next0, o, next_pitch, t, st); }
+    return 1;
+}
+
+template <int R, typename PIX>
+int run_march0(const PIX* img, size_t img_pitch, int w, int h, float shift, const OctaveView& o0, const Taps& dd,
+               const Taps& inc0, cudaStream_t st)
+{
+    const Partition part = make_partition(o0.w, o0.h);
+    const bool x2 = sizeof(PIX) == 1 && shift == 1.0f && o0.w == 2 * w && o0.h == 2 * h;
+    if (x2) {
+        ensure_smem(march_level0_kernel<R, PIX, true>, Geo<R>::smem);
+        march_level0_kernel<R, PIX, true><<<part.B, NT, Geo<R>::smem, st>>>(img, img_pitch, w, h, shift, o0.gauss, o0.w, o0.h,
+                                                                           o0.pitch, part, dd, inc0);
+    } else {
+        ensure_smem(march_level0_kernel<R, PIX, false>, Geo<R>::smem);
+        march_level0_kernel<R, PIX, false><<<part.B, NT, Geo<R>::smem, st>>>(img, img_pitch, w, h, shift, o0.gauss, o0.w, o0.h,
+                                                                            o0.pitch, part, dd, inc0);
+    }
+    return 1;
+}
+
+} // namespace
+
+int march_blur_level(const OctaveView& o, int level, const Taps& t, int R, float* next0, int next_pitch, cudaStream_t st)
+{
+    switch (R) {
+#define PSB_CASE(N) case N: return run_march<N>(o, level, t, next0, next_pitch, st);
+        PSB_CASE(3) PSB_CASE(4) PSB_CASE(5) PSB_CASE(6) PSB_CASE(7) PSB_CASE(8) PSB_CASE(9) PSB_CASE(10)
+        PSB_CASE(11) PSB_CASE(12) PSB_CASE(13) PSB_CASE(14) PSB_CASE(15) PSB_CASE(16)
+#undef PSB_CASE
+        default: return -1;
+    }
+}
+
+int march_level0_u8(const uint8_t* img, size_t img_pitch, int w, int h, float shift, const OctaveView& o0,
+                    const Taps& dd, const Taps& inc0, int R, cudaStream_t st)
+{
+    switch (R) {
+#define PSB_CASE(N) case N: return run_march0<N, uint8_t>(img, img_pitch, w, h, shift, o0, dd, inc0, st);
+        PSB_CASE(3) PSB_CASE(4) PSB_CASE(5) PSB_CASE(6) PSB_CASE(7) PSB_CASE(8) PSB_CASE(9)
+#undef PSB_CASE
+        default: return -1;
+    }
+}
+
+int march_level0_f32(const float* img, size_t img_pitch, int w, int h, float shift, const OctaveView& o0,
+                     const Taps& dd, const Taps& inc0, int R, cudaStream_t st)
+{
+    switch (R) {
+#define PSB_CASE(N) case N: return run_march0<N, float>(img, img_pitch, w, h, shift, o0, dd, inc0, st);
+        PSB_CASE(3) PSB_CASE(4) PSB_CASE(5) PSB_CASE(6) PSB_CASE(7) PSB_CASE(8) PSB_CASE(9)
+#undef PSB_CASE
+        default: return -1;
+    }
+}
+
+} // namespace psb

@@ -13,6 +13,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -26,6 +27,9 @@ thread_local std::string g_create_error;
 
 struct Slot {
     cudaStream_t stream = nullptr;
+    cudaStream_t side = nullptr;      // levels L+1, L+2 of an octave run here, beside the next octave
+    cudaEvent_t  ev_fork[kMaxOctaves] = {};
+    cudaEvent_t  ev_join = nullptr;
     // input
     uint8_t* d_img = nullptr;      // max_w*max_h*4 bytes (u8 or f32 images)
     uint8_t* h_img = nullptr;      // pinned staging, same size
@@ -126,9 +130,20 @@ int build_view(ps_ctx* ctx, Slot& s, int w, int h)
     return PS_OK;
 }
 
+// POPSIFT_B200_FORK=0 keeps the whole pyramid on one stream (A/B switch)
+bool fork_choice()
+{
+    static const bool v = [] { const char* e = getenv("POPSIFT_B200_FORK"); return !(e && e[0] == '0'); }();
+    return v;
+}
+
+// Dependency graph of the pyramid: within an octave level l needs level l-1; octave o+1 needs only level L
+// of octave o.  Levels L+1 and L+2 of octave o are therefore issued on the slot's side stream and overlap
+// the (much smaller) next octaves, which would otherwise run alone at a fraction of the GPU.
 int run_pyramid(ps_ctx* ctx, Slot& s)
 {
     const int L = ctx->levels;
+    const bool fork = fork_choice() && s.num_octaves > 1;
     int n = 0, r;
     if (s.is_float)
         r = launch_level0_f32(reinterpret_cast<const float*>(s.d_img), (size_t)s.w, s.w, s.h, ctx->cfg.upscale,
@@ -138,13 +153,29 @@ int run_pyramid(ps_ctx* ctx, Slot& s)
                              ctx->dd0, ctx->rows[0], s.stream);
     if (r < 0) return ctx->fail(PS_ERR_ARG, "unsupported level-0 filter span %d", ctx->dd0.span);
     n += r;
-    for (int o = 0; o < s.num_octaves; ++o)
+    bool forked = false;
+    for (int o = 0; o < s.num_octaves; ++o) {
+        const bool last = (o + 1 == s.num_octaves);
         for (int l = 1; l < L + 3; ++l) {
-            const OctaveView* next = (l == L && o + 1 < s.num_octaves) ? &s.view.oct[o + 1] : nullptr;
-            r = launch_blur_level(s.view.oct[o], l, ctx->rows[l], next, s.stream);
+            const OctaveView* next = (l == L && !last) ? &s.view.oct[o + 1] : nullptr;
+            cudaStream_t st = s.stream;
+            if (fork && !last && l > L) {
+                if (l == L + 1) {
+                    PS_CUDA(ctx, cudaEventRecord(s.ev_fork[o], s.stream));
+                    PS_CUDA(ctx, cudaStreamWaitEvent(s.side, s.ev_fork[o], 0));
+                    forked = true;
+                }
+                st = s.side;
+            }
+            r = launch_blur_level(s.view.oct[o], l, ctx->rows[l], next, st);
             if (r < 0) return ctx->fail(PS_ERR_ARG, "unsupported filter span %d", ctx->rows[l].span);
             n += r;
         }
+    }
+    if (forked) {
+        PS_CUDA(ctx, cudaEventRecord(s.ev_join, s.side));
+        PS_CUDA(ctx, cudaStreamWaitEvent(s.stream, s.ev_join, 0));
+    }
     ctx->launches += n;
     PS_CUDA(ctx, cudaGetLastError());
     return PS_OK;
@@ -199,6 +230,9 @@ extern "C" void ps_destroy(ps_ctx* ctx)
         cudaFreeHost(s.h_feat); cudaFreeHost(s.h_desc);
         for (auto& e : s.ev) if (e) cudaEventDestroy(e);
         if (s.done) cudaEventDestroy(s.done);
+        for (auto& e : s.ev_fork) if (e) cudaEventDestroy(e);
+        if (s.ev_join) cudaEventDestroy(s.ev_join);
+        if (s.side) cudaStreamDestroy(s.side);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     delete ctx;
@@ -259,6 +293,9 @@ extern "C" ps_ctx* ps_create(int device, const ps_config* cfg, int max_w, int ma
     for (Slot& s : ctx->slots) {
 #define PS_TRY(call) if ((e = (call)) != cudaSuccess) { std::string m = #call; ps_destroy(ctx); return bail(m.c_str(), e); }
         PS_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        PS_TRY(cudaStreamCreateWithFlags(&s.side, cudaStreamNonBlocking));
+        for (auto& ev : s.ev_fork) PS_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        PS_TRY(cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming));
         PS_TRY(cudaMalloc(&s.d_img, (size_t)max_w * max_h * 4));
         PS_TRY(cudaHostAlloc(&s.h_img, (size_t)max_w * max_h * 4, cudaHostAllocDefault));
         PS_TRY(cudaMalloc(&s.d_planes, planes * sizeof(float)));
@@ -477,4 +514,29 @@ extern "C" int ps_run_pyramid_only(ps_ctx* ctx, int slot)
     if (!s->submitted) return ctx->fail(PS_ERR_STATE, "ps_run_pyramid_only: nothing submitted");
     PS_CUDA(ctx, cudaSetDevice(ctx->device));
     return run_pyramid(ctx, *s);
+}
+
+extern "C" int ps_run_level_only(ps_ctx* ctx, int slot, int octave, int level)
+{
+    Slot* s = get_slot(ctx, slot);
+    if (!s) return PS_ERR_ARG;
+    if (!s->submitted) return ctx->fail(PS_ERR_STATE, "ps_run_level_only: nothing submitted");
+    const int L = ctx->levels;
+    if (octave < 0 || octave >= s->num_octaves || level < 0 || level >= L + 3 || (level == 0 && octave != 0))
+        return ctx->fail(PS_ERR_ARG, "ps_run_level_only: bad octave/level %d/%d", octave, level);
+    PS_CUDA(ctx, cudaSetDevice(ctx->device));
+    int r;
+    if (level == 0) {
+        r = s->is_float ? launch_level0_f32(reinterpret_cast<const float*>(s->d_img), (size_t)s->w, s->w, s->h, ctx->cfg.upscale,
+                                            ctx->cfg.sift_mode, s->view.oct[0], ctx->dd0, ctx->rows[0], s->stream)
+                        : launch_level0_u8(s->d_img, (size_t)s->w, s->w, s->h, ctx->cfg.upscale, ctx->cfg.sift_mode,
+                                           s->view.oct[0], ctx->dd0, ctx->rows[0], s->stream);
+    } else {
+        const OctaveView* next = (level == L && octave + 1 < s->num_octaves) ? &s->view.oct[octave + 1] : nullptr;
+        r = launch_blur_level(s->view.oct[octave], level, ctx->rows[level], next, s->stream);
+    }
+    if (r < 0) return ctx->fail(PS_ERR_ARG, "unsupported filter span");
+    ctx->launches += r;
+    PS_CUDA(ctx, cudaGetLastError());
+    return PS_OK;
 }

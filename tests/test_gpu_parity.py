@@ -1,0 +1,211 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI, against
+  (1) the CPU oracle on the same seeded inputs (bit-exact planes and extrema),
+  (2) the committed golden fixtures produced by the unmodified reference on a B200,
+  (3) the reference library itself, live (oracle/_ref/ref_dump travels with the snapshot),
+  (4) size-independent properties at the benchmark's full 4K size.
+Tolerances (from BASELINE.json north_star): keypoint-match F1 >= 0.99, identical counts in VLFeat
+mode, per-descriptor L2 < 1e-3.  Measured: F1 = 1.0, identical counts in every mode, L2 < 6e-5."""
+import hashlib
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import compare
+import oracle_lib as ol
+from popsift_b200 import api
+from popsift_b200.synth import make_frame, write_pgm
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = os.path.join(HERE, "golden")
+REF = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "ref_dump")
+F1_MIN, L2_MAX = 0.99, 1e-3
+
+
+def mk_cfg(mode="popsift", norm="rootsift", **kw):
+    c = api.Config()
+    c.setMode(mode)
+    c.setNormMode("RootSift" if norm == "rootsift" else "classic")
+    if "downsampling" in kw:
+        c.setDownsampling(kw["downsampling"])
+    if "octaves" in kw:
+        c.setOctaves(kw["octaves"])
+    if "levels" in kw:
+        c.setLevels(kw["levels"])
+    if "sigma" in kw:
+        c.setSigma(kw["sigma"])
+    return c
+
+
+def run_gpu(img, cfg, slots=1):
+    h, w = img.shape
+    ps = api.PopSift(cfg, max_width=w, max_height=h, slots=slots)
+    feats = ps.enqueue(w, h, img).get()
+    return ps, feats
+
+
+def test_planes_bit_identical_to_oracle_and_reference_hashes():
+    img = make_frame(256, 192, 3)
+    ps, _ = run_gpu(img, mk_cfg("vlfeat", "classic"))
+    o = ol.Oracle(ol.make_config(mode="vlfeat", norm="classic"), 256, 192)
+    o.run(img, 1)
+    meta = json.loads(bytes(np.load(os.path.join(G, "planes_f256.npz"))["meta"]).decode())
+    assert len(ps.slot_geometry(0)) == o.num_octaves == 6
+    for oc in range(6):
+        for l in range(6):
+            p = ps.plane(0, oc, l)
+            assert np.array_equal(p, o.gauss(oc, l)), ("gauss", oc, l)
+            assert hashlib.sha256(p.tobytes()).hexdigest() == meta["g_%d_%d" % (oc, l)]["sha256"]
+        for l in range(5):
+            p = ps.plane(0, oc, l, dog=True)
+            assert np.array_equal(p, o.dog(oc, l)), ("dog", oc, l)
+            assert hashlib.sha256(p.tobytes()).hexdigest() == meta["d_%d_%d" % (oc, l)]["sha256"]
+    ps.uninit()
+
+
+@pytest.mark.parametrize("w,h,seed,kw", [
+    (640, 480, 1, {}), (641, 479, 5, {}), (640, 480, 1, dict(downsampling=0)), (333, 517, 9, dict(downsampling=0)),
+    (320, 200, 11, dict(levels=4)), (200, 320, 12, dict(sigma=1.2, levels=2)), (97, 61, 13, {}), (32, 32, 14, {}),
+])
+def test_planes_and_extrema_bit_exact_vs_oracle(w, h, seed, kw):
+    """odd sizes, non-default levels / sigma (generic-radius kernel), tiny images"""
+    img = make_frame(w, h, seed)
+    for mode in ("popsift", "vlfeat"):
+        ps, feats = run_gpu(img, mk_cfg(mode, "classic", **kw))
+        okw = dict(mode=mode, norm="classic")
+        okw.update(kw)
+        o = ol.Oracle(ol.make_config(**okw), w, h)
+        o.run(img)
+        L = kw.get("levels", 3)
+        for oc in range(o.num_octaves):
+            for l in range(L + 3):
+                assert np.array_equal(ps.plane(0, oc, l), o.gauss(oc, l)), ("gauss", oc, l)
+            for l in range(L + 2):
+                assert np.array_equal(ps.plane(0, oc, l, dog=True), o.dog(oc, l)), ("dog", oc, l)
+        ge, oe = ps.extrema(0), o.extrema()
+        a = sorted((int(e["octave"]), float(e["x"]), float(e["y"]), int(e["lpos"])) for e in ge)
+        b = sorted((int(e[4]), float(e[0]), float(e[1]), int(e[3])) for e in oe)
+        assert a == b
+        of, od = o.features()
+        assert feats.getFeatureCount() == len(of) and feats.getDescriptorCount() == len(od)
+        if len(od):
+            r = compare.report(*feats.keypoints(), *ol.flatten(of, od))
+            assert r["f1"] >= F1_MIN and r["desc_l2_max"] < L2_MAX, r
+        ps.uninit()
+
+
+@pytest.mark.parametrize("name,w,h,seed,mode,norm,kw", [
+    ("f256_popsift_rs", 256, 192, 3, "popsift", "rootsift", {}),
+    ("f256_vlfeat_classic", 256, 192, 3, "vlfeat", "classic", {}),
+    ("f640_popsift_rs_a", 640, 480, 1, "popsift", "rootsift", {}),
+    ("f640_vlfeat_classic_a", 640, 480, 1, "vlfeat", "classic", {}),
+    ("f640_ds0", 640, 480, 1, "popsift", "rootsift", dict(downsampling=0)),
+])
+def test_features_vs_golden_reference_outputs(name, w, h, seed, mode, norm, kw):
+    z = np.load(os.path.join(G, "feat_%s.npz" % name))
+    rf, rd = z["feat"], z["desc"]
+    ps, feats = run_gpu(make_frame(w, h, seed), mk_cfg(mode, norm, **kw))
+    assert feats.getFeatureCount() == len(rf)          # identical keypoint counts
+    assert feats.getDescriptorCount() == len(rd)
+    r = compare.report(*feats.keypoints(), *ol.flatten(rf, rd))
+    assert r["f1"] >= F1_MIN and r["recall"] == 1.0 and r["desc_l2_max"] < L2_MAX, r
+    ps.uninit()
+
+
+def test_1080p_counts_vs_golden():
+    for name, mode, norm in (("f1080_popsift_rs", "popsift", "rootsift"), ("f1080_vlfeat_classic", "vlfeat", "classic")):
+        z = np.load(os.path.join(G, "feat_%s.npz" % name))
+        ps, feats = run_gpu(make_frame(1920, 1080, 100), mk_cfg(mode, norm))
+        assert feats.getFeatureCount() == len(z["feat"])
+        assert feats.getDescriptorCount() == int(z["n_desc"][0])
+        ps.uninit()
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/ref_dump not built")
+@pytest.mark.parametrize("w,h,seed,mode,norm,extra", [
+    (1920, 1080, 101, "vlfeat", "classic", []),
+    (1920, 1080, 102, "popsift", "rootsift", []),
+    (800, 600, 21, "vlfeat", "classic", ["--downsampling", "0"]),
+    (3840, 2160, 7, "vlfeat", "classic", ["--octaves", "5"]),
+])
+def test_live_against_reference_library(tmp_path, w, h, seed, mode, norm, extra):
+    """same bytes -> reference libpopsift (compiled from /root/reference for sm_100) and this library,
+    on the same B200"""
+    img = make_frame(w, h, seed)
+    pgm, out = str(tmp_path / "f.pgm"), str(tmp_path / "f.bin")
+    write_pgm(pgm, img)
+    subprocess.run([REF, "-i", pgm, "-o", out, "--mode", mode, "--norm", norm] + extra, check=True, capture_output=True)
+    rf, rd = ol.read_ref_features(out)
+    kw = {}
+    if "--downsampling" in extra:
+        kw["downsampling"] = 0
+    if "--octaves" in extra:
+        kw["octaves"] = 5
+    ps, feats = run_gpu(img, mk_cfg(mode, norm, **kw))
+    assert feats.getFeatureCount() == len(rf), (feats.getFeatureCount(), len(rf))
+    assert feats.getDescriptorCount() == len(rd), (feats.getDescriptorCount(), len(rd))
+    r = compare.report(*feats.keypoints(), *ol.flatten(rf, rd))
+    assert r["f1"] >= F1_MIN and r["desc_l2_max"] < L2_MAX, r
+    ps.uninit()
+
+
+def test_full_size_properties_4k():
+    """At the benchmark size the oracle is too slow for every test run; check properties instead:
+    determinism across slots/streams, DoG[l] == G[l+1]-G[l] exactly, octave o+1 level 0 ==
+    decimated level L of octave o, descriptors unit-length (classic) and finite."""
+    w, h = 3840, 2160
+    img = make_frame(w, h, 7)
+    cfg = mk_cfg("vlfeat", "classic", octaves=5)
+    ps = api.PopSift(cfg, max_width=w, max_height=h, slots=2)
+    j0, j1 = ps.enqueue(w, h, img), ps.enqueue(w, h, img)
+    f0, f1 = j0.get(), j1.get()
+    assert f0.getFeatureCount() == f1.getFeatureCount() > 5000
+    assert f0.getDescriptorCount() == f1.getDescriptorCount()
+    k0, d0 = f0.keypoints()
+    k1, d1 = f1.keypoints()
+    o0 = np.lexsort((k0[:, 3], k0[:, 2], k0[:, 1], k0[:, 0])); o1 = np.lexsort((k1[:, 3], k1[:, 2], k1[:, 1], k1[:, 0]))
+    assert np.array_equal(k0[o0], k1[o1]) and np.array_equal(d0[o0], d1[o1])      # run-to-run deterministic
+    n = np.linalg.norm(d0.astype(np.float64), axis=1)
+    assert np.isfinite(d0).all() and np.abs(n - 1.0).max() < 1e-3
+    for oc in (1, 4):
+        g = [ps.plane(1, oc, l) for l in range(6)]
+        for l in range(5):
+            assert np.array_equal(ps.plane(1, oc, l, dog=True), g[l + 1] - g[l])
+    g3 = ps.plane(1, 1, 3)
+    assert np.array_equal(ps.plane(1, 2, 0), g3[::2, ::2])
+    ps.uninit()
+
+
+def test_edge_cases():
+    # constant image: no keypoints, no error
+    ps, feats = run_gpu(np.full((120, 160), 128, np.uint8), mk_cfg())
+    assert feats.getFeatureCount() == 0 and feats.getDescriptorCount() == 0
+    ps.uninit()
+    # image larger than the context
+    ps = api.PopSift(mk_cfg(), max_width=64, max_height=64)
+    with pytest.raises(api.PopSiftError):
+        ps.enqueue(128, 128, np.zeros((128, 128), np.uint8))
+    # wrong image mode (reference popsift.cpp:247-253)
+    with pytest.raises(api.PopSiftError):
+        ps.enqueue(64, 64, np.zeros((64, 64), np.float32))
+    ps.uninit()
+    # unsupported sigma is refused at create time (reference gauss_filter.cu:131-137)
+    c = mk_cfg(); c.setSigma(2.5)
+    with pytest.raises(api.PopSiftError):
+        api.PopSift(c, max_width=64, max_height=64)
+
+
+def test_many_frames_in_flight_keep_fifo_order():
+    frames = [make_frame(320, 240, 200 + i) for i in range(6)]
+    cfg = mk_cfg()
+    ps1 = api.PopSift(cfg, max_width=320, max_height=240, slots=1)
+    ref = [ps1.enqueue(320, 240, f).get().getDescriptorCount() for f in frames]
+    ps1.uninit()
+    ps4 = api.PopSift(cfg, max_width=320, max_height=240, slots=4)
+    jobs = [ps4.enqueue(320, 240, f) for f in frames]
+    got = [j.get().getDescriptorCount() for j in jobs]
+    assert got == ref
+    ps4.uninit()
