@@ -72,50 +72,61 @@ def octave_pixels():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).
+    The sampler is started ahead of the region; only samples stamped inside [t0, t1] are used."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    FIELDS = ["timestamp", "clocks.sm", "clocks.max.sm", "power.draw", "clocks_event_reasons.hw_slowdown",
+              "clocks_event_reasons.hw_thermal_slowdown", "clocks_event_reasons.sw_thermal_slowdown",
+              "clocks_event_reasons.sw_power_cap"]
 
     def __init__(self, device):
-        self.device, self.proc, self.lines = device, None, []
+        self.device, self.proc, self.rows = device, None, []
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+        for fields in (self.FIELDS, [f.replace("clocks_event_reasons", "clocks_throttle_reasons") for f in self.FIELDS]):
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + ",".join(fields),
+                                              "--format=csv,noheader,nounits", "-lms", "20"],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            except Exception:
+                self.proc = None
+                return
+            time.sleep(0.3)
+            if self.proc.poll() is None:
+                break
+        self.t = threading.Thread(target=self._read, daemon=True)
+        self.t.start()
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        sm, mx, reasons, n_all = [], [], set(), 0
+        for ts, ln in self.rows:
             p = [x.strip() for x in ln.split(",")]
-            if len(p) < 9:
+            if len(p) < 8:
+                continue
+            n_all += 1
+            if t0 is not None and not (t0 - 0.02 <= ts <= t1 + 0.02):
                 continue
             try:
                 sm.append(float(p[1])); mx.append(float(p[2]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_total": n_all}
 
 
 def measured_peak():
@@ -175,12 +186,12 @@ def run_ours(args, rank, world, local_rank):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step_dev()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
     launches0 = L.ps_launch_count(ctx)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     slot_streams = [torch.cuda.ExternalStream(L.ps_slot_stream(ctx, s)) for s in range(SLOTS)]
@@ -190,6 +201,7 @@ def run_ours(args, rank, world, local_rank):
     for st in slot_streams:        # the slots' work is ordered after ev0
         st.wait_event(ev0)
     t0 = time.perf_counter()
+    wall0 = time.time()
     counts = (0, 0)
     for _ in range(args.steps):
         counts = step_dev()
@@ -202,7 +214,7 @@ def run_ours(args, rank, world, local_rank):
     wall_ms = (time.perf_counter() - t0) * 1e3
     dev_ms = ev0.elapsed_time(ev1)
     launches = L.ps_launch_count(ctx) - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(wall0, time.time()) if rank == 0 else None
 
     # ---------------- roofline of the pyramid stage (same context, slot 0 holds the last frame) ----
     chk(L.ps_submit_dev_u8(ctx, 0, dev_frames[0].data_ptr(), W, W, H))
@@ -264,12 +276,12 @@ def run_ours(args, rank, world, local_rank):
     e2e_wall_ms = (time.perf_counter() - t0) * 1e3
     ps.uninit()
 
-    # max over ranks (device-timed `value`; wall-clock for e2e, which includes host work by definition)
-    t = torch.tensor([dev_ms, wall_ms, e2e_wall_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    dev_ms, wall_ms, e2e_wall_ms = [float(x) for x in t.tolist()]
-    total_pix = npix_step * args.steps * world
+    # whole-job aggregate: SUM of pixels, MAX over ranks of the elapsed time (device-timed for `value`;
+    # wall clock for e2e, which includes host work by definition)
+    from popsift_b200 import shard
+    total_pix, dev_ms = shard.aggregate(npix_step * args.steps, dev_ms, device="cuda")
+    _, wall_ms = shard.aggregate(0, wall_ms, device="cuda")
+    _, e2e_wall_ms = shard.aggregate(0, e2e_wall_ms, device="cuda")
     if rank != 0:
         return None
 

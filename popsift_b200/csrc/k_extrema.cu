@@ -2,11 +2,9 @@
 //
 // Replaces find_extrema_in_dog / is_extremum / ModeFunctions / solve
 // (reference src/popsift/s_extrema.cu:22-558, s_solve.h:25-86).  One launch covers every
-// octave and level of an image (the reference launches once per octave): a flat list of
-// 32x8-pixel tiles over all (octave, level) pairs; each warp scans one 32-pixel row segment.
-// The contrast pre-test uses one coalesced read of the centre plane; the 26 neighbours are only
-// fetched (through L1/L2) by the few lanes that pass it.  Survivors are refined in registers and
-// appended with one warp-ballot + one atomicAdd per warp.
+// octave and all levels of an image (the reference launches once per octave with one CTA layer per
+// level): see the scan kernel below.  Survivors of the 26-neighbour test are refined in registers
+// and appended with one warp-ballot + one atomicAdd per warp.
 //
 // Parity contract: with bit-identical DoG planes, the accepted set and (x, y, lpos) of every
 // extremum are bit-identical to the reference's.  The floating-point pattern below is the one in
@@ -20,14 +18,6 @@ namespace psb {
 
 namespace {
 
-struct ScanParams {
-    // tile lists: tile_begin[o] = first tile index of octave o (tiles of all L levels of an octave
-    // are contiguous); tiles_x[o] = tiles per row
-    int tile_begin[kMaxOctaves + 1];
-    int tiles_x[kMaxOctaves];
-    int tiles_per_level[kMaxOctaves];
-};
-
 struct DogView {
     const float* base;
     int w, h, pitch, nplanes;
@@ -40,23 +30,6 @@ struct DogView {
         return __ldg(base + z * plane + (size_t)y * pitch + x);
     }
 };
-
-__device__ __forceinline__ bool strict_extremum(const DogView& d, int x, int y, int z, float val)
-{
-    bool gt = true, lt = true;
-#pragma unroll
-    for (int dz = -1; dz <= 1; ++dz)
-#pragma unroll
-        for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-                if (dx == 0 && dy == 0 && dz == 0) continue;
-                const float f = d.at(x + dx, y + dy, z + dz);
-                gt = gt && (val > f);
-                lt = lt && (val < f);
-            }
-    return gt || lt;
-}
 
 __device__ __forceinline__ bool solve3(float i00, float i01, float i02, float i11, float i12, float i22,
                                        float& bx, float& by, float& bz)
@@ -163,80 +136,171 @@ __device__ bool refine(const DogView& dv, const Consts& k, int x, int y, int lev
     return true;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(256)
+// ---- scan kernel -------------------------------------------------------------------------------
+//
+// A warp owns 30 output columns (lanes 1..30; lanes 0 and 31 only carry the x-halo) and walks down
+// SCAN_ROWS rows.  For every row it loads one value per DoG plane (coalesced 128-byte reads), forms the
+// horizontal 3-max / 3-min of each plane with two shuffles, and keeps the last three rows in registers.
+// The 26-neighbour test of a voxel is then a handful of max/min over those registers:
+//     strict maximum  <=>  v > max( 3x3 of plane l-1, 3x3 of plane l+1, 8 neighbours in plane l )
+// All NLEV levels of the octave are evaluated in the same pass, so each DoG value is loaded from HBM
+// once (the reference re-reads 27 texels per candidate, s_extrema.cu:56-120).  The verdict is identical:
+// a voxel survives iff it is strictly greater, or strictly smaller, than all 26 neighbours.
+constexpr int SCAN_COLS = 30;      // output columns per warp
+constexpr int SCAN_WARPS = 8;      // warps side by side in x
+constexpr int SCAN_ROWS = 32;      // rows walked by a CTA
+
+struct ScanParams {
+    int tile_begin[kMaxOctaves + 1];   // first CTA index of each octave
+    int tiles_x[kMaxOctaves];
+    int first_level;                   // first level evaluated (1-based DoG level)
+};
+
+template <int MODE, int NLEV>
+__global__ void __launch_bounds__(SCAN_WARPS * 32, 3)
 find_extrema_kernel(PyramidView pyr, Consts k, ScanParams sp, InitialExtremum* __restrict__ iext, Counters* ct)
 {
-    // which octave does this tile belong to?
     const int tile = blockIdx.x;
     int o = 0;
     while (o + 1 < pyr.num_octaves && tile >= sp.tile_begin[o + 1]) ++o;
     const OctaveView& ov = pyr.oct[o];
     const int local = tile - sp.tile_begin[o];
-    const int lvl_idx = local / sp.tiles_per_level[o];
-    const int t2 = local - lvl_idx * sp.tiles_per_level[o];
-    const int ty = t2 / sp.tiles_x[o];
-    const int tx = t2 - ty * sp.tiles_x[o];
-    const int level = lvl_idx + 1;
+    const int ty = local / sp.tiles_x[o];
+    const int tx = local - ty * sp.tiles_x[o];
     const int maxlevel = pyr.levels + 2;      // reference passes _levels-1 (s_extrema.cu:597)
+    const int lvl0 = sp.first_level;          // planes lvl0-1 .. lvl0+NLEV are read
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int x = tx * 32 + lane + 1;
-    const int y = ty * 8 + warp + 1;
+    const int W = ov.w, H = ov.h;
+    const int x = tx * (SCAN_WARPS * SCAN_COLS) + warp * SCAN_COLS + lane;   // lane 0 is the left halo column
+    const int xc = min(x, W - 1);
+    const int y0 = ty * SCAN_ROWS + 1;                                        // first output row
+    if (y0 > H - 2) return;
+    bool xout = (lane >= 1 && lane <= SCAN_COLS) && (x >= 1) && (x <= W - 2);
+    if (MODE == PS_MODE_OPENCV) xout = xout && !(x < 5 || x >= W - 5);
 
     DogView dv;
-    dv.base = ov.dog; dv.w = ov.w; dv.h = ov.h; dv.pitch = ov.pitch; dv.plane = ov.plane;
+    dv.base = ov.dog; dv.w = W; dv.h = H; dv.pitch = ov.pitch; dv.plane = ov.plane;
     dv.nplanes = pyr.levels + 2;
 
-    bool found = false;
-    InitialExtremum e;
-    e.xpos = e.ypos = e.sigma = 0.f; e.lpos = 0;
-    // border voxels can never be strict extrema under clamp addressing (reference quirk)
-    bool inside = (x <= ov.w - 2) && (y <= ov.h - 2);
-    if (MODE == PS_MODE_OPENCV) inside = inside && !(x < 5 || y < 5 || x >= ov.w - 5 || y >= ov.h - 5);
-    if (inside) {
-        const float val = __ldg(ov.dog + (size_t)level * ov.plane + (size_t)y * ov.pitch + x);
-        bool ok;
-        if (MODE == PS_MODE_OPENCV) ok = fabsf(val) >= floorf(k.threshold);
-        else if (MODE == PS_MODE_VLFEAT) ok = fabsf(val) >= __fmul_rn(__fmul_rn(0.8f, 2.0f), k.threshold);
-        else ok = fabsf(val) >= __fmul_rn(1.6f, k.threshold);
-        if (ok && strict_extremum(dv, x, y, level, val))
-            found = refine<MODE>(dv, k, x, y, level, maxlevel, val, e);
+    float thr;
+    if (MODE == PS_MODE_OPENCV) thr = floorf(k.threshold);
+    else if (MODE == PS_MODE_VLFEAT) thr = __fmul_rn(__fmul_rn(0.8f, 2.0f), k.threshold);
+    else thr = __fmul_rn(1.6f, k.threshold);
+
+    constexpr int NP = NLEV + 2;
+    const float* colp = ov.dog + (size_t)(lvl0 - 1) * ov.plane + xc;
+    // ring of three rows: value, horizontal 3-max, horizontal 3-min
+    float v[3][NP], hx[3][NP], hn[3][NP];
+
+    // rows y+1, y+2, y+3: three rows of loads stay in flight per warp (~46 KB per SM, enough to cover
+    // the HBM latency at full bandwidth) while row y is evaluated
+    float pend[3][NP];
+    auto issue_row = [&](int slot, int y) {
+        const int yc = min(max(y, 0), H - 1);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) pend[slot][p] = __ldg(colp + (size_t)p * ov.plane + (size_t)yc * ov.pitch);
+    };
+    auto finish_row = [&](int slot, int ps) {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const float c = pend[ps][p];
+            const float l = __shfl_up_sync(0xffffffffu, c, 1);
+            const float r = __shfl_down_sync(0xffffffffu, c, 1);
+            v[slot][p] = c;
+            hx[slot][p] = fmaxf(fmaxf(l, r), c);
+            hn[slot][p] = fminf(fminf(l, r), c);
+        }
+    };
+    issue_row(0, y0 - 1); issue_row(1, y0);
+    finish_row(0, 0); finish_row(1, 1);
+    issue_row(0, y0 + 1); issue_row(1, y0 + 2); issue_row(2, y0 + 3);
+
+#pragma unroll 1
+    for (int rr = 0; rr < SCAN_ROWS; rr += 3) {
+        // three rows per trip so that the ring slots are compile-time constants
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int y = y0 + rr + u;
+            if (rr + u >= SCAN_ROWS || y > H - 2) break;           // warp-uniform
+            const int sa = u % 3, sb = (u + 1) % 3, sc = (u + 2) % 3;    // above, centre, below
+            finish_row(sc, u);              // row y+1 has landed (pending slot u)
+            issue_row(u, y + 4);            // refill the slot: rows y+2 .. y+4 are now in flight
+            bool yok = true;
+            if (MODE == PS_MODE_OPENCV) yok = !(y < 5 || y >= H - 5);
+#pragma unroll
+            for (int q = 0; q < NLEV; ++q) {
+                const int p = q + 1;                              // centre plane index in the register ring
+                const float c = v[sb][p];
+                // left / right neighbours in the own plane, own row
+                const float l = __shfl_up_sync(0xffffffffu, c, 1);
+                const float r = __shfl_down_sync(0xffffffffu, c, 1);
+                float mx = fmaxf(fmaxf(hx[sa][p], hx[sc][p]), fmaxf(l, r));
+                float mn = fminf(fminf(hn[sa][p], hn[sc][p]), fminf(l, r));
+                mx = fmaxf(mx, fmaxf(fmaxf(hx[sa][p - 1], hx[sb][p - 1]), hx[sc][p - 1]));
+                mn = fminf(mn, fminf(fminf(hn[sa][p - 1], hn[sb][p - 1]), hn[sc][p - 1]));
+                mx = fmaxf(mx, fmaxf(fmaxf(hx[sa][p + 1], hx[sb][p + 1]), hx[sc][p + 1]));
+                mn = fminf(mn, fminf(fminf(hn[sa][p + 1], hn[sb][p + 1]), hn[sc][p + 1]));
+                const bool cand = xout && yok && (fabsf(c) >= thr) && ((c > mx) || (c < mn));
+                if (__any_sync(0xffffffffu, cand)) {
+                    bool found = false;
+                    InitialExtremum e;
+                    e.xpos = e.ypos = e.sigma = 0.f; e.lpos = 0;
+                    if (cand) found = refine<MODE>(dv, k, x, y, lvl0 + q, maxlevel, c, e);
+                    const unsigned mask = __ballot_sync(0xffffffffu, found);
+                    if (mask != 0) {
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(&ct->ext_ct[o], __popc(mask));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        const int idx = base + __popc(mask & ((1u << lane) - 1u));
+                        if (found && idx < k.max_extrema) iext[(size_t)o * k.max_extrema + idx] = e;
+                    }
+                }
+            }
+        }
     }
-    const unsigned mask = __ballot_sync(0xffffffffu, found);
-    if (mask == 0) return;
-    int base = 0;
-    if (lane == 0) base = atomicAdd(&ct->ext_ct[o], __popc(mask));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    const int idx = base + __popc(mask & ((1u << lane) - 1u));
-    if (found && idx < k.max_extrema) iext[(size_t)o * k.max_extrema + idx] = e;
+}
+
+template <int MODE>
+int launch_scan(const PyramidView& pyr, const Consts& k, InitialExtremum* iext, Counters* ct, cudaStream_t st)
+{
+    int launches = 0;
+    // levels are evaluated in groups of up to 3 (all of them at once for the default levels = 3)
+    for (int first = 1; first <= pyr.levels; first += 3) {
+        const int nlev = pyr.levels - first + 1 < 3 ? pyr.levels - first + 1 : 3;
+        ScanParams sp;
+        sp.first_level = first;
+        int total = 0;
+        for (int o = 0; o < kMaxOctaves; ++o) {
+            sp.tile_begin[o] = total;
+            sp.tiles_x[o] = 1;
+            if (o < pyr.num_octaves && pyr.oct[o].w >= 3 && pyr.oct[o].h >= 3) {
+                const int tx = (pyr.oct[o].w - 2 + SCAN_WARPS * SCAN_COLS - 1) / (SCAN_WARPS * SCAN_COLS);
+                const int ty = (pyr.oct[o].h - 2 + SCAN_ROWS - 1) / SCAN_ROWS;
+                sp.tiles_x[o] = tx;
+                total += tx * ty;
+            }
+        }
+        sp.tile_begin[kMaxOctaves] = total;
+        if (total == 0) continue;
+        if (nlev == 3)      find_extrema_kernel<MODE, 3><<<total, SCAN_WARPS * 32, 0, st>>>(pyr, k, sp, iext, ct);
+        else if (nlev == 2) find_extrema_kernel<MODE, 2><<<total, SCAN_WARPS * 32, 0, st>>>(pyr, k, sp, iext, ct);
+        else                find_extrema_kernel<MODE, 1><<<total, SCAN_WARPS * 32, 0, st>>>(pyr, k, sp, iext, ct);
+        ++launches;
+    }
+    return launches;
 }
 
 } // namespace
 
 int launch_find_extrema(const PyramidView& pyr, const Consts& k, InitialExtremum* iext, Counters* ct, cudaStream_t st)
 {
-    ScanParams sp;
-    int total = 0;
-    for (int o = 0; o < pyr.num_octaves; ++o) {
-        const int tx = (pyr.oct[o].w - 2 + 31) / 32;   // x in [1, w-2]
-        const int ty = (pyr.oct[o].h - 2 + 7) / 8;
-        sp.tile_begin[o] = total;
-        sp.tiles_x[o] = tx > 0 ? tx : 1;
-        sp.tiles_per_level[o] = (tx > 0 && ty > 0) ? tx * ty : 0;
-        if (sp.tiles_per_level[o] == 0) { sp.tiles_per_level[o] = 1; sp.tile_begin[o] = total; total += 0; sp.tile_begin[o + 1] = total; continue; }
-        total += sp.tiles_per_level[o] * pyr.levels;
-        sp.tile_begin[o + 1] = total;
-    }
-    for (int o = pyr.num_octaves; o < kMaxOctaves; ++o) { sp.tile_begin[o + 1] = total; sp.tiles_x[o] = 1; sp.tiles_per_level[o] = 1; }
-    if (total == 0) return 0;
     switch (k.sift_mode) {
-        case PS_MODE_OPENCV: find_extrema_kernel<PS_MODE_OPENCV><<<total, 256, 0, st>>>(pyr, k, sp, iext, ct); break;
-        case PS_MODE_VLFEAT: find_extrema_kernel<PS_MODE_VLFEAT><<<total, 256, 0, st>>>(pyr, k, sp, iext, ct); break;
-        default:             find_extrema_kernel<PS_MODE_POPSIFT><<<total, 256, 0, st>>>(pyr, k, sp, iext, ct); break;
+        case PS_MODE_OPENCV: return launch_scan<PS_MODE_OPENCV>(pyr, k, iext, ct, st);
+        case PS_MODE_VLFEAT: return launch_scan<PS_MODE_VLFEAT>(pyr, k, iext, ct, st);
+        default:             return launch_scan<PS_MODE_POPSIFT>(pyr, k, iext, ct, st);
     }
-    return 1;
 }
 
 } // namespace psb

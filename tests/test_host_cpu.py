@@ -125,3 +125,25 @@ def test_no_cpu_fallback_without_a_gpu():
     with pytest.raises(api.PopSiftError) as ei:
         api.PopSift(api.Config(), max_width=64, max_height=64)
     assert "no CUDA device" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+def test_fast_unorm16_division_is_exact_for_every_r16():
+    """k_pyramid_march.cu::unorm16_to_float: q = x*c; q += c*fma(-q, 65535, x) with c = RN(1/65535) equals the
+    correctly rounded x/65535 (what the texture unit returns) for all 65536 inputs."""
+    from fractions import Fraction
+
+    def rn32(fr):
+        f = np.float32(float(fr))
+        cands = [f, np.nextafter(f, np.float32(np.inf)), np.nextafter(f, np.float32(-np.inf))]
+        return min(cands, key=lambda c: (abs(Fraction(float(c)) - fr), int(c.view(np.uint32)) & 1))
+
+    def fma32(a, b, c):
+        return rn32(Fraction(float(a)) * Fraction(float(b)) + Fraction(float(c)))
+
+    c = np.array([0x37800080], dtype=np.uint32).view(np.float32)[0]
+    assert c == np.float32(1.0) / np.float32(65535.0)
+    for r in list(range(0, 65536, 7)) + [1, 2, 255, 256, 257, 65534, 65535] + [(257 * s + 2) >> 2 for s in range(1021)]:
+        x = np.float32(r)
+        q = np.float32(x * c)
+        q2 = fma32(fma32(-q, np.float32(65535.0), x), c, q)
+        assert q2 == rn32(Fraction(r, 65535)), r
