@@ -55,7 +55,7 @@ __device__ __forceinline__ bool solve3(float i00, float i01, float i02, float i1
 }
 
 template <int MODE>
-__device__ bool refine(const DogView& dv, const Consts& k, int x, int y, int level, int maxlevel, float val,
+__device__ __noinline__ bool refine(const DogView& dv, const Consts& k, int x, int y, int level, int maxlevel, float val,
                        InitialExtremum& out)
 {
     const int width = dv.w, height = dv.h;
@@ -157,7 +157,7 @@ struct ScanParams {
 };
 
 template <int MODE, int NLEV>
-__global__ void __launch_bounds__(SCAN_WARPS * 32, 3)
+__global__ void __launch_bounds__(SCAN_WARPS * 32, 2)
 find_extrema_kernel(PyramidView pyr, Consts k, ScanParams sp, InitialExtremum* __restrict__ iext, Counters* ct)
 {
     const int tile = blockIdx.x;
@@ -197,10 +197,12 @@ find_extrema_kernel(PyramidView pyr, Consts k, ScanParams sp, InitialExtremum* _
     // rows y+1, y+2, y+3: three rows of loads stay in flight per warp (~46 KB per SM, enough to cover
     // the HBM latency at full bandwidth) while row y is evaluated
     float pend[3][NP];
+    const unsigned plane_u = (unsigned)ov.plane;     // a whole octave (<= 15 planes) stays below 2^32 floats
     auto issue_row = [&](int slot, int y) {
         const int yc = min(max(y, 0), H - 1);
+        const float* rowp = colp + (size_t)yc * ov.pitch;
 #pragma unroll
-        for (int p = 0; p < NP; ++p) pend[slot][p] = __ldg(colp + (size_t)p * ov.plane + (size_t)yc * ov.pitch);
+        for (int p = 0; p < NP; ++p) pend[slot][p] = __ldg(rowp + p * plane_u);
     };
     auto finish_row = [&](int slot, int ps) {
 #pragma unroll
@@ -229,6 +231,7 @@ find_extrema_kernel(PyramidView pyr, Consts k, ScanParams sp, InitialExtremum* _
             issue_row(u, y + 4);            // refill the slot: rows y+2 .. y+4 are now in flight
             bool yok = true;
             if (MODE == PS_MODE_OPENCV) yok = !(y < 5 || y >= H - 5);
+            unsigned candbits = 0u;
 #pragma unroll
             for (int q = 0; q < NLEV; ++q) {
                 const int p = q + 1;                              // centre plane index in the register ring
@@ -242,12 +245,21 @@ find_extrema_kernel(PyramidView pyr, Consts k, ScanParams sp, InitialExtremum* _
                 mn = fminf(mn, fminf(fminf(hn[sa][p - 1], hn[sb][p - 1]), hn[sc][p - 1]));
                 mx = fmaxf(mx, fmaxf(fmaxf(hx[sa][p + 1], hx[sb][p + 1]), hx[sc][p + 1]));
                 mn = fminf(mn, fminf(fminf(hn[sa][p + 1], hn[sb][p + 1]), hn[sc][p + 1]));
-                const bool cand = xout && yok && (fabsf(c) >= thr) && ((c > mx) || (c < mn));
-                if (__any_sync(0xffffffffu, cand)) {
+                if ((fabsf(c) >= thr) && ((c > mx) || (c < mn))) candbits |= 1u << q;
+            }
+            if (!(xout && yok)) candbits = 0u;
+            if (__any_sync(0xffffffffu, candbits != 0u)) {
+                // rare path (a few voxels per thousand): refine and append, level by level
+                for (int q = 0; q < NLEV; ++q) {
+                    const bool cand = (candbits >> q) & 1u;
+                    if (!__any_sync(0xffffffffu, cand)) continue;
                     bool found = false;
                     InitialExtremum e;
                     e.xpos = e.ypos = e.sigma = 0.f; e.lpos = 0;
-                    if (cand) found = refine<MODE>(dv, k, x, y, lvl0 + q, maxlevel, c, e);
+                    float cval = v[sb][1];
+                    if (q == 1 && NLEV > 1) cval = v[sb][2];
+                    if (q == 2 && NLEV > 2) cval = v[sb][3];
+                    if (cand) found = refine<MODE>(dv, k, x, y, lvl0 + q, maxlevel, cval, e);
                     const unsigned mask = __ballot_sync(0xffffffffu, found);
                     if (mask != 0) {
                         int base = 0;
