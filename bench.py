@@ -153,8 +153,9 @@ def run_ours(args, rank, world, local_rank):
     if not ctx:
         raise SystemExit("ps_create failed: " + L.ps_last_error(None).decode())
     dev_frames = [torch.from_numpy(f).cuda() for f in frames]
-    feat_buf = np.zeros(200000, dtype=api.FEATURE_DTYPE)
-    desc_buf = np.zeros((200000, 128), dtype=np.float32)
+    # page-locked result buffers (ps_host_alloc): ps_download DMA-copies straight into them
+    res = api._PinnedBlock(L, 200000, 200000)
+    feat_buf, desc_buf = res.feat, res.desc
     nf, nd = C.c_int32(), C.c_int32()
 
     def chk(rc):
@@ -245,6 +246,7 @@ def run_ours(args, rank, world, local_rank):
         if it >= 3:
             dom_ms.append(a.elapsed_time(b) / (LEVELS + 2))
     L.ps_destroy(ctx)
+    res.free()
     del dev_frames, flush
     torch.cuda.empty_cache()
 

@@ -142,6 +142,11 @@ int ps_counts(ps_ctx* ctx, int slot, int32_t* n_feat, int32_t* n_desc);
  * copies n_feat Feature records and n_desc descriptors to the caller's arrays; Feature::desc[]
  * are host pointers into `desc`. */
 int ps_download(ps_ctx* ctx, int slot, ps_feature* feat, ps_descriptor* desc);
+/* page-locked host memory for images and results (thin wrappers of cudaHostAlloc / cudaFreeHost).
+ * ps_submit_* and ps_download detect page-locked buffers and copy straight from / into them; pageable
+ * buffers are staged through the slot's own pinned buffers (one extra host memcpy). */
+void* ps_host_alloc(size_t bytes);
+void  ps_host_free(void* p);
 /* waits for the slot's stream without reading anything */
 int ps_sync(ps_ctx* ctx, int slot);
 

@@ -50,7 +50,7 @@ assert FEATURE_DTYPE.itemsize == 72 and EXTREMUM_DTYPE.itemsize == 44
 EXPORTS = ["ps_abi_version", "ps_config_default", "ps_gauss_tables_compute", "ps_geometry", "ps_create", "ps_destroy",
            "ps_last_error", "ps_submit_u8", "ps_submit_f32", "ps_submit_dev_u8", "ps_counts", "ps_download",
            "ps_sync", "ps_debug_plane", "ps_debug_extrema", "ps_slot_geometry", "ps_set_timing", "ps_stage_ms",
-           "ps_launch_count", "ps_slot_stream", "ps_run_pyramid_only", "ps_run_level_only"]
+           "ps_launch_count", "ps_slot_stream", "ps_run_pyramid_only", "ps_run_level_only", "ps_host_alloc", "ps_host_free"]
 
 _lib = None
 
@@ -90,6 +90,9 @@ def load_library():
     L.ps_slot_stream.argtypes = [C.c_void_p, C.c_int]
     L.ps_run_pyramid_only.argtypes = [C.c_void_p, C.c_int]
     L.ps_run_level_only.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.ps_host_alloc.restype = C.c_void_p
+    L.ps_host_alloc.argtypes = [C.c_size_t]
+    L.ps_host_free.argtypes = [C.c_void_p]
     _lib = L
     return L
 
@@ -211,12 +214,31 @@ class Config:
         return [(W[i], H[i]) for i in range(n)]
 
 
+class _PinnedBlock:
+    """One page-locked result buffer (features + descriptors); returned to its pool when released."""
+
+    def __init__(self, lib, n_feat: int, n_desc: int):
+        self.lib, self.n_feat, self.n_desc = lib, n_feat, n_desc
+        self.pf = lib.ps_host_alloc(max(n_feat, 1) * 72)
+        self.pd = lib.ps_host_alloc(max(n_desc, 1) * 512)
+        if not self.pf or not self.pd:
+            raise PopSiftError("ps_host_alloc failed")
+        self.feat = np.ctypeslib.as_array(C.cast(self.pf, C.POINTER(C.c_uint8)), shape=(max(n_feat, 1) * 72,)).view(FEATURE_DTYPE)
+        self.desc = np.ctypeslib.as_array(C.cast(self.pd, C.POINTER(C.c_float)), shape=(max(n_desc, 1), 128))
+
+    def free(self):
+        if self.pf:
+            self.lib.ps_host_free(self.pf); self.lib.ps_host_free(self.pd)
+            self.pf = self.pd = None
+
+
 class Features:
     """popsift::FeaturesHost (reference src/popsift/features.h:71-102)."""
 
-    def __init__(self, feat: np.ndarray, desc: np.ndarray):
+    def __init__(self, feat: np.ndarray, desc: np.ndarray, block=None, pool=None):
         self.feat = feat
         self.desc = desc
+        self._block, self._pool = block, pool
         base = desc.ctypes.data if len(desc) else 0
         idx = np.full((len(feat), 4), -1, dtype=np.int64)
         for k in range(4):
@@ -227,6 +249,12 @@ class Features:
     def getFeatureCount(self): return len(self.feat)
     def getDescriptorCount(self): return len(self.desc)
     size = getFeatureCount
+
+    def __del__(self):
+        # hand the page-locked buffer back for the next image (like deleting the reference's FeaturesHost)
+        if getattr(self, "_pool", None) is not None and self._block is not None:
+            self._pool.append(self._block)
+            self._block = None
 
     def keypoints(self):
         """rows (x, y, sigma, theta) per (feature, orientation) and the matching descriptors"""
@@ -280,6 +308,7 @@ class PopSift:
         self._max = (max_width, max_height)
         self._next = 0
         self._busy = [None] * slots
+        self._pool = []          # page-locked result buffers, recycled when a Features object dies
         if max_width and max_height:
             self._create(max_width, max_height)
 
@@ -318,11 +347,16 @@ class PopSift:
     def _collect(self, slot: int) -> Features:
         nf, nd = C.c_int32(), C.c_int32()
         self._check(self._lib.ps_counts(self._ctx, slot, C.byref(nf), C.byref(nd)))
-        feat = np.zeros(nf.value, dtype=FEATURE_DTYPE)
-        desc = np.zeros((nd.value, 128), dtype=np.float32)
-        self._check(self._lib.ps_download(self._ctx, slot, feat.ctypes.data, desc.ctypes.data))
+        blk = None
+        for i, b in enumerate(self._pool):
+            if b.n_feat >= nf.value and b.n_desc >= nd.value:
+                blk = self._pool.pop(i)
+                break
+        if blk is None:
+            blk = _PinnedBlock(self._lib, int(nf.value * 1.25) + 1024, int(nd.value * 1.25) + 1024)
+        self._check(self._lib.ps_download(self._ctx, slot, blk.pf, blk.pd))
         self._busy[slot] = None
-        return Features(feat, desc)
+        return Features(blk.feat[:nf.value], blk.desc[:nd.value], blk, self._pool)
 
     # --- test / benchmark taps ------------------------------------------------------------
     def plane(self, slot, octave, level, dog=False) -> np.ndarray:
@@ -363,6 +397,8 @@ class PopSift:
         if self._ctx:
             self._lib.ps_destroy(self._ctx)
             self._ctx = None
+        while self._pool:
+            self._pool.pop().free()
 
     def __del__(self):
         try:

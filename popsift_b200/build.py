@@ -29,6 +29,8 @@ NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC",
 LIB_SOURCES = ["ps_tables.cpp", "ps_ctx.cu", "k_pyramid.cu", "k_pyramid_march.cu", "k_extrema.cu", "k_orient.cu", "k_desc.cu",
                "host/sift_conf.cpp", "host/features.cpp", "host/popsift.cpp", "host/device_prop.cpp"]
 DEMO_SOURCES = ["app/popsift_demo.cpp", "app/pgmread.cpp"]
+API_CHECK = os.path.join(BIN_DIR, "api_check")
+API_CHECK_SRC = os.path.join(ROOT, "tests", "cpp", "api_check.cpp")
 
 
 def _newer(target: str, deps) -> bool:
@@ -77,6 +79,10 @@ def build(verbose: bool = False, force: bool = False) -> str:
     if demo_objs and (force or _newer(DEMO, demo_objs + [LIB])):
         subprocess.check_call(["nvcc"] + ARCH + ["-o", DEMO] + demo_objs +
                               ["-L" + LIB_DIR, "-lpopsift_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../lib", "-lpthread"])
+    if os.path.exists(API_CHECK_SRC) and (force or _newer(API_CHECK, [API_CHECK_SRC, LIB] + hdrs)):
+        # a plain host compiler is enough for a caller of the C++ API: no CUDA in the translation unit
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"), API_CHECK_SRC, "-o", API_CHECK,
+                               "-L" + LIB_DIR, "-lpopsift_b200", "-Wl,-rpath," + "$ORIGIN/../lib", "-lpthread"])
     return LIB
 
 

@@ -2,10 +2,13 @@
 // (reference src/popsift/features.cu:25-110,310-338): one line per (feature, orientation):
 //   x y 1/sigma^2 0 1/sigma^2 d0 .. d127
 #include "popsift/features.h"
+#include "pinned_pool.h"
 
 #include <cmath>
 #include <cstdlib>
 #include <iomanip>
+#include <map>
+#include <mutex>
 #include <new>
 #include <stdexcept>
 
@@ -19,19 +22,16 @@ FeaturesHost::FeaturesHost(int num_ext, int num_ori) : _ext(nullptr), _ori(nullp
 
 FeaturesHost::~FeaturesHost()
 {
-    std::free(_ext);
-    std::free(_ori);
+    popsift::detail::pinned_pool().put(_ext);
+    popsift::detail::pinned_pool().put(_ori);
 }
 
 void FeaturesHost::reset(int num_ext, int num_ori)
 {
-    std::free(_ext); _ext = nullptr;
-    std::free(_ori); _ori = nullptr;
-    // page-aligned like the reference's arrays (features.cu:63-84)
-    const size_t fb = ((size_t)(num_ext > 0 ? num_ext : 1) * sizeof(Feature) + 4095) / 4096 * 4096;
-    const size_t db = ((size_t)(num_ori > 0 ? num_ori : 1) * sizeof(Descriptor) + 4095) / 4096 * 4096;
-    _ext = static_cast<Feature*>(std::aligned_alloc(4096, fb));
-    _ori = static_cast<Descriptor*>(std::aligned_alloc(4096, db));
+    popsift::detail::pinned_pool().put(_ext); _ext = nullptr;
+    popsift::detail::pinned_pool().put(_ori); _ori = nullptr;
+    _ext = static_cast<Feature*>(popsift::detail::pinned_pool().get((size_t)(num_ext > 0 ? num_ext : 1) * sizeof(Feature)));
+    _ori = static_cast<Descriptor*>(popsift::detail::pinned_pool().get((size_t)(num_ori > 0 ? num_ori : 1) * sizeof(Descriptor)));
     if (!_ext || !_ori) throw std::runtime_error("Runtime error:\n    Failed to (re)allocate memory for downloading features");
     setFeatureCount(num_ext);
     setDescriptorCount(num_ori);

@@ -14,6 +14,7 @@
 // (popsift.cpp:118-122 writes it back into the stored Config).
 #include "popsift/popsift.h"
 #include "popsift_b200.h"
+#include "pinned_pool.h"
 
 #include <algorithm>
 #include <condition_variable>
@@ -34,7 +35,9 @@ SiftJob::SiftJob(int w, int h, const unsigned char* imageData) : _w(w), _h(h), _
 {
     _f = _p.get_future();
     const size_t n = (size_t)w * h;
-    _imageData = static_cast<unsigned char*>(std::malloc(n ? n : 1));
+    // page-locked copy: ps_submit_* then DMA-copies straight from it (one host copy instead of the
+    // reference's two, popsift.cpp:392-395 + s_image.cu:75)
+    _imageData = static_cast<unsigned char*>(popsift::detail::pinned_pool().get(n ? n : 1));
     if (!_imageData) throw std::runtime_error("Memory limitation\nE    Failed to allocate memory for SiftJob");
     std::memcpy(_imageData, imageData, n);
 }
@@ -43,12 +46,14 @@ SiftJob::SiftJob(int w, int h, const float* imageData) : _w(w), _h(h), _isFloat(
 {
     _f = _p.get_future();
     const size_t n = (size_t)w * h * sizeof(float);
-    _imageData = static_cast<unsigned char*>(std::malloc(n ? n : 1));
+    // page-locked copy: ps_submit_* then DMA-copies straight from it (one host copy instead of the
+    // reference's two, popsift.cpp:392-395 + s_image.cu:75)
+    _imageData = static_cast<unsigned char*>(popsift::detail::pinned_pool().get(n ? n : 1));
     if (!_imageData) throw std::runtime_error("Memory limitation\nE    Failed to allocate memory for SiftJob");
     std::memcpy(_imageData, imageData, n);
 }
 
-SiftJob::~SiftJob() { std::free(_imageData); }
+SiftJob::~SiftJob() { popsift::detail::pinned_pool().put(_imageData); }
 
 void SiftJob::setFeatures(popsift::FeaturesBase* f) { _p.set_value(f); }
 void SiftJob::setError(std::exception_ptr ptr) { _err = ptr; }

@@ -314,13 +314,13 @@ extern "C" ps_ctx* ps_create(int device, const ps_config* cfg, int max_w, int ma
     return ctx;
 }
 
+static bool is_pinned(const void* p);
+
 static int stage_input(ps_ctx* ctx, Slot& s, const void* host_img, size_t bytes)
 {
     // Pinned caller memory goes straight to the device; pageable memory is staged through the
     // slot's pinned buffer (the reference always stages: popsift.cpp:392-395 + s_image.cu:75).
-    cudaPointerAttributes at{};
-    const bool pinned = cudaPointerGetAttributes(&at, host_img) == cudaSuccess && at.type == cudaMemoryTypeHost;
-    cudaGetLastError();
+    const bool pinned = is_pinned(host_img);
     const void* src = host_img;
     if (!pinned) {
         // the staging buffer may still be in flight for the previous image of this slot
@@ -412,6 +412,26 @@ static int grow_pinned(ps_ctx* ctx, void** p, size_t* cap, size_t need, size_t e
     return PS_OK;
 }
 
+static bool is_pinned(const void* p)
+{
+    cudaPointerAttributes at{};
+    const bool yes = cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    return yes;
+}
+
+extern "C" void* ps_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+extern "C" void ps_host_free(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
 extern "C" int ps_download(ps_ctx* ctx, int slot, ps_feature* feat, ps_descriptor* desc)
 {
     Slot* s = get_slot(ctx, slot);
@@ -423,14 +443,24 @@ extern "C" int ps_download(ps_ctx* ctx, int slot, ps_feature* feat, ps_descripto
     if (nf == 0) return PS_OK;
     if (!feat || (nd && !desc)) return ctx->fail(PS_ERR_ARG, "ps_download: null output array");
     int rc;
-    if ((rc = grow_pinned(ctx, (void**)&s->h_feat, &s->h_feat_cap, nf, sizeof(ps_feature))) != PS_OK) return rc;
-    if ((rc = grow_pinned(ctx, (void**)&s->h_desc, &s->h_desc_cap, nd, sizeof(ps_descriptor))) != PS_OK) return rc;
-    PS_CUDA(ctx, cudaMemcpyAsync(s->h_feat, s->d_feat, nf * sizeof(ps_feature), cudaMemcpyDeviceToHost, s->stream));
-    if (nd) PS_CUDA(ctx, cudaMemcpyAsync(s->h_desc, s->d_desc, nd * sizeof(ps_descriptor), cudaMemcpyDeviceToHost, s->stream));
-    PS_CUDA(ctx, cudaStreamSynchronize(s->stream));
-    if (nd) std::memcpy(desc, s->h_desc, nd * sizeof(ps_descriptor));
+    // page-locked destinations receive the DMA directly; pageable ones go through the slot's staging
+    const bool direct = is_pinned(feat) && (nd == 0 || is_pinned(desc));
+    ps_feature* hf = feat;
+    if (direct) {
+        PS_CUDA(ctx, cudaMemcpyAsync(feat, s->d_feat, nf * sizeof(ps_feature), cudaMemcpyDeviceToHost, s->stream));
+        if (nd) PS_CUDA(ctx, cudaMemcpyAsync(desc, s->d_desc, nd * sizeof(ps_descriptor), cudaMemcpyDeviceToHost, s->stream));
+        PS_CUDA(ctx, cudaStreamSynchronize(s->stream));
+    } else {
+        if ((rc = grow_pinned(ctx, (void**)&s->h_feat, &s->h_feat_cap, nf, sizeof(ps_feature))) != PS_OK) return rc;
+        if ((rc = grow_pinned(ctx, (void**)&s->h_desc, &s->h_desc_cap, nd, sizeof(ps_descriptor))) != PS_OK) return rc;
+        PS_CUDA(ctx, cudaMemcpyAsync(s->h_feat, s->d_feat, nf * sizeof(ps_feature), cudaMemcpyDeviceToHost, s->stream));
+        if (nd) PS_CUDA(ctx, cudaMemcpyAsync(s->h_desc, s->d_desc, nd * sizeof(ps_descriptor), cudaMemcpyDeviceToHost, s->stream));
+        PS_CUDA(ctx, cudaStreamSynchronize(s->stream));
+        if (nd) std::memcpy(desc, s->h_desc, nd * sizeof(ps_descriptor));
+        hf = s->h_feat;
+    }
     for (size_t i = 0; i < nf; ++i) {
-        ps_feature f = s->h_feat[i];
+        ps_feature f = hf[i];
         const int first = f.pad_;
         f.pad_ = 0;
         for (int r = 0; r < PS_MAX_ORI; ++r) f.desc[r] = (r < f.num_ori) ? desc + first + r : nullptr;

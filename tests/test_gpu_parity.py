@@ -209,3 +209,42 @@ def test_many_frames_in_flight_keep_fifo_order():
     got = [j.get().getDescriptorCount() for j in jobs]
     assert got == ref
     ps4.uninit()
+
+
+BIN = os.path.join(os.path.dirname(HERE), "popsift_b200", "bin")
+
+
+def test_cpp_dropin_api_matches_c_abi(tmp_path):
+    """the C++ classes (popsift::Config / PopSift / SiftJob / Features) give the same result as the C ABI"""
+    exe = os.path.join(BIN, "api_check")
+    assert os.path.exists(exe), "build the product first (python -m popsift_b200.build)"
+    w, h = 640, 480
+    img = make_frame(w, h, 1)
+    raw = str(tmp_path / "f.raw")
+    img.tofile(raw)
+    out = subprocess.run([exe, str(w), str(h), raw, "vlfeat", "classic", "3"], check=True, capture_output=True, text=True).stdout.split("\n")
+    ps, feats = run_gpu(img, mk_cfg("vlfeat", "classic"))
+    want = (feats.getFeatureCount(), feats.getDescriptorCount())
+    s = float(feats.desc.astype(np.float64).sum())
+    for line in out[:3]:
+        nf, nd, cs = line.split()
+        assert (int(nf), int(nd)) == want
+        assert abs(float(cs) - s) < 1e-3 * max(1.0, abs(s))
+    ps.uninit()
+
+
+def test_popsift_demo_cli(tmp_path):
+    """popsift-demo -i file.pgm writes output-features.txt: one line per descriptor, 5 + 128 numbers"""
+    exe = os.path.join(BIN, "popsift-demo")
+    assert os.path.exists(exe)
+    img = make_frame(320, 240, 4)
+    write_pgm(str(tmp_path / "in.pgm"), img)
+    r = subprocess.run([exe, "-i", "in.pgm", "--vlfeat-mode", "--norm-mode", "classic", "--octaves", "4"], cwd=str(tmp_path),
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = open(str(tmp_path / "output-features.txt")).read().strip().split("\n")
+    ps, feats = run_gpu(img, mk_cfg("vlfeat", "classic", octaves=4))
+    assert len(lines) == feats.getDescriptorCount()
+    assert all(len(l.split()) == 133 for l in lines)
+    assert "Number of feature points: %d number of feature descriptors: %d" % (feats.getFeatureCount(), feats.getDescriptorCount()) in r.stderr
+    ps.uninit()
