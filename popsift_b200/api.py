@@ -17,7 +17,7 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpopsift_b200.so")
+LIB_PATH = os.environ.get("POPSIFT_B200_LIB") or os.path.join(_HERE, "lib", "libpopsift_b200.so")
 
 PS_MAX_OCTAVES = 20
 MODE = {"popsift": 0, "opencv": 1, "vlfeat": 2}

@@ -4,7 +4,7 @@
 
 namespace psb {
 
-struct Taps { float g[PS_GAUSS_ALIGN]; };   // one half-kernel, passed by value (constant bank)
+struct alignas(16) Taps { float g[PS_GAUSS_ALIGN]; };   // one half-kernel, passed by value (constant bank)
 
 // column-marching fast path (k_pyramid_march.cu); return -1 when the radius is not instantiated
 int march_blur_level(const OctaveView& o, int level, const Taps& t, int R, float* next0, int next_pitch, cudaStream_t st);
