@@ -35,108 +35,110 @@ constexpr int Q = 16;       // rows per chunk
 constexpr int NT = 128;     // threads per CTA
 constexpr int HBW = TW + 4; // ring-buffer row stride (== 4 mod 32: conflict-free 128-bit row-wise stores)
 
-constexpr int pad4mod32(int v) { return v + ((4 - (v % 32)) + 32) % 32; }
+// smallest stride >= v whose float4 count is odd: rows j = 0..7 of a quarter-warp then start in eight
+// different 4-bank groups, which is all a conflict-free row-wise LDS.128 / STS.128 needs
+constexpr int pad_odd4(int v) { return v + ((4 - (v % 8)) + 8) % 8; }
 
 template <int R>
 struct Geo {
     static constexpr int RP = (R + 3) / 4 * 4;          // halo rounded to float4
     static constexpr int SW = TW + 2 * RP;              // staged columns per row
-    static constexpr int SWP = pad4mod32(SW);           // stage row stride
+    static constexpr int SWP = pad_odd4(SW);            // stage row stride
+    // staging buffers: chunk k, chunk k-1 (DoG centre rows) and NBUF-2 chunks in flight.  Two chunks
+    // ahead where four buffers still leave room for 4 CTAs per SM (R <= 8).
+    static constexpr int NBUF = (R <= 8) ? 4 : 3;
+    static constexpr int AHEAD = NBUF - 2;
     static constexpr int RING = Q + 2 * R;              // lines in the ring buffer
     static constexpr int V4 = Q * SW / 4;               // float4 per staged chunk
     static constexpr int PF = (V4 + NT - 1) / NT;       // float4 prefetch registers per thread
-    static constexpr size_t smem = sizeof(float) * (3 * Q * SWP + RING * HBW);   // 3 staging buffers + ring
+    static constexpr size_t smem = sizeof(float) * (NBUF * Q * SWP + RING * HBW);   // staging buffers + ring
     static_assert(R <= Q, "centre rows must still be in the two staging buffers");
 };
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
-// ---- staging: source rows -> registers -> shared -------------------------------------------
+// ---- staging: source rows -> shared (cp.async) ------------------------------------------------
 //
-// The float4 a thread moves in slot k of a chunk is the same (row j_k, column group i4_k) for every
-// chunk, so its global offset (relative to the chunk's first row) and its shared-memory offset are
-// computed once per CTA.
+// The 16-byte piece a thread moves in slot k of a chunk is the same (row j_k, column group i4_k) for
+// every chunk, so its global offset (relative to the chunk's first row) and its shared-memory offset
+// are computed once per CTA.  Strips that touch the left or right image border (EDGE) skip the pieces
+// that start outside the image and patch the missing halo columns in shared memory afterwards
+// (clamp-to-edge), so they cost one extra barrier per chunk instead of a scalar gather.
 
 template <int R>
 struct StageMap {
-    int goff[Geo<R>::PF];     // j*pitch + (x0 - RP + 4*i4)   (floats; used on the interior fast path)
+    int goff[Geo<R>::PF];     // j*pitch + (x0 - RP + 4*i4)   (floats)
     int soff[Geo<R>::PF];     // j*SWP + 4*i4                 (floats)
+    unsigned live;            // bit k: slot k exists for this thread and starts inside the image
 };
 
-template <int R>
-__device__ __forceinline__ void make_stage_map(StageMap<R>& m, int pitch, int x0)
+template <int R, bool EDGE>
+__device__ __forceinline__ void make_stage_map(StageMap<R>& m, int pitch, int x0, int W)
 {
     using G = Geo<R>;
+    m.live = 0;
 #pragma unroll
     for (int k = 0; k < G::PF; ++k) {
         const int e = threadIdx.x + k * NT;
         const int j = e / (G::SW / 4);
         const int i4 = e - j * (G::SW / 4);
-        m.goff[k] = j * pitch + (x0 - G::RP + 4 * i4);
+        const int gx = x0 - G::RP + 4 * i4;
+        m.goff[k] = j * pitch + gx;
         m.soff[k] = j * G::SWP + 4 * i4;
+        if (e < G::V4 && (!EDGE || (gx >= 0 && gx < W))) m.live |= 1u << k;
     }
 }
 
-// FASTX: the strip and its halo lie inside the image (aligned 128-bit loads, no column clamp)
-template <int R, bool FASTX>
-__device__ __forceinline__ void prefetch_f32(float4 (&pf)[Geo<R>::PF], const StageMap<R>& m,
-                                             const float* __restrict__ src, int W, int H, int pitch, int iy, int x0)
+__device__ __forceinline__ void cp_async16(float* s, const float* g)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(s);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(g) : "memory");
+}
+
+// asynchronous global->shared copy of one chunk; rows outside the image clamp to the border rows
+template <int R, bool EDGE>
+__device__ __forceinline__ void stage_async(const StageMap<R>& m, const float* __restrict__ src, int H, int pitch, int iy,
+                                            float* __restrict__ S)
 {
     using G = Geo<R>;
-    const bool rows_inside = (iy >= 0) && (iy + Q <= H);
-    if (FASTX && rows_inside) {
+    if (iy >= 0 && iy + Q <= H) {
         const float* base = src + (long long)iy * pitch;
 #pragma unroll
-        for (int k = 0; k < G::PF; ++k)
-            if ((k + 1) * NT <= G::V4 || threadIdx.x + k * NT < G::V4)
-                pf[k] = __ldg(reinterpret_cast<const float4*>(base + m.goff[k]));
+        for (int k = 0; k < G::PF; ++k) {
+            const bool whole = !EDGE && (k + 1) * NT <= G::V4;      // slot k exists for every thread
+            if (whole || (m.live >> k & 1)) cp_async16(S + m.soff[k], base + m.goff[k]);
+        }
     } else {
 #pragma unroll
-        for (int k = 0; k < G::PF; ++k) {
-            if ((k + 1) * NT <= G::V4 || threadIdx.x + k * NT < G::V4) {
-                const int e = threadIdx.x + k * NT;
-                const int j = e / (G::SW / 4);
+        for (int k = 0; k < G::PF; ++k)
+            if (m.live >> k & 1) {
+                const int j = (threadIdx.x + k * NT) / (G::SW / 4);
                 const int gy = clampi(iy + j, 0, H - 1);
-                const float* row = src + (size_t)gy * pitch;
-                const int gx = x0 - G::RP + 4 * (e - j * (G::SW / 4));
-                if (FASTX || (gx >= 0 && gx + 3 < W)) {
-                    pf[k] = __ldg(reinterpret_cast<const float4*>(row + gx));
-                } else {
-                    pf[k].x = __ldg(row + clampi(gx, 0, W - 1));
-                    pf[k].y = __ldg(row + clampi(gx + 1, 0, W - 1));
-                    pf[k].z = __ldg(row + clampi(gx + 2, 0, W - 1));
-                    pf[k].w = __ldg(row + clampi(gx + 3, 0, W - 1));
-                }
+                cp_async16(S + m.soff[k], src + (long long)gy * pitch + (m.goff[k] - j * pitch));
             }
-        }
     }
 }
 
+// EDGE strips: replicate the border column into the halo columns the copy skipped.  Outputs right of
+// the image are never stored, so only R columns past the last image column have to be valid.
 template <int R>
-__device__ __forceinline__ void commit_stage(const float4 (&pf)[Geo<R>::PF], const StageMap<R>& m, float* __restrict__ S)
+__device__ __forceinline__ void patch_halo(float* __restrict__ S, int x0, int W)
 {
     using G = Geo<R>;
-#pragma unroll
-    for (int k = 0; k < G::PF; ++k)
-        if ((k + 1) * NT <= G::V4 || threadIdx.x + k * NT < G::V4)
-            *reinterpret_cast<float4*>(S + m.soff[k]) = pf[k];
-}
-
-// interior strip, but some rows of the chunk are outside the image: clamp rows, aligned 128-bit loads
-template <int R, bool FASTX>
-__device__ __forceinline__ void stage_sync(const StageMap<R>& m, const float* __restrict__ src, int W, int H, int pitch,
-                                           int iy, int x0, float* __restrict__ S)
-{
-    using G = Geo<R>;
-#pragma unroll
-    for (int k = 0; k < G::PF; ++k)
-        if ((k + 1) * NT <= G::V4 || threadIdx.x + k * NT < G::V4) {
-            const int e = threadIdx.x + k * NT;
-            const int j = e / (G::SW / 4);
-            const int gy = clampi(iy + j, 0, H - 1);
-            const int gx = x0 - G::RP + 4 * (e - j * (G::SW / 4));
-            *reinterpret_cast<float4*>(S + m.soff[k]) = __ldg(reinterpret_cast<const float4*>(src + (size_t)gy * pitch + gx));
-        }
+    const int j = threadIdx.x & (Q - 1);
+    const int u = threadIdx.x >> 4;                      // 0..NT/Q-1
+    float* row = S + j * G::SWP;
+    if (x0 < G::RP) {                                    // left border: stage column RP - x0 is x = 0
+        const int c0 = G::RP - x0;
+        const float v = row[c0];
+        for (int c = u; c < c0; c += NT / Q) row[c] = v;
+    }
+    const int cl = W - 1 - (x0 - G::RP);                 // stage column of x = W-1
+    if (cl + 1 < G::SW) {
+        const float v = row[cl];
+        const int ce = min(cl + R, G::SW - 1);
+        for (int c = cl + 1 + u; c <= ce; c += NT / Q) row[c] = v;
+    }
 }
 
 // ---- row pass: stage -> ring ------------------------------------------------------------------
@@ -267,65 +269,38 @@ __device__ __forceinline__ void col_pass(const float* __restrict__ HB, const flo
         col_emit<R, WRITE_DOG, NEXT, true>(win, Scur, Sprev, jbase, y_first, ys, ye, pd, pg, pn, pitch, next_pitch, t);
 }
 
-// asynchronous global->shared copy of one chunk (interior strips, rows inside the image)
-template <int R>
-__device__ __forceinline__ void stage_async(const StageMap<R>& m, const float* __restrict__ src, int pitch, int iy,
-                                            float* __restrict__ S)
-{
-    using G = Geo<R>;
-    const float* base = src + (long long)iy * pitch;
-#pragma unroll
-    for (int k = 0; k < G::PF; ++k)
-        if ((k + 1) * NT <= G::V4 || threadIdx.x + k * NT < G::V4) {
-            const unsigned sa = (unsigned)__cvta_generic_to_shared(S + m.soff[k]);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(base + m.goff[k]) : "memory");
-        }
-}
-
-template <int R, bool FASTX, bool NEXT, bool ASYNC>
+template <int R, bool EDGE, bool NEXT>
 __device__ __forceinline__ void march_body(float* __restrict__ smem, const float* __restrict__ src, float* __restrict__ dst,
                                            float* __restrict__ dog, float* __restrict__ next0, int W, int H, int pitch,
                                            int next_pitch, int x0, int ys, int ye, const Taps& taps)
 {
     using G = Geo<R>;
     constexpr int SB = Q * G::SWP;         // floats per staging buffer (buffer b starts at smem + b*SB)
-    float* HB = smem + 3 * SB;
+    constexpr int AHEAD = G::AHEAD;        // chunks in flight
+    float* HB = smem + G::NBUF * SB;
     const int nchunks = (ye - ys + 2 * R + Q - 1) / Q;
 
     StageMap<R> map;
-    make_stage_map<R>(map, pitch, x0);
-    // Staging of chunk k+1 overlaps the computation of chunk k.  Interior strips with all rows inside the
-    // image use cp.async straight into the third staging buffer; everything else (edge strips, clamped
-    // rows) goes through registers (prefetch -> commit).
-    auto rows_inside = [&](int iy) { return iy >= 0 && iy + Q <= H; };
-    constexpr bool REGS = !FASTX || !ASYNC;     // stage through registers (prefetch -> commit)
-    float4 pf[REGS ? G::PF : 1];
-    bool in_regs;
-    {
-        const int iy = ys - R;
-        if constexpr (!REGS) {
-            if (rows_inside(iy)) stage_async<R>(map, src, pitch, iy, smem);
-            else stage_sync<R, true>(map, src, W, H, pitch, iy, x0, smem);
-            in_regs = false;
-        } else { prefetch_f32<R, FASTX>(pf, map, src, W, H, pitch, iy, x0); in_regs = true; }
+    make_stage_map<R, EDGE>(map, pitch, x0, W);
+    // staging of chunks k+1 .. k+AHEAD overlaps the computation of chunk k
+    auto issue = [&](int k) { stage_async<R, EDGE>(map, src, H, pitch, ys - R + k * Q, smem + (k % G::NBUF) * SB); };
+#pragma unroll
+    for (int k = 0; k < AHEAD; ++k) {
+        if (k < nchunks) issue(k);
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
     int slot_in = 0;                     // ring slot of the chunk's first input row
     int cur = 0;                         // staging buffer of chunk k
     for (int k = 0; k < nchunks; ++k) {
         float* Scur = smem + cur * SB;
-        float* Sprev = smem + (cur == 0 ? 2 : cur - 1) * SB;
-        const int nxt = cur == 2 ? 0 : cur + 1;
-        if constexpr (REGS) { if (in_regs) commit_stage<R>(pf, map, Scur); }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();                  // chunk k staged; column pass k-1 finished (ring + buffer `nxt` are free)
-        if (k + 1 < nchunks) {
-            const int iy = ys - R + (k + 1) * Q;
-            if constexpr (!REGS) {
-                if (rows_inside(iy)) stage_async<R>(map, src, pitch, iy, smem + nxt * SB);
-                else stage_sync<R, true>(map, src, W, H, pitch, iy, x0, smem + nxt * SB);
-            } else { prefetch_f32<R, FASTX>(pf, map, src, W, H, pitch, iy, x0); in_regs = true; }
-            asm volatile("cp.async.commit_group;" ::: "memory");
+        float* Sprev = smem + (cur == 0 ? G::NBUF - 1 : cur - 1) * SB;
+        asm volatile("cp.async.wait_group %0;" :: "n"(AHEAD - 1) : "memory");
+        __syncthreads();                  // chunk k staged; column pass k-1 finished (ring + buffer of chunk k-2 are free)
+        if (k + AHEAD < nchunks) issue(k + AHEAD);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (EDGE) {
+            patch_halo<R>(Scur, x0, W);
+            __syncthreads();
         }
         row_pass<R, false>(Scur, HB, slot_in, taps);
         __syncthreads();
@@ -333,8 +308,9 @@ __device__ __forceinline__ void march_body(float* __restrict__ smem, const float
         if (slot_old >= G::RING) slot_old -= G::RING;
         col_pass<R, true, NEXT>(HB, Scur, Sprev, slot_old, ys - 2 * R + k * Q, ys, ye, x0, W, dst, dog, next0, pitch, next_pitch, taps);
         slot_in = slot_old;
-        cur = nxt;
+        cur = cur == G::NBUF - 1 ? 0 : cur + 1;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();                      // the next sub-segment reuses the buffers
 }
 
@@ -344,7 +320,7 @@ __device__ __forceinline__ void march_body(float* __restrict__ smem, const float
 // CTAs at about the same time (a strip-major split of the same work measured ~30 % slower).
 struct Partition { int strips, C, seg_units, B; };
 
-template <int R, bool ASYNC, bool NEXT>
+template <int R, bool NEXT>
 __global__ void __launch_bounds__(NT, 4)
 march_level_kernel(const float* __restrict__ src, float* __restrict__ dst, float* __restrict__ dog,
                    float* __restrict__ next0, int W, int H, int pitch, int next_pitch, Partition part, Taps taps)
@@ -356,9 +332,9 @@ march_level_kernel(const float* __restrict__ src, float* __restrict__ dst, float
     const int x0 = strip * TW;
     const int ys = seg * part.seg_units * Q;
     const int ye = min(H, ys + part.seg_units * Q);
-    const bool fast = (x0 - G::RP >= 0) && (x0 + TW + G::RP <= W);
-    if (fast) march_body<R, true, NEXT, ASYNC>(smem, src, dst, dog, next0, W, H, pitch, next_pitch, x0, ys, ye, taps);
-    else      march_body<R, false, NEXT, ASYNC>(smem, src, dst, dog, next0, W, H, pitch, next_pitch, x0, ys, ye, taps);
+    const bool edge = (x0 - G::RP < 0) || (x0 + TW + G::RP > W);
+    if (!edge) march_body<R, false, NEXT>(smem, src, dst, dog, next0, W, H, pitch, next_pitch, x0, ys, ye, taps);
+    else       march_body<R, true, NEXT>(smem, src, dst, dog, next0, W, H, pitch, next_pitch, x0, ys, ye, taps);
 }
 
 // ---- octave 0, level 0 from the input image -----------------------------------------------------
@@ -408,7 +384,7 @@ __device__ __forceinline__ void level0_body(float* __restrict__ smem, AxisTap* _
     using G = Geo<R>;
     float* S0 = smem;
     float* S1 = smem + Q * G::SWP;
-    float* HB = smem + 3 * Q * G::SWP;
+    float* HB = smem + G::NBUF * Q * G::SWP;
     const int nchunks = (ye - ys + 2 * R + Q - 1) / Q;
     constexpr int TAIL = G::SW - NT;          // columns beyond the first NT (= 2*RP)
 
@@ -556,20 +532,12 @@ void ensure_smem(K kernel, size_t bytes)
         }
 }
 
-// interior strips are staged with cp.async (default); POPSIFT_B200_ASYNC=0 selects the register
-// prefetch path for A/B timing
-bool async_choice()
-{
-    static const bool v = [] { const char* e = getenv("POPSIFT_B200_ASYNC"); return !(e && e[0] == '0'); }();
-    return v;
-}
-
-template <int R, bool ASYNC, bool NEXT>
+template <int R, bool NEXT>
 void launch_march(const Partition& part, const float* src, float* dst, float* dog, float* next0, const OctaveView& o,
                   int next_pitch, const Taps& t, cudaStream_t st)
 {
-    ensure_smem(march_level_kernel<R, ASYNC, NEXT>, Geo<R>::smem);
-    march_level_kernel<R, ASYNC, NEXT><<<part.B, NT, Geo<R>::smem, st>>>(src, dst, dog, next0, o.w, o.h, o.pitch, next_pitch, part, t);
+    ensure_smem(march_level_kernel<R, NEXT>, Geo<R>::smem);
+    march_level_kernel<R, NEXT><<<part.B, NT, Geo<R>::smem, st>>>(src, dst, dog, next0, o.w, o.h, o.pitch, next_pitch, part, t);
 }
 
 template <int R>
@@ -579,11 +547,8 @@ int run_march(const OctaveView& o, int level, const Taps& t, float* next0, int n
     const float* src = o.gauss + o.plane * (level - 1);
     float* dst = o.gauss + o.plane * level;
     float* dog = o.dog + o.plane * (level - 1);
-    const bool as = async_choice();
-    if (next0) { if (as) launch_march<R, true, true>(part, src, dst, dog, next0, o, next_pitch, t, st);
-                 else    launch_march<R, false, true>(part, src, dst, dog, next0, o, next_pitch, t, st); }
-    else       { if (as) launch_march<R, true, false>(part, src, dst, dog, next0, o, next_pitch, t, st);
-                 else    launch_march<R, false, false>(part, src, dst, dog, next0, o, next_pitch, t, st); }
+    if (next0) launch_march<R, true>(part, src, dst, dog, next0, o, next_pitch, t, st);
+    else       launch_march<R, false>(part, src, dst, dog, next0, o, next_pitch, t, st);
     return 1;
 }
 
