@@ -20,6 +20,7 @@
 // reference's sm_100 SASS); results are bit-identical to the tile kernels and to the reference.
 #include "ps_internal.h"
 #include "k_pyramid.h"
+#include "k_partition.h"
 
 #include <cstdlib>
 #include <mutex>
@@ -314,12 +315,6 @@ __device__ __forceinline__ void march_body(float* __restrict__ smem, const float
     __syncthreads();                      // the next sub-segment reuses the buffers
 }
 
-// Work partition: strips of TW columns x segments of whole chunk-rows (Q rows), ONE wave of CTAs
-// (148 SMs x 4 resident CTAs).  CTA b handles strip b % strips, segment b / strips: CTAs that run
-// side by side touch the same image rows, so every DRAM page of a row is streamed by neighbouring
-// CTAs at about the same time (a strip-major split of the same work measured ~30 % slower).
-struct Partition { int strips, C, seg_units, B; };
-
 template <int R, bool NEXT>
 __global__ void __launch_bounds__(NT, 4)
 march_level_kernel(const float* __restrict__ src, float* __restrict__ dst, float* __restrict__ dog,
@@ -327,11 +322,9 @@ march_level_kernel(const float* __restrict__ src, float* __restrict__ dst, float
 {
     using G = Geo<R>;
     extern __shared__ __align__(16) float smem[];
-    const int strip = blockIdx.x % part.strips;
-    const int seg = blockIdx.x / part.strips;
+    int strip, ys, ye;
+    if (!locate(part, blockIdx.x, H, Q, strip, ys, ye)) return;
     const int x0 = strip * TW;
-    const int ys = seg * part.seg_units * Q;
-    const int ye = min(H, ys + part.seg_units * Q);
     const bool edge = (x0 - G::RP < 0) || (x0 + TW + G::RP > W);
     if (!edge) march_body<R, false, NEXT>(smem, src, dst, dog, next0, W, H, pitch, next_pitch, x0, ys, ye, taps);
     else       march_body<R, true, NEXT>(smem, src, dst, dog, next0, W, H, pitch, next_pitch, x0, ys, ye, taps);
@@ -492,28 +485,21 @@ march_level0_kernel(const PIX* __restrict__ img, size_t img_pitch, int w, int h,
     __shared__ AxisTap ax[G::SW];
     __shared__ AxisTap ay[Q];
     __shared__ unsigned short Hs[X2 ? NS2 : 1][G::SW];
-    const int strip = blockIdx.x % part.strips;
-    const int seg = blockIdx.x / part.strips;
-    const int ys = seg * part.seg_units * Q;
-    level0_body<R, PIX, X2>(smem, ax, ay, Hs, img, img_pitch, w, h, shift, dst, W, H, pitch, strip * TW, ys,
-                            min(H, ys + part.seg_units * Q), dd, inc0);
+    int strip, ys, ye;
+    if (!locate(part, blockIdx.x, H, Q, strip, ys, ye)) return;
+    level0_body<R, PIX, X2>(smem, ax, ay, Hs, img, img_pitch, w, h, shift, dst, W, H, pitch, strip * TW, ys, ye, dd, inc0);
 }
 
 // ---- launch helpers ---------------------------------------------------------------------------
 
-Partition make_partition(int W, int H)
+// POPSIFT_B200_UNIFORM=1 keeps every strip at the same segment length (A/B timing)
+bool uniform_choice()
 {
-    Partition p;
-    p.strips = (W + TW - 1) / TW;
-    p.C = (H + Q - 1) / Q;
-    int segments = 592 / p.strips;                 // one wave: 148 SMs x 4 resident CTAs
-    if (segments < 1) segments = 1;
-    p.seg_units = (p.C + segments - 1) / segments;
-    if (p.seg_units < 4) p.seg_units = 4;          // keep the 2R-row warm-up a small fraction of the work
-    segments = (p.C + p.seg_units - 1) / p.seg_units;
-    p.B = p.strips * segments;
-    return p;
+    static const bool v = [] { const char* e = getenv("POPSIFT_B200_UNIFORM"); return e && e[0] == '1'; }();
+    return v;
 }
+
+Partition make_partition(int W, int H) { return psb::make_partition(W, H, TW, Q, 592, uniform_choice()); }   // 148 SMs x 4 CTAs
 
 // opt in to > 48 KB dynamic shared memory once per (kernel, device)
 template <typename K>

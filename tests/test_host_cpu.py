@@ -147,3 +147,15 @@ def test_fast_unorm16_division_is_exact_for_every_r16():
         q = np.float32(x * c)
         q2 = fma32(fma32(-q, np.float32(65535.0), x), c, q)
         assert q2 == rn32(Fraction(r, 65535)), r
+
+
+def test_march_partition_covers_every_row_once():
+    """The pyramid kernels' strip x segment partition (k_partition.h): host sweep over plane sizes."""
+    import subprocess
+    from popsift_b200 import build as B
+    B.build()
+    out = subprocess.run([B.PART_CHECK], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.startswith("OK"), out.stdout
+    # the 4K workload fills all 592 slots of one wave
+    assert "B=592" in out.stdout, out.stdout
