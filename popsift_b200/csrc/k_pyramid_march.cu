@@ -22,6 +22,7 @@
 #include "k_pyramid.h"
 #include "k_partition.h"
 
+#include <cstdint>
 #include <cstdlib>
 #include <mutex>
 #include <set>
@@ -361,15 +362,10 @@ __device__ __forceinline__ float unorm16_to_float(unsigned r16)
     return __fmaf_rn(rem, c, q);
 }
 
-constexpr int NS2 = Q / 2 + 2;   // source rows a chunk of Q virtual rows can touch in the exact-2x case
-
-// X2 = true: 8-bit input, octave 0 is exactly the 2x up-scaled image (default Config: W == 2w, H == 2h,
-// shift == 1).  The virtual texture sample then only depends on the SUM s4 of the 2x2 source texels
-// {r0,r1} x {c0,c1} (indices repeated when a fraction is 0): r16 = (257*s4 + 2) >> 2.  The sums are
-// built in two cheap steps (row sums Hs, then column sums) instead of a general bilinear blend.
-template <int R, typename PIX, bool X2>
+// General path (any scale factor, 8-bit or float input): every staged sample is one emulated
+// bilinear texture fetch.
+template <int R, typename PIX>
 __device__ __forceinline__ void level0_body(float* __restrict__ smem, AxisTap* __restrict__ ax, AxisTap* __restrict__ ay,
-                                            unsigned short (* __restrict__ Hs)[Geo<R>::SW],
                                             const PIX* __restrict__ img, size_t img_pitch, int w, int h, float shift,
                                             float* __restrict__ dst, int W, int H, int pitch, int x0, int ys, int ye,
                                             const Taps& dd, const Taps& inc0)
@@ -379,90 +375,38 @@ __device__ __forceinline__ void level0_body(float* __restrict__ smem, AxisTap* _
     float* S1 = smem + Q * G::SWP;
     float* HB = smem + G::NBUF * Q * G::SWP;
     const int nchunks = (ye - ys + 2 * R + Q - 1) / Q;
-    constexpr int TAIL = G::SW - NT;          // columns beyond the first NT (= 2*RP)
 
-    for (int i = threadIdx.x; i < G::SW; i += NT) {
-        const int X = x0 - G::RP + i;
-        if (X2) {
-            AxisTap t;
-            t.i0 = clampi(X >> 1, 0, w - 1);
-            t.i1 = clampi((X + 1) >> 1, 0, w - 1);
-            t.a = 0;
-            ax[i] = t;
-        } else {
-            ax[i] = virt_axis(X, shift, W, w);
-        }
-    }
+    for (int i = threadIdx.x; i < G::SW; i += NT) ax[i] = virt_axis(x0 - G::RP + i, shift, W, w);
     __syncthreads();
-    // this thread's main column and (for X2) its two source columns
-    const int ci = threadIdx.x;
-    const int c0 = X2 ? ax[ci].i0 : 0, c1 = X2 ? ax[ci].i1 : 0;
 
     int slot_in = 0;
     for (int k = 0; k < nchunks; ++k) {
         float* Scur = (k & 1) ? S1 : S0;
         const int iy = ys - R + k * Q;
-        if (X2) {
-            // step A: row sums of the source rows this chunk touches (thread = column, rows unrolled)
-            const int vy0 = clampi(iy, 0, H - 1);
-            const int rmin = vy0 >> 1;
-#pragma unroll
-            for (int r = 0; r < NS2; ++r) {
-                const PIX* row = img + (size_t)min(rmin + r, h - 1) * img_pitch;
-                Hs[r][ci] = (unsigned short)((unsigned)row[c0] + (unsigned)row[c1]);
+        // rows outside the octave clamp to the border row of the row-filtered plane
+        if (threadIdx.x < Q) ay[threadIdx.x] = virt_axis(clampi(iy + threadIdx.x, 0, H - 1), shift, H, h);
+        __syncthreads();
+        for (int e = threadIdx.x; e < Q * G::SW; e += NT) {
+            const int j = e / G::SW;
+            const int i = e - j * G::SW;
+            const AxisTap ty = ay[j];
+            const AxisTap tx = ax[i];
+            const PIX* r0 = img + (size_t)ty.i0 * img_pitch;
+            const PIX* r1 = img + (size_t)ty.i1 * img_pitch;
+            float v;
+            if (sizeof(PIX) == 1) {
+                const unsigned t00 = (unsigned)r0[tx.i0], t10 = (unsigned)r0[tx.i1];
+                const unsigned t01 = (unsigned)r1[tx.i0], t11 = (unsigned)r1[tx.i1];
+                const unsigned wx1 = tx.a, wx0 = 256u - wx1, wy1 = ty.a, wy0 = 256u - wy1;
+                const unsigned num = wx0 * wy0 * t00 + wx1 * wy0 * t10 + wx0 * wy1 * t01 + wx1 * wy1 * t11;
+                v = unorm16_to_float((num * 257u + 32768u) >> 16);
+            } else {
+                const float fx = (float)tx.a * (1.0f / 256.0f), fy = (float)ty.a * (1.0f / 256.0f);
+                const float top = __fmaf_rn(fx, (float)r0[tx.i1] - (float)r0[tx.i0], (float)r0[tx.i0]);
+                const float bot = __fmaf_rn(fx, (float)r1[tx.i1] - (float)r1[tx.i0], (float)r1[tx.i0]);
+                v = __fmaf_rn(fy, bot - top, top);
             }
-            for (int e = threadIdx.x; e < NS2 * TAIL; e += NT) {
-                const int r = e / TAIL;
-                const int i = NT + (e - r * TAIL);
-                const PIX* row = img + (size_t)min(rmin + r, h - 1) * img_pitch;
-                const AxisTap tx = ax[i];
-                Hs[r][i] = (unsigned short)((unsigned)row[tx.i0] + (unsigned)row[tx.i1]);
-            }
-            __syncthreads();
-            // step B: column sums -> unorm16 -> float (row indices are warp-uniform)
-#pragma unroll
-            for (int j = 0; j < Q; ++j) {
-                const int vy = clampi(iy + j, 0, H - 1);
-                const int ra = (vy >> 1) - rmin;
-                const int rb = min((vy + 1) >> 1, h - 1) - rmin;
-                const unsigned s4 = (unsigned)Hs[ra][ci] + (unsigned)Hs[rb][ci];
-                Scur[j * G::SWP + ci] = unorm16_to_float((257u * s4 + 2u) >> 2);
-            }
-            for (int e = threadIdx.x; e < Q * TAIL; e += NT) {
-                const int j = e / TAIL;
-                const int i = NT + (e - j * TAIL);
-                const int vy = clampi(iy + j, 0, H - 1);
-                const int ra = (vy >> 1) - rmin;
-                const int rb = min((vy + 1) >> 1, h - 1) - rmin;
-                const unsigned s4 = (unsigned)Hs[ra][i] + (unsigned)Hs[rb][i];
-                Scur[j * G::SWP + i] = unorm16_to_float((257u * s4 + 2u) >> 2);
-            }
-        } else {
-            // rows outside the octave clamp to the border row of the row-filtered plane
-            if (threadIdx.x < Q) ay[threadIdx.x] = virt_axis(clampi(iy + threadIdx.x, 0, H - 1), shift, H, h);
-            __syncthreads();
-            for (int e = threadIdx.x; e < Q * G::SW; e += NT) {
-                const int j = e / G::SW;
-                const int i = e - j * G::SW;
-                const AxisTap ty = ay[j];
-                const AxisTap tx = ax[i];
-                const PIX* r0 = img + (size_t)ty.i0 * img_pitch;
-                const PIX* r1 = img + (size_t)ty.i1 * img_pitch;
-                float v;
-                if (sizeof(PIX) == 1) {
-                    const unsigned t00 = (unsigned)r0[tx.i0], t10 = (unsigned)r0[tx.i1];
-                    const unsigned t01 = (unsigned)r1[tx.i0], t11 = (unsigned)r1[tx.i1];
-                    const unsigned wx1 = tx.a, wx0 = 256u - wx1, wy1 = ty.a, wy0 = 256u - wy1;
-                    const unsigned num = wx0 * wy0 * t00 + wx1 * wy0 * t10 + wx0 * wy1 * t01 + wx1 * wy1 * t11;
-                    v = unorm16_to_float((num * 257u + 32768u) >> 16);
-                } else {
-                    const float fx = (float)tx.a * (1.0f / 256.0f), fy = (float)ty.a * (1.0f / 256.0f);
-                    const float top = __fmaf_rn(fx, (float)r0[tx.i1] - (float)r0[tx.i0], (float)r0[tx.i0]);
-                    const float bot = __fmaf_rn(fx, (float)r1[tx.i1] - (float)r1[tx.i0], (float)r1[tx.i0]);
-                    v = __fmaf_rn(fy, bot - top, top);
-                }
-                Scur[j * G::SWP + i] = v;
-            }
+            Scur[j * G::SWP + i] = v;
         }
         __syncthreads();
         row_pass<R, true>(Scur, HB, slot_in, dd);
@@ -475,7 +419,7 @@ __device__ __forceinline__ void level0_body(float* __restrict__ smem, AxisTap* _
     }
 }
 
-template <int R, typename PIX, bool X2>
+template <int R, typename PIX>
 __global__ void __launch_bounds__(NT)
 march_level0_kernel(const PIX* __restrict__ img, size_t img_pitch, int w, int h, float shift,
                     float* __restrict__ dst, int W, int H, int pitch, Partition part, Taps dd, Taps inc0)
@@ -484,10 +428,128 @@ march_level0_kernel(const PIX* __restrict__ img, size_t img_pitch, int w, int h,
     extern __shared__ __align__(16) float smem[];
     __shared__ AxisTap ax[G::SW];
     __shared__ AxisTap ay[Q];
-    __shared__ unsigned short Hs[X2 ? NS2 : 1][G::SW];
     int strip, ys, ye;
     if (!locate(part, blockIdx.x, H, Q, strip, ys, ye)) return;
-    level0_body<R, PIX, X2>(smem, ax, ay, Hs, img, img_pitch, w, h, shift, dst, W, H, pitch, strip * TW, ys, ye, dd, inc0);
+    level0_body<R, PIX>(smem, ax, ay, img, img_pitch, w, h, shift, dst, W, H, pitch, strip * TW, ys, ye, dd, inc0);
+}
+
+// ---- octave 0, level 0, the default case: 8-bit input, exactly 2x up-scaled -------------------------
+//
+// W == 2w, H == 2h, shift == 1.  Virtual sample (X, Y) then only depends on the SUM s4 of the 2x2 source
+// texels {Y>>1, (Y+1)>>1} x {X>>1, (X+1)>>1} (indices repeat when a fraction is 0):
+// r16 = (257*s4 + 2) >> 2, value = r16/65535.  Per chunk the CTA needs 9 source rows x (SW/2 + 1) bytes:
+// they are staged as raw bytes with 4-byte cp.async two chunks ahead (the tile is < 1 KB), then
+// "expanded" into the float staging buffer: thread = virtual column, the column's 9 row sums live in
+// registers and the row pairing is static because the chunk's first row has the parity of R.
+template <int R>
+struct Geo0 {
+    using G = Geo<R>;
+    static constexpr int TROWS = Q / 2 + 2;             // source rows per tile (9 used away from the border)
+    static constexpr int TSW = G::SW / 2 + 4;           // bytes per tile row (multiple of 4)
+    static constexpr int PIECES = TROWS * (TSW / 4);    // 4-byte pieces per tile
+    static constexpr int NP = (PIECES + NT - 1) / NT;
+    static constexpr int AHEAD = 2, NRAW = AHEAD + 2;
+    static constexpr int TAIL = G::SW - NT;             // staged columns beyond the first NT (= 2*RP)
+    // float staging buffer, ring, raw tiles
+    static constexpr size_t smem = sizeof(float) * (Q * G::SWP + G::RING * HBW) + (size_t)NRAW * TROWS * TSW;
+    static_assert(TAIL >= 0 && TAIL <= NT, "one extra expand pass covers the halo columns");
+};
+
+__device__ __forceinline__ float s4_to_float(unsigned s4) { return unorm16_to_float((257u * s4 + 2u) >> 2); }
+
+template <int R>
+__global__ void __launch_bounds__(NT, 6)
+march_level0x2_kernel(const uint8_t* __restrict__ img, size_t img_pitch, int w, int h,
+                      float* __restrict__ dst, int W, int H, int pitch, Partition part, Taps dd, Taps inc0)
+{
+    using G = Geo<R>;
+    using G0 = Geo0<R>;
+    extern __shared__ __align__(16) float smem[];
+    int strip, ys, ye;
+    if (!locate(part, blockIdx.x, H, Q, strip, ys, ye)) return;
+    const int x0 = strip * TW;
+    float* S = smem;
+    float* HB = smem + Q * G::SWP;
+    uint8_t* T = reinterpret_cast<uint8_t*>(HB + G::RING * HBW);
+    const int nchunks = (ye - ys + 2 * R + Q - 1) / Q;
+    const int sx0 = ((x0 - G::RP) >> 1) & ~3;           // source column of tile byte 0 (may be negative)
+
+    // tile offsets of the two source columns of this thread's virtual columns (main + halo tail)
+    auto col_offsets = [&](int i, int& o0, int& o1) {
+        const int X = x0 - G::RP + i;
+        o0 = clampi(X >> 1, 0, w - 1) - sx0;
+        o1 = clampi((X + 1) >> 1, 0, w - 1) - sx0;
+    };
+    int m0, m1, t0 = 0, t1 = 0;
+    col_offsets(threadIdx.x, m0, m1);
+    const bool has_tail = threadIdx.x < G0::TAIL;
+    if (has_tail) col_offsets(NT + threadIdx.x, t0, t1);
+
+    auto issue = [&](int k) {
+        const int rbase = (ys - R + k * Q) >> 1;         // floor: tile row r holds source row clamp(rbase + r)
+        uint8_t* Tk = T + (k % G0::NRAW) * (G0::TROWS * G0::TSW);
+#pragma unroll
+        for (int q = 0; q < G0::NP; ++q) {
+            const int e = threadIdx.x + q * NT;
+            const int r = e / (G0::TSW / 4);
+            const int c4 = 4 * (e - r * (G0::TSW / 4));
+            const int sc = sx0 + c4;
+            if (e < G0::PIECES && sc >= 0 && sc < w) {
+                const uint8_t* g = img + (size_t)clampi(rbase + r, 0, h - 1) * img_pitch + sc;
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(Tk + r * G0::TSW + c4);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sa), "l"(g) : "memory");
+            }
+        }
+    };
+    // expand one virtual column of chunk k: 16 staged samples
+    auto expand = [&](int k, int i, int o0, int o1) {
+        const int iy = ys - R + k * Q;
+        const uint8_t* Tk = T + (k % G0::NRAW) * (G0::TROWS * G0::TSW);
+        float* out = S + i;
+        if (iy >= 0 && iy + Q < H && (iy & 1) == (R & 1)) {
+            constexpr int P = R & 1;
+            unsigned hs[Q / 2 + 1];
+#pragma unroll
+            for (int r = 0; r < Q / 2 + 1; ++r) hs[r] = (unsigned)Tk[r * G0::TSW + o0] + (unsigned)Tk[r * G0::TSW + o1];
+#pragma unroll
+            for (int j = 0; j < Q; ++j) out[j * G::SWP] = s4_to_float(hs[(P + j) >> 1] + hs[(P + j + 1) >> 1]);
+        } else {
+            const int rbase = iy >> 1;
+            for (int j = 0; j < Q; ++j) {
+                const int vy = clampi(iy + j, 0, H - 1);
+                const int ra = clampi((vy >> 1) - rbase, 0, G0::TROWS - 1);
+                const int rb = clampi(min((vy + 1) >> 1, h - 1) - rbase, 0, G0::TROWS - 1);
+                const unsigned s4 = (unsigned)Tk[ra * G0::TSW + o0] + (unsigned)Tk[ra * G0::TSW + o1] +
+                                    (unsigned)Tk[rb * G0::TSW + o0] + (unsigned)Tk[rb * G0::TSW + o1];
+                out[j * G::SWP] = s4_to_float(s4);
+            }
+        }
+    };
+
+#pragma unroll
+    for (int k = 0; k < G0::AHEAD; ++k) {
+        if (k < nchunks) issue(k);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.wait_group %0;" :: "n"(G0::AHEAD - 1) : "memory");
+    __syncthreads();                                      // tile 0 visible
+    int slot_in = 0;
+    for (int k = 0; k < nchunks; ++k) {
+        // S was last read by row pass k-1 (before the barrier that ended iteration k-1's row pass)
+        expand(k, threadIdx.x, m0, m1);
+        if (has_tail) expand(k, NT + threadIdx.x, t0, t1);
+        if (k + G0::AHEAD < nchunks) issue(k + G0::AHEAD);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        __syncthreads();                                  // chunk k expanded; column pass k-1 finished (ring free)
+        row_pass<R, true>(S, HB, slot_in, dd);
+        asm volatile("cp.async.wait_group %0;" :: "n"(G0::AHEAD - 1) : "memory");
+        __syncthreads();                                  // ring lines of chunk k written; tile k+1 visible
+        int slot_old = slot_in + Q;
+        if (slot_old >= G::RING) slot_old -= G::RING;
+        col_pass<R, false, false>(HB, S, S, slot_old, ys - 2 * R + k * Q, ys, ye, x0, W, dst, nullptr, nullptr, pitch, 0, inc0);
+        slot_in = slot_old;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // ---- launch helpers ---------------------------------------------------------------------------
@@ -499,7 +561,17 @@ bool uniform_choice()
     return v;
 }
 
-Partition make_partition(int W, int H) { return psb::make_partition(W, H, TW, Q, 592, uniform_choice()); }   // 148 SMs x 4 CTAs
+Partition make_partition(int W, int H, int slots = 592)     // one wave: 148 SMs x 4 resident CTAs
+{
+    return psb::make_partition(W, H, TW, Q, slots, uniform_choice());
+}
+
+// resident CTAs of the exact-2x level-0 kernel (POPSIFT_B200_L0SLOTS overrides, A/B timing)
+int level0_slots()
+{
+    static const int v = [] { const char* e = getenv("POPSIFT_B200_L0SLOTS"); const int n = e ? atoi(e) : 0; return n > 0 ? n : 148 * 6; }();
+    return v;
+}
 
 // opt in to > 48 KB dynamic shared memory once per (kernel, device)
 template <typename K>
@@ -542,17 +614,21 @@ template <int R, typename PIX>
 int run_march0(const PIX* img, size_t img_pitch, int w, int h, float shift, const OctaveView& o0, const Taps& dd,
                const Taps& inc0, cudaStream_t st)
 {
-    const Partition part = make_partition(o0.w, o0.h);
-    const bool x2 = sizeof(PIX) == 1 && shift == 1.0f && o0.w == 2 * w && o0.h == 2 * h;
-    if (x2) {
-        ensure_smem(march_level0_kernel<R, PIX, true>, Geo<R>::smem);
-        march_level0_kernel<R, PIX, true><<<part.B, NT, Geo<R>::smem, st>>>(img, img_pitch, w, h, shift, o0.gauss, o0.w, o0.h,
-                                                                           o0.pitch, part, dd, inc0);
-    } else {
-        ensure_smem(march_level0_kernel<R, PIX, false>, Geo<R>::smem);
-        march_level0_kernel<R, PIX, false><<<part.B, NT, Geo<R>::smem, st>>>(img, img_pitch, w, h, shift, o0.gauss, o0.w, o0.h,
-                                                                            o0.pitch, part, dd, inc0);
+    if constexpr (sizeof(PIX) == 1) {
+        const bool x2 = shift == 1.0f && o0.w == 2 * w && o0.h == 2 * h && (img_pitch & 3) == 0 &&
+                        (reinterpret_cast<uintptr_t>(img) & 3) == 0;
+        if (x2) {
+            const Partition part = make_partition(o0.w, o0.h, level0_slots());
+            ensure_smem(march_level0x2_kernel<R>, Geo0<R>::smem);
+            march_level0x2_kernel<R><<<part.B, NT, Geo0<R>::smem, st>>>(img, img_pitch, w, h, o0.gauss, o0.w, o0.h, o0.pitch,
+                                                                        part, dd, inc0);
+            return 1;
+        }
     }
+    const Partition part = make_partition(o0.w, o0.h);
+    ensure_smem(march_level0_kernel<R, PIX>, Geo<R>::smem);
+    march_level0_kernel<R, PIX><<<part.B, NT, Geo<R>::smem, st>>>(img, img_pitch, w, h, shift, o0.gauss, o0.w, o0.h,
+                                                                  o0.pitch, part, dd, inc0);
     return 1;
 }
 

@@ -137,6 +137,10 @@ bool fork_choice()
     return v;
 }
 
+// device pitch of the 8-bit input image: rows start 4-byte aligned (the level-0 kernel stages them with
+// 4-byte cp.async)
+static inline size_t u8_pitch(int w) { return ((size_t)w + 3) & ~(size_t)3; }
+
 // Dependency graph of the pyramid: within an octave level l needs level l-1; octave o+1 needs only level L
 // of octave o.  Levels L+1 and L+2 of octave o are therefore issued on the slot's side stream and overlap
 // the (much smaller) next octaves, which would otherwise run alone at a fraction of the GPU.
@@ -149,7 +153,7 @@ int run_pyramid(ps_ctx* ctx, Slot& s)
         r = launch_level0_f32(reinterpret_cast<const float*>(s.d_img), (size_t)s.w, s.w, s.h, ctx->cfg.upscale,
                               ctx->cfg.sift_mode, s.view.oct[0], ctx->dd0, ctx->rows[0], s.stream);
     else
-        r = launch_level0_u8(s.d_img, (size_t)s.w, s.w, s.h, ctx->cfg.upscale, ctx->cfg.sift_mode, s.view.oct[0],
+        r = launch_level0_u8(s.d_img, u8_pitch(s.w), s.w, s.h, ctx->cfg.upscale, ctx->cfg.sift_mode, s.view.oct[0],
                              ctx->dd0, ctx->rows[0], s.stream);
     if (r < 0) return ctx->fail(PS_ERR_ARG, "unsupported level-0 filter span %d", ctx->dd0.span);
     n += r;
@@ -328,7 +332,11 @@ static int stage_input(ps_ctx* ctx, Slot& s, const void* host_img, size_t bytes)
         std::memcpy(s.h_img, host_img, bytes);
         src = s.h_img;
     }
-    PS_CUDA(ctx, cudaMemcpyAsync(s.d_img, src, bytes, cudaMemcpyHostToDevice, s.stream));
+    if (!s.is_float && u8_pitch(s.w) != (size_t)s.w)
+        PS_CUDA(ctx, cudaMemcpy2DAsync(s.d_img, u8_pitch(s.w), src, (size_t)s.w, (size_t)s.w, (size_t)s.h,
+                                       cudaMemcpyHostToDevice, s.stream));
+    else
+        PS_CUDA(ctx, cudaMemcpyAsync(s.d_img, src, bytes, cudaMemcpyHostToDevice, s.stream));
     return PS_OK;
 }
 
@@ -373,7 +381,7 @@ extern "C" int ps_submit_dev_u8(ps_ctx* ctx, int slot, const uint8_t* dev_img, s
     if (rc != PS_OK) return rc;
     s->is_float = false;
     if (ctx->timing) PS_CUDA(ctx, cudaEventRecord(s->ev[0], s->stream));
-    PS_CUDA(ctx, cudaMemcpy2DAsync(s->d_img, (size_t)w, dev_img, pitch, (size_t)w, (size_t)h, cudaMemcpyDeviceToDevice, s->stream));
+    PS_CUDA(ctx, cudaMemcpy2DAsync(s->d_img, u8_pitch(w), dev_img, pitch, (size_t)w, (size_t)h, cudaMemcpyDeviceToDevice, s->stream));
     return submit_common(ctx, *s);
 }
 
@@ -559,7 +567,7 @@ extern "C" int ps_run_level_only(ps_ctx* ctx, int slot, int octave, int level)
     if (level == 0) {
         r = s->is_float ? launch_level0_f32(reinterpret_cast<const float*>(s->d_img), (size_t)s->w, s->w, s->h, ctx->cfg.upscale,
                                             ctx->cfg.sift_mode, s->view.oct[0], ctx->dd0, ctx->rows[0], s->stream)
-                        : launch_level0_u8(s->d_img, (size_t)s->w, s->w, s->h, ctx->cfg.upscale, ctx->cfg.sift_mode,
+                        : launch_level0_u8(s->d_img, u8_pitch(s->w), s->w, s->h, ctx->cfg.upscale, ctx->cfg.sift_mode,
                                            s->view.oct[0], ctx->dd0, ctx->rows[0], s->stream);
     } else {
         const OctaveView* next = (level == L && octave + 1 < s->num_octaves) ? &s->view.oct[octave + 1] : nullptr;
