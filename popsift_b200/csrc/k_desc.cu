@@ -44,19 +44,62 @@ __device__ __forceinline__ float tree_down(float v)
 }
 
 constexpr int DWARPS = 4;     // warps that share one descriptor (one CTA per descriptor in flight)
-// a bin can reach ~8e4 (232 fully weighted pixels of gradient magnitude 360): 17 integer bits
-__device__ const float kFix = 32768.0f;
-__device__ const float kUnfix = 1.0f / 32768.0f;
+constexpr int DTHREADS = DWARPS * 32;
+// a bin can reach ~8e4 (232 fully weighted pixels of gradient magnitude 360): 17 integer bits; one
+// contribution stays below 360 * 2^14 < 2^23, so float -> fixed point is a single FFMA onto 2^23
+__device__ const float kFix = 16384.0f;
+__device__ const float kUnfix = 1.0f / 16384.0f;
+__device__ const float kMagic = 8388608.0f;      // 2^23
 
-__global__ void __launch_bounds__(DWARPS * 32)
+// atan2 to 3.5e-7 rad: one reciprocal, a degree-6 minimax polynomial in a^2 on [0,1] and three
+// selects (atan2f is ~40 instructions).  The orientation only feeds a linear interpolation between
+// two bins, so the error moves a normalised descriptor by < 1e-6.
+__device__ __forceinline__ float fast_rcp(float v) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+__device__ __forceinline__ float fast_ex2(float v) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+
+__device__ __forceinline__ float fast_atan2(float y, float x)
+{
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    // dark regions hold denormal gradients: rcp.ftz would turn them into inf (and 0 * inf into NaN);
+    // their magnitude is ~0, so the angle is irrelevant
+    const float a = mx > 1e-30f ? mn * fast_rcp(mx) : 0.0f;
+    const float s = a * a;
+    float p = 0.006811764091253281f;
+    p = fmaf(p, s, -0.03360414132475853f);
+    p = fmaf(p, s, 0.07962359488010406f);
+    p = fmaf(p, s, -0.1323333978652954f);
+    p = fmaf(p, s, 0.19807815551757812f);
+    p = fmaf(p, s, -0.3331736922264099f);
+    p = fmaf(p, s, 0.9999961256980896f);
+    float r = p * a;
+    if (ay > ax) r = 1.57079632679489662f - r;
+    if (x < 0.0f) r = 3.14159265358979323846f - r;
+    return copysignf(r, y);
+}
+
+// floor(v) for |v| < 2^22 without the conversion pipe: v + 1.5 * 2^23 rounded down keeps floor(v) (two's
+// complement) in the low mantissa bits; floor_val turns the same float back into floor(v)
+__device__ const float kMagicS = 12582912.0f;    // 1.5 * 2^23
+__device__ __forceinline__ unsigned floor_bits(float v) { return __float_as_uint(__fadd_rd(v, kMagicS)); }
+__device__ __forceinline__ float floor_val(unsigned bits) { return __fsub_rn(__uint_as_float(bits), kMagicS); }
+// round(w * c) for 0 <= w*c < 2^23 (fixed-point contribution)
+__device__ __forceinline__ unsigned fix_bits(float w, float c) { return __float_as_uint(__fmaf_rn(w, c, kMagic)) & 0x7fffffu; }
+
+__device__ __forceinline__ float fast_sqrt(float v) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+
+__global__ void __launch_bounds__(DTHREADS)
 descriptor_kernel(PyramidView pyr, Consts k, const ps_extremum* __restrict__ ext,
                   const int* __restrict__ feat_to_ext, ps_descriptor* __restrict__ desc, Counters* ct)
 {
-    // 128 bins per warp in 32-bit fixed point (15 fractional bits): integer shared-memory atomics are
+    // 128 bins in 32-bit fixed point (15 fractional bits): integer shared-memory atomics are
     // native (ATOMS.ADD) whereas float ones are compare-and-swap loops, and integer sums do not depend
     // on the order of the adds -> run-to-run deterministic descriptors
     __shared__ __align__(16) unsigned H[128];
     __shared__ int next_d;
+    // per row of the support: x = candidates before the row (exclusive prefix), y = first column - x
+    __shared__ int2 row_tab[DTHREADS + 1];
+    __shared__ int warp_sum[DWARPS];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int total = ct->ori_total;
@@ -77,7 +120,6 @@ descriptor_kernel(PyramidView pyr, Consts k, const ps_extremum* __restrict__ ext
         const float* pl = ov.gauss + (size_t)lvl * ov.plane;
 
         if (warp == 0) *reinterpret_cast<uint4*>(H + 4 * lane) = make_uint4(0u, 0u, 0u, 0u);
-        __syncthreads();
 
         const float x = e.xpos, y = e.ypos;
         const float SBP = fabsf(__fmul_rn(3.0f, e.sigma));
@@ -92,58 +134,111 @@ descriptor_kernel(PyramidView pyr, Consts k, const ps_extremum* __restrict__ ext
             const int ymin = max(1, (int)floorf(y - half) - 1);
             const int xmax = min(width - 2, (int)floorf(x + half) + 1);
             const int ymax = min(height - 2, (int)floorf(y + half) + 1);
-            const int wx = xmax - xmin + 1;
             const int hy = ymax - ymin + 1;
-            const int loops = (wx > 0 && hy > 0) ? wx * hy : 0;
-            const float inv_wx = 1.0f / (float)max(wx, 1);
-
-            for (int i = threadIdx.x; i < loops; i += DWARPS * 32) {
-                // i / wx without an integer division (exact for the sizes at hand: fix up by one)
-                int q = (int)((float)i * inv_wx);
-                if (q * wx > i) --q;
-                if ((q + 1) * wx <= i) ++q;
-                const int ii = q + ymin;
-                const int jj = i - q * wx + xmin;
-                const float ddx = (float)jj - x, ddy = (float)ii - y;
-                const float rx = __fmaf_rn(crsbp, ddx, __fmul_rn(srsbp, ddy));
-                const float ry = __fmaf_rn(crsbp, ddy, __fmul_rn(-srsbp, ddx));
-                if (!(fabsf(rx) < 2.5f && fabsf(ry) < 2.5f)) continue;
-                const float* p = pl + (size_t)ii * pitch + jj;       // interior pixel: neighbours exist
-                const float gdx = __fsub_rn(__ldg(p + 1), __ldg(p - 1));
-                const float gdy = __fsub_rn(__ldg(p + pitch), __ldg(p - pitch));
-                const float mod = hypotf(gdx, gdy);
-                float th = atan2f(gdy, gdx);
-                const float ww = __expf(-__fmul_rn(__fmaf_rn(ry, ry, __fmul_rn(rx, rx)), 0.125f));
-                th = __fsub_rn(th, ang);
-                th = __fadd_rn(th, th < 0.0f ? dPi2 : 0.0f);
-                th = __fsub_rn(th, th >= dPi2 ? dPi2 : 0.0f);
-                const float tth = __fmul_ru(th, d4RPi);
-                const int fo0 = (int)floorf(tth);
-                const float do0 = __fsub_rn(tth, (float)fo0);
-                const int b0 = fo0 & 7, b1 = (fo0 + 1) & 7;
-                const float wm = __fmul_rn(ww, mod);
-                const float w0 = __fmul_rn(__fsub_rn(1.0f, do0), wm), w1 = __fmul_rn(do0, wm);
-                // the (at most) 2x2 cells whose bilinear window covers this pixel
-                const float fx = __fadd_rn(rx, 1.5f), fy = __fadd_rn(ry, 1.5f);
-                const float flx = floorf(fx), fly = floorf(fy);
-                const int cx0 = (int)flx, cy0 = (int)fly;
-                const float ax = __fsub_rn(fx, flx), ay = __fsub_rn(fy, fly);     // in [0,1)
-#pragma unroll
-                for (int sy = 0; sy < 2; ++sy) {
-                    const int cy = cy0 + sy;
-                    const float wy = sy ? ay : __fsub_rn(1.0f, ay);
-                    if (cy < 0 || cy > 3 || wy <= 0.0f) continue;
-#pragma unroll
-                    for (int sx = 0; sx < 2; ++sx) {
-                        const int cx = cx0 + sx;
-                        const float wxx = sx ? ax : __fsub_rn(1.0f, ax);
-                        if (cx < 0 || cx > 3 || wxx <= 0.0f) continue;
-                        const float wc = __fmul_rn(wxx, wy);
-                        unsigned* hb = H + ((cy << 2) + cx) * 8;
-                        atomicAdd(hb + b0, __float2uint_rn(__fmul_rn(__fmul_rn(w0, wc), kFix)));
-                        atomicAdd(hb + b1, __float2uint_rn(__fmul_rn(__fmul_rn(w1, wc), kFix)));
+            // The support is a rotated square; only ~half of its bounding box lies inside.  Each row's
+            // candidate interval [lo, hi] is bounded from the two slabs |rx| < 2.5, |ry| < 2.5 (one pixel
+            // of slack; the exact test stays in the sample loop), the candidates of up to DTHREADS rows are
+            // numbered with a prefix sum and handed out round-robin, so lanes only visit pixels that are
+            // (almost always) inside.
+            const float inv_c = 1.0f / crsbp, inv_s = 1.0f / srsbp;     // +-inf when the support is axis-aligned
+            for (int rb = 0; rb < hy; rb += DTHREADS) {
+                const int r = rb + threadIdx.x;
+                int lo = xmin, hi = xmax;
+                if (r < hy) {
+                    const float ddy = (float)(ymin + r) - y;
+                    // |crsbp*ddx + srsbp*ddy| < 2.5
+                    if (fabsf(crsbp) > 1e-6f) {
+                        const float u0 = (-2.5f - srsbp * ddy) * inv_c, u1 = (2.5f - srsbp * ddy) * inv_c;
+                        lo = max(lo, (int)floorf(fmaxf(x + fminf(u0, u1), -1e6f)) - 1);
+                        hi = min(hi, (int)floorf(fminf(x + fmaxf(u0, u1), 1e6f)) + 2);
+                    }
+                    // |crsbp*ddy - srsbp*ddx| < 2.5
+                    if (fabsf(srsbp) > 1e-6f) {
+                        const float v0 = (crsbp * ddy - 2.5f) * inv_s, v1 = (crsbp * ddy + 2.5f) * inv_s;
+                        lo = max(lo, (int)floorf(fmaxf(x + fminf(v0, v1), -1e6f)) - 1);
+                        hi = min(hi, (int)floorf(fminf(x + fmaxf(v0, v1), 1e6f)) + 2);
                     }
                 }
+                const int cnt = (r < hy && hi >= lo) ? hi - lo + 1 : 0;
+                int inc = cnt;                                   // inclusive scan over the CTA
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                if (lane == 31) warp_sum[warp] = inc;
+                __syncthreads();                                 // also orders the reset of H / previous pass
+                int base = 0;
+#pragma unroll
+                for (int wq = 0; wq < DWARPS; ++wq) if (wq < warp) base += warp_sum[wq];
+                row_tab[threadIdx.x] = make_int2(base + inc - cnt, lo - (base + inc - cnt));
+                if (threadIdx.x == DTHREADS - 1) row_tab[DTHREADS] = make_int2(base + inc, 0);
+                __syncthreads();
+                const int n = row_tab[DTHREADS].x;
+
+                int row = 0, cur_off = row_tab[0].y, next_pre = row_tab[1].x;
+                for (int i = threadIdx.x; i < n; i += DTHREADS) {
+                    while (i >= next_pre) {
+                        ++row;
+                        cur_off = row_tab[row].y;
+                        next_pre = row_tab[row + 1].x;
+                    }
+                    const int ii = ymin + rb + row;
+                    const int jj = i + cur_off;
+                    const float ddx = (float)jj - x, ddy = (float)ii - y;
+                    const float rx = __fmaf_rn(crsbp, ddx, __fmul_rn(srsbp, ddy));
+                    const float ry = __fmaf_rn(crsbp, ddy, __fmul_rn(-srsbp, ddx));
+                    if (!(fabsf(rx) < 2.5f && fabsf(ry) < 2.5f)) continue;
+                    const float* p = pl + (ii * pitch + jj);             // interior pixel: neighbours exist; a plane is < 2^31 floats
+                    const float gdx = __fsub_rn(__ldg(p + 1), __ldg(p - 1));
+                    const float gdy = __fsub_rn(__ldg(p + pitch), __ldg(p - pitch));
+                    const float mod = fast_sqrt(__fmaf_rn(gdx, gdx, __fmul_rn(gdy, gdy)));
+                    float th = fast_atan2(gdy, gdx);
+                    // exp(-(rx^2 + ry^2) / 8); the exponent stays above -2.3, no range handling needed
+                    const float ww = fast_ex2(__fmul_rn(__fmaf_rn(ry, ry, __fmul_rn(rx, rx)), -0.125f * 1.4426950408889634f));
+                    th = __fsub_rn(th, ang);
+                    th = __fadd_rn(th, th < 0.0f ? dPi2 : 0.0f);
+                    th = __fsub_rn(th, th >= dPi2 ? dPi2 : 0.0f);
+                    const float tth = __fmul_ru(th, d4RPi);
+                    const unsigned fb = floor_bits(tth);
+                    const float do0 = __fsub_rn(tth, floor_val(fb));           // tth may be negative: the bins wrap mod 8
+                    const int b0 = fb & 7, b1 = (fb + 1) & 7;
+                    const float wm = __fmul_rn(__fmul_rn(ww, mod), kFix);
+                    const float w1 = __fmul_rn(do0, wm), w0 = __fsub_rn(wm, w1);
+                    // the (at most) 2x2 cells whose bilinear window covers this pixel
+                    // cell coordinates biased by one so that the floor trick sees a non-negative number
+                    const float fx = __fadd_rn(rx, 2.5f), fy = __fadd_rn(ry, 2.5f);     // in (0, 5)
+                    const unsigned bx = floor_bits(fx), by = floor_bits(fy);
+                    const int cx0 = (int)(bx & 7u) - 1, cy0 = (int)(by & 7u) - 1;       // -1 .. 3
+                    const float ax1 = __fsub_rn(fx, floor_val(bx));                     // in [0,1)
+                    const float ay1 = __fsub_rn(fy, floor_val(by));
+                    const float ax0 = __fsub_rn(1.0f, ax1), ay0 = __fsub_rn(1.0f, ay1);
+                    unsigned* hb = H + ((cy0 << 2) + cx0) * 8;            // cell (cx0, cy0); may be out of range
+                    // rx + 2.5 can round up to exactly 5.0 (cell 4): every cell index is range-checked on both sides
+                    const bool x0ok = (unsigned)cx0 < 4u, x1ok = (unsigned)(cx0 + 1) < 4u;
+                    const bool y0ok = (unsigned)cy0 < 4u, y1ok = (unsigned)(cy0 + 1) < 4u;
+                    if (x0ok && y0ok) {
+                        const float wc = __fmul_rn(ax0, ay0);
+                        atomicAdd(hb + b0, fix_bits(w0, wc));
+                        atomicAdd(hb + b1, fix_bits(w1, wc));
+                    }
+                    if (x1ok && y0ok) {
+                        const float wc = __fmul_rn(ax1, ay0);
+                        atomicAdd(hb + 8 + b0, fix_bits(w0, wc));
+                        atomicAdd(hb + 8 + b1, fix_bits(w1, wc));
+                    }
+                    if (x0ok && y1ok) {
+                        const float wc = __fmul_rn(ax0, ay1);
+                        atomicAdd(hb + 32 + b0, fix_bits(w0, wc));
+                        atomicAdd(hb + 32 + b1, fix_bits(w1, wc));
+                    }
+                    if (x1ok && y1ok) {
+                        const float wc = __fmul_rn(ax1, ay1);
+                        atomicAdd(hb + 40 + b0, fix_bits(w0, wc));
+                        atomicAdd(hb + 40 + b1, fix_bits(w1, wc));
+                    }
+                }
+                // the next pass (or the next descriptor) rewrites row_tab only after its own barrier
             }
         }
         __syncthreads();
@@ -206,7 +301,7 @@ __global__ void prep_features_kernel(Consts k, const ps_extremum* __restrict__ e
 int launch_descriptors(const PyramidView& pyr, const Consts& k, const ps_extremum* ext, const int* feat_to_ext,
                        ps_descriptor* desc, Counters* ct, cudaStream_t st)
 {
-    descriptor_kernel<<<148 * 16, DWARPS * 32, 0, st>>>(pyr, k, ext, feat_to_ext, desc, ct);
+    descriptor_kernel<<<148 * 16, DTHREADS, 0, st>>>(pyr, k, ext, feat_to_ext, desc, ct);
     return 1;
 }
 

@@ -14,6 +14,8 @@
 //   contr= v + 0.5*fma(dz,Dz, fma(dy,Dy, dx*Dx));  det2 = fma(DDx,DDy, -(DXx*DXx))
 #include "ps_internal.h"
 
+#include <cstdlib>
+
 namespace psb {
 
 namespace {
@@ -274,9 +276,88 @@ find_extrema_kernel(PyramidView pyr, Consts k, ScanParams sp, InitialExtremum* _
     }
 }
 
+// ---- candidate-driven scan ---------------------------------------------------------------------
+//
+// The pyramid kernels append every DoG sample with |value| >= threshold to a per-(octave, level) list
+// while they write the plane (CandSink).  On real and synthetic images that is a few samples per
+// thousand, so testing only those against their 26 neighbours (early exit on the first neighbour that
+// beats them) replaces the dense scan's read of every DoG plane: one thread per candidate, grid-stride
+// over the concatenated lists, no host round trip (the counts are read from the device counters).
+// Accepted set and refinement are those of the dense kernel: same comparisons, same refine<MODE>.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+cand_extrema_kernel(PyramidView pyr, Consts k, InitialExtremum* __restrict__ iext, Counters* ct)
+{
+    const int L = pyr.levels;
+    const int nseg = pyr.num_octaves * L;
+    const int maxlevel = L + 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    int seg = -1;
+    long long seg_end = 0, seg_begin = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;; i += stride) {
+        while (i >= seg_end) {
+            if (++seg >= nseg) return;
+            const int o = seg / L, q = seg - o * L;
+            const long long cap = (long long)pyr.oct[o].plane;
+            long long n = ct->cand_ct[o][q];
+            if (n > cap) n = cap;
+            seg_begin = seg_end;
+            seg_end += n;
+        }
+        const int o = seg / L, q = seg - o * L;
+        const OctaveView& ov = pyr.oct[o];
+        const unsigned packed = ov.cand[(size_t)q * ov.plane + (size_t)(i - seg_begin)];
+        const int x = (int)(packed & 0xffffu), y = (int)(packed >> 16);
+        const int W = ov.w, H = ov.h;
+        bool inside = x >= 1 && x <= W - 2 && y >= 1 && y <= H - 2;
+        if (MODE == PS_MODE_OPENCV) inside = inside && !(x < 5 || x >= W - 5) && !(y < 5 || y >= H - 5);
+        if (!inside) continue;
+        const int level = q + 1;                                  // DoG plane of the candidate
+        const float* pc = ov.dog + (size_t)level * ov.plane + (size_t)y * ov.pitch + x;
+        const float c = __ldg(pc);
+        // strict maximum or strict minimum of the 3x3x3 neighbourhood
+        bool ismax = true, ismin = true;
+        auto beat = [&](float n) { ismax = ismax && c > n; ismin = ismin && c < n; };
+        auto row3 = [&](const float* r) { beat(__ldg(r - 1)); beat(__ldg(r)); beat(__ldg(r + 1)); };
+        beat(__ldg(pc - 1)); beat(__ldg(pc + 1));
+        if (!(ismax || ismin)) continue;
+        row3(pc - ov.pitch);
+        if (!(ismax || ismin)) continue;
+        row3(pc + ov.pitch);
+        if (!(ismax || ismin)) continue;
+        const float* pb = pc - ov.plane;
+        row3(pb - ov.pitch); row3(pb); row3(pb + ov.pitch);
+        if (!(ismax || ismin)) continue;
+        const float* pa = pc + ov.plane;
+        row3(pa - ov.pitch); row3(pa); row3(pa + ov.pitch);
+        if (!(ismax || ismin)) continue;
+
+        DogView dv;
+        dv.base = ov.dog; dv.w = W; dv.h = H; dv.pitch = ov.pitch; dv.plane = ov.plane;
+        dv.nplanes = L + 2;
+        InitialExtremum e;
+        e.xpos = e.ypos = e.sigma = 0.f; e.lpos = 0;
+        if (refine<MODE>(dv, k, x, y, level, maxlevel, c, e)) {
+            const int idx = atomicAdd(&ct->ext_ct[o], 1);
+            if (idx < k.max_extrema) iext[(size_t)o * k.max_extrema + idx] = e;
+        }
+    }
+}
+
+// POPSIFT_B200_DENSE_SCAN=1 forces the dense scan kernels (A/B timing and cross-check)
+static bool dense_choice()
+{
+    static const bool v = [] { const char* e = getenv("POPSIFT_B200_DENSE_SCAN"); return e && e[0] == '1'; }();
+    return v;
+}
+
 template <int MODE>
 int launch_scan(const PyramidView& pyr, const Consts& k, InitialExtremum* iext, Counters* ct, cudaStream_t st)
 {
+    if (pyr.cands_filled && !dense_choice()) {
+        cand_extrema_kernel<MODE><<<148 * 8, 256, 0, st>>>(pyr, k, iext, ct);
+        return 1;
+    }
     int launches = 0;
     // levels are evaluated in groups of up to 3 (all of them at once for the default levels = 3)
     for (int first = 1; first <= pyr.levels; first += 3) {

@@ -330,14 +330,17 @@ int launch_level0_f32(const float* img, size_t img_pitch_floats, int w, int h, f
     return launch_level0_any<float>(img, img_pitch_floats, w, h, upscale, sift_mode, o0, dd, inc0, st);
 }
 
-int launch_blur_level(const OctaveView& o, int level, const GaussRow& g, const OctaveView* next, cudaStream_t st)
+bool blur_level_collects(const GaussRow& g) { return use_march() && march_supports(g.span - 1); }
+
+int launch_blur_level(const OctaveView& o, int level, const GaussRow& g, const OctaveView* next, const CandSink* sink,
+                      cudaStream_t st)
 {
     const int R = g.span - 1;
     const Taps t = make_taps(g);
     float* next0 = next ? next->gauss : nullptr;
     const int next_pitch = next ? next->pitch : 0;
     if (use_march()) {
-        const int r = march_blur_level(o, level, t, R, next0, next_pitch, st);
+        const int r = march_blur_level(o, level, t, R, next0, next_pitch, sink, st);
         if (r >= 0) return r;
     }
     switch (R) {

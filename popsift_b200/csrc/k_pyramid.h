@@ -7,7 +7,9 @@ namespace psb {
 struct alignas(16) Taps { float g[PS_GAUSS_ALIGN]; };   // one half-kernel, passed by value (constant bank)
 
 // column-marching fast path (k_pyramid_march.cu); return -1 when the radius is not instantiated
-int march_blur_level(const OctaveView& o, int level, const Taps& t, int R, float* next0, int next_pitch, cudaStream_t st);
+int march_blur_level(const OctaveView& o, int level, const Taps& t, int R, float* next0, int next_pitch,
+                     const CandSink* sink, cudaStream_t st);
+bool march_supports(int R);
 int march_level0_u8(const uint8_t* img, size_t img_pitch, int w, int h, float shift, const OctaveView& o0,
                     const Taps& dd, const Taps& inc0, int R, cudaStream_t st);
 int march_level0_f32(const float* img, size_t img_pitch, int w, int h, float shift, const OctaveView& o0,

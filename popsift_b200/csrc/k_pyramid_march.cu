@@ -199,15 +199,44 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm(
 
 constexpr int QH = Q / 2;   // output rows per thread in the column pass
 
-template <int R, bool WRITE_DOG, bool NEXT, bool GUARD>
+// Rare path of the column pass: append the threshold-passing DoG samples of a warp's 64 x QH block to
+// the level's candidate list (one atomic per warp).  Bit 2*jj + i of `pm`: sample (x + i, y0 + jj).
+__device__ __noinline__ void append_cands(const CandSink cs, unsigned pm, int x, int y0)
+{
+    const unsigned lane = threadIdx.x & 31;
+    const int n = __popc(pm);
+    int incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += t;
+    }
+    int base = 0;
+    if (lane == 31) base = atomicAdd(cs.count, incl);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    int idx = base + incl - n;
+    while (pm) {
+        const int b = __ffs(pm) - 1;
+        pm &= pm - 1;
+        if (idx < cs.cap) cs.list[idx] = (unsigned)(x + (b & 1)) | ((unsigned)(y0 + (b >> 1)) << 16);
+        ++idx;
+    }
+}
+
+// All 32 lanes of a warp run the whole column pass (lanes right of the image only skip their stores),
+// so the candidate vote can use the full mask.
+template <int R, bool WRITE_DOG, bool NEXT, bool GUARD, bool CAND>
 __device__ __forceinline__ void col_emit(const f32x2 (&win)[QH + 2 * R], const float* __restrict__ Scur,
                                          const float* __restrict__ Sprev, int jbase, int y_first, int ys, int ye,
                                          float* __restrict__ pd, float* __restrict__ pg, float* __restrict__ pn,
-                                         int pitch, int next_pitch, const Taps& t)
+                                         int pitch, int next_pitch, const Taps& t, const CandSink& sink, int x, int W)
 {
     using G = Geo<R>;
     const int c2 = 2 * (threadIdx.x & 63);
     const int par = y_first & 1;
+    const bool col_in = !GUARD || x < W;            // GUARD: the pair may start right of the image
+    const bool pair_in = !GUARD || x + 1 < W;
+    unsigned pm = 0;
 #pragma unroll
     for (int jj = 0; jj < QH; ++jj) {
         f32x2 acc = pack2(0.0f, 0.0f);
@@ -219,7 +248,7 @@ __device__ __forceinline__ void col_emit(const f32x2 (&win)[QH + 2 * R], const f
         }
         acc = fma2(win[jj + R], pack2(t.g[0], t.g[0]), acc);
         const int j = jbase + jj;                       // row of the chunk's output block (0..Q-1)
-        const bool ok = !GUARD || (y_first + j >= ys && y_first + j < ye);
+        const bool ok = !GUARD || (col_in && y_first + j >= ys && y_first + j < ye);
         if (ok) {
             *reinterpret_cast<f32x2*>(pd) = acc;
             float a0, a1;
@@ -228,20 +257,29 @@ __device__ __forceinline__ void col_emit(const f32x2 (&win)[QH + 2 * R], const f
                 // centre source row: chunk-relative row j-R lives in the current (j >= R) or previous buffer
                 const float* cp = (j >= R) ? Scur + (j - R) * G::SWP : Sprev + (j - R + Q) * G::SWP;
                 const float2 cs = *reinterpret_cast<const float2*>(cp + G::RP + c2);
-                *reinterpret_cast<float2*>(pg) = make_float2(__fsub_rn(a0, cs.x), __fsub_rn(a1, cs.y));
+                const float g0 = __fsub_rn(a0, cs.x), g1 = __fsub_rn(a1, cs.y);
+                *reinterpret_cast<float2*>(pg) = make_float2(g0, g1);
+                if (CAND) {
+                    if (fabsf(g0) >= sink.thr) pm |= 1u << (2 * jj);
+                    if (pair_in && fabsf(g1) >= sink.thr) pm |= 2u << (2 * jj);
+                }
             }
             if (NEXT && ((j & 1) == par)) pn[(size_t)((y_first + j) >> 1) * next_pitch] = a0;
         }
         pd += pitch;
         if (WRITE_DOG) pg += pitch;
     }
+    if (CAND) {
+        if (__any_sync(0xffffffffu, pm != 0u)) append_cands(sink, pm, x, y_first + jbase);
+    }
 }
 
-template <int R, bool WRITE_DOG, bool NEXT>
+template <int R, bool WRITE_DOG, bool NEXT, bool CAND = false>
 __device__ __forceinline__ void col_pass(const float* __restrict__ HB, const float* __restrict__ Scur,
                                          const float* __restrict__ Sprev, int slot_oldest, int y_first,
                                          int ys, int ye, int x0, int W, float* __restrict__ dst, float* __restrict__ dog,
-                                         float* __restrict__ next0, int pitch, int next_pitch, const Taps& t)
+                                         float* __restrict__ next0, int pitch, int next_pitch, const Taps& t,
+                                         const CandSink& sink = CandSink())
 {
     using G = Geo<R>;
     const int c2 = 2 * (threadIdx.x & 63);
@@ -258,23 +296,22 @@ __device__ __forceinline__ void col_pass(const float* __restrict__ HB, const flo
     for (int i = 0; i < QH + 2 * R; ++i)
         win[i] = *reinterpret_cast<const f32x2*>((i < nw ? a0 : a1) + i * HBW);
     const int x = x0 + c2;
-    if (x >= W) return;
     const int yb = y_first + jbase;
-    if (yb + QH <= ys || yb >= ye) return;                     // nothing of this half-block is inside the segment
-    const long long o = (long long)yb * pitch + x;             // may be negative for guarded rows (never dereferenced)
+    if (yb + QH <= ys || yb >= ye) return;                     // nothing of this half-block is inside the segment (warp-uniform)
+    const long long o = (long long)yb * pitch + x;             // may point outside for guarded samples (never dereferenced)
     float* pd = dst + o;
     float* pg = WRITE_DOG ? dog + o : nullptr;
     float* pn = NEXT ? next0 + (x >> 1) : nullptr;
-    if (yb >= ys && yb + QH <= ye)
-        col_emit<R, WRITE_DOG, NEXT, false>(win, Scur, Sprev, jbase, y_first, ys, ye, pd, pg, pn, pitch, next_pitch, t);
+    if (yb >= ys && yb + QH <= ye && x0 + TW <= W)
+        col_emit<R, WRITE_DOG, NEXT, false, CAND>(win, Scur, Sprev, jbase, y_first, ys, ye, pd, pg, pn, pitch, next_pitch, t, sink, x, W);
     else
-        col_emit<R, WRITE_DOG, NEXT, true>(win, Scur, Sprev, jbase, y_first, ys, ye, pd, pg, pn, pitch, next_pitch, t);
+        col_emit<R, WRITE_DOG, NEXT, true, CAND>(win, Scur, Sprev, jbase, y_first, ys, ye, pd, pg, pn, pitch, next_pitch, t, sink, x, W);
 }
 
-template <int R, bool EDGE, bool NEXT>
+template <int R, bool EDGE, bool NEXT, bool CAND>
 __device__ __forceinline__ void march_body(float* __restrict__ smem, const float* __restrict__ src, float* __restrict__ dst,
                                            float* __restrict__ dog, float* __restrict__ next0, int W, int H, int pitch,
-                                           int next_pitch, int x0, int ys, int ye, const Taps& taps)
+                                           int next_pitch, int x0, int ys, int ye, const Taps& taps, const CandSink& sink)
 {
     using G = Geo<R>;
     constexpr int SB = Q * G::SWP;         // floats per staging buffer (buffer b starts at smem + b*SB)
@@ -308,7 +345,8 @@ __device__ __forceinline__ void march_body(float* __restrict__ smem, const float
         __syncthreads();
         int slot_old = slot_in + Q;       // oldest line = the one after the newest
         if (slot_old >= G::RING) slot_old -= G::RING;
-        col_pass<R, true, NEXT>(HB, Scur, Sprev, slot_old, ys - 2 * R + k * Q, ys, ye, x0, W, dst, dog, next0, pitch, next_pitch, taps);
+        col_pass<R, true, NEXT, CAND>(HB, Scur, Sprev, slot_old, ys - 2 * R + k * Q, ys, ye, x0, W, dst, dog, next0, pitch,
+                                      next_pitch, taps, sink);
         slot_in = slot_old;
         cur = cur == G::NBUF - 1 ? 0 : cur + 1;
     }
@@ -316,10 +354,10 @@ __device__ __forceinline__ void march_body(float* __restrict__ smem, const float
     __syncthreads();                      // the next sub-segment reuses the buffers
 }
 
-template <int R, bool NEXT>
+template <int R, bool NEXT, bool CAND>
 __global__ void __launch_bounds__(NT, 4)
 march_level_kernel(const float* __restrict__ src, float* __restrict__ dst, float* __restrict__ dog,
-                   float* __restrict__ next0, int W, int H, int pitch, int next_pitch, Partition part, Taps taps)
+                   float* __restrict__ next0, int W, int H, int pitch, int next_pitch, Partition part, Taps taps, CandSink sink)
 {
     using G = Geo<R>;
     extern __shared__ __align__(16) float smem[];
@@ -327,8 +365,8 @@ march_level_kernel(const float* __restrict__ src, float* __restrict__ dst, float
     if (!locate(part, blockIdx.x, H, Q, strip, ys, ye)) return;
     const int x0 = strip * TW;
     const bool edge = (x0 - G::RP < 0) || (x0 + TW + G::RP > W);
-    if (!edge) march_body<R, false, NEXT>(smem, src, dst, dog, next0, W, H, pitch, next_pitch, x0, ys, ye, taps);
-    else       march_body<R, true, NEXT>(smem, src, dst, dog, next0, W, H, pitch, next_pitch, x0, ys, ye, taps);
+    if (!edge) march_body<R, false, NEXT, CAND>(smem, src, dst, dog, next0, W, H, pitch, next_pitch, x0, ys, ye, taps, sink);
+    else       march_body<R, true, NEXT, CAND>(smem, src, dst, dog, next0, W, H, pitch, next_pitch, x0, ys, ye, taps, sink);
 }
 
 // ---- octave 0, level 0 from the input image -----------------------------------------------------
@@ -590,23 +628,28 @@ void ensure_smem(K kernel, size_t bytes)
         }
 }
 
-template <int R, bool NEXT>
+template <int R, bool NEXT, bool CAND>
 void launch_march(const Partition& part, const float* src, float* dst, float* dog, float* next0, const OctaveView& o,
-                  int next_pitch, const Taps& t, cudaStream_t st)
+                  int next_pitch, const Taps& t, const CandSink& sink, cudaStream_t st)
 {
-    ensure_smem(march_level_kernel<R, NEXT>, Geo<R>::smem);
-    march_level_kernel<R, NEXT><<<part.B, NT, Geo<R>::smem, st>>>(src, dst, dog, next0, o.w, o.h, o.pitch, next_pitch, part, t);
+    ensure_smem(march_level_kernel<R, NEXT, CAND>, Geo<R>::smem);
+    march_level_kernel<R, NEXT, CAND><<<part.B, NT, Geo<R>::smem, st>>>(src, dst, dog, next0, o.w, o.h, o.pitch, next_pitch,
+                                                                        part, t, sink);
 }
 
 template <int R>
-int run_march(const OctaveView& o, int level, const Taps& t, float* next0, int next_pitch, cudaStream_t st)
+int run_march(const OctaveView& o, int level, const Taps& t, float* next0, int next_pitch, const CandSink* sink, cudaStream_t st)
 {
     const Partition part = make_partition(o.w, o.h);
     const float* src = o.gauss + o.plane * (level - 1);
     float* dst = o.gauss + o.plane * level;
     float* dog = o.dog + o.plane * (level - 1);
-    if (next0) launch_march<R, true>(part, src, dst, dog, next0, o, next_pitch, t, st);
-    else       launch_march<R, false>(part, src, dst, dog, next0, o, next_pitch, t, st);
+    const bool cand = sink && sink->list && o.w <= 65535 && o.h <= 65535;
+    const CandSink cs = cand ? *sink : CandSink();
+    if (next0) { if (cand) launch_march<R, true, true>(part, src, dst, dog, next0, o, next_pitch, t, cs, st);
+                 else      launch_march<R, true, false>(part, src, dst, dog, next0, o, next_pitch, t, cs, st); }
+    else       { if (cand) launch_march<R, false, true>(part, src, dst, dog, next0, o, next_pitch, t, cs, st);
+                 else      launch_march<R, false, false>(part, src, dst, dog, next0, o, next_pitch, t, cs, st); }
     return 1;
 }
 
@@ -634,10 +677,13 @@ int run_march0(const PIX* img, size_t img_pitch, int w, int h, float shift, cons
 
 } // namespace
 
-int march_blur_level(const OctaveView& o, int level, const Taps& t, int R, float* next0, int next_pitch, cudaStream_t st)
+bool march_supports(int R) { return R >= 3 && R <= 16; }
+
+int march_blur_level(const OctaveView& o, int level, const Taps& t, int R, float* next0, int next_pitch,
+                     const CandSink* sink, cudaStream_t st)
 {
     switch (R) {
-#define PSB_CASE(N) case N: return run_march<N>(o, level, t, next0, next_pitch, st);
+#define PSB_CASE(N) case N: return run_march<N>(o, level, t, next0, next_pitch, sink, st);
         PSB_CASE(3) PSB_CASE(4) PSB_CASE(5) PSB_CASE(6) PSB_CASE(7) PSB_CASE(8) PSB_CASE(9) PSB_CASE(10)
         PSB_CASE(11) PSB_CASE(12) PSB_CASE(13) PSB_CASE(14) PSB_CASE(15) PSB_CASE(16)
 #undef PSB_CASE

@@ -102,7 +102,7 @@ size_t plane_budget(const ps_config& cfg, int w, int h, int levels)
     int32_t W[kMaxOctaves], H[kMaxOctaves];
     const int n = ps_geometry(&cfg, w, h, W, H);
     size_t total = 0;
-    for (int o = 0; o < n; ++o) total += round_up(W[o], 32) * (size_t)H[o] * (size_t)(2 * levels + 5);
+    for (int o = 0; o < n; ++o) total += round_up(W[o], 32) * (size_t)H[o] * (size_t)(3 * levels + 5);   // + `levels` candidate lists
     return total;
 }
 
@@ -122,6 +122,7 @@ int build_view(ps_ctx* ctx, Slot& s, int w, int h)
         v.plane = (size_t)v.pitch * v.h;
         v.gauss = s.d_planes + off;  off += v.plane * (L + 3);
         v.dog = s.d_planes + off;    off += v.plane * (L + 2);
+        v.cand = reinterpret_cast<uint32_t*>(s.d_planes + off);  off += v.plane * L;
     }
     if (off > s.planes_floats) return ctx->fail(PS_ERR_TOO_LARGE, "%dx%d exceeds the slot's plane memory", w, h);
     s.view.num_octaves = s.num_octaves;
@@ -141,6 +142,19 @@ bool fork_choice()
 // 4-byte cp.async)
 static inline size_t u8_pitch(int w) { return ((size_t)w + 3) & ~(size_t)3; }
 
+// The sink of Gaussian level l of octave o: DoG plane l-1 is scanned for extrema when 1 <= l-1 <= L.
+static bool level_sink(ps_ctx* ctx, Slot& s, int o, int l, CandSink& cs)
+{
+    const int L = ctx->levels;
+    if (!s.view.cands_filled || l < 2 || l > L + 1) return false;
+    const OctaveView& v = s.view.oct[o];
+    cs.list = v.cand + (size_t)(l - 2) * v.plane;
+    cs.count = &s.d_ct->cand_ct[o][l - 2];
+    cs.thr = extrema_threshold(ctx->k);
+    cs.cap = (int)(v.plane < (size_t)0x7fffffff ? v.plane : (size_t)0x7fffffff);
+    return true;
+}
+
 // Dependency graph of the pyramid: within an octave level l needs level l-1; octave o+1 needs only level L
 // of octave o.  Levels L+1 and L+2 of octave o are therefore issued on the slot's side stream and overlap
 // the (much smaller) next octaves, which would otherwise run alone at a fraction of the GPU.
@@ -149,6 +163,12 @@ int run_pyramid(ps_ctx* ctx, Slot& s)
     const int L = ctx->levels;
     const bool fork = fork_choice() && s.num_octaves > 1;
     int n = 0, r;
+    // the pyramid kernels report the threshold-passing DoG samples when every scanned level runs on the
+    // marching kernels (16-bit coordinates in the lists)
+    bool collects = L <= kMaxLevels;
+    for (int l = 2; l <= L + 1 && collects; ++l) collects = blur_level_collects(ctx->rows[l]);
+    for (int o = 0; o < s.num_octaves && collects; ++o) collects = s.view.oct[o].w <= 65535 && s.view.oct[o].h <= 65535;
+    s.view.cands_filled = collects ? 1 : 0;
     if (s.is_float)
         r = launch_level0_f32(reinterpret_cast<const float*>(s.d_img), (size_t)s.w, s.w, s.h, ctx->cfg.upscale,
                               ctx->cfg.sift_mode, s.view.oct[0], ctx->dd0, ctx->rows[0], s.stream);
@@ -171,7 +191,9 @@ int run_pyramid(ps_ctx* ctx, Slot& s)
                 }
                 st = s.side;
             }
-            r = launch_blur_level(s.view.oct[o], l, ctx->rows[l], next, st);
+            CandSink cs;
+            const bool has_sink = level_sink(ctx, s, o, l, cs);
+            r = launch_blur_level(s.view.oct[o], l, ctx->rows[l], next, has_sink ? &cs : nullptr, st);
             if (r < 0) return ctx->fail(PS_ERR_ARG, "unsupported filter span %d", ctx->rows[l].span);
             n += r;
         }
@@ -551,6 +573,8 @@ extern "C" int ps_run_pyramid_only(ps_ctx* ctx, int slot)
     if (!s) return PS_ERR_ARG;
     if (!s->submitted) return ctx->fail(PS_ERR_STATE, "ps_run_pyramid_only: nothing submitted");
     PS_CUDA(ctx, cudaSetDevice(ctx->device));
+    // a repeated pyramid appends its candidates again: start from empty lists like a submit does
+    PS_CUDA(ctx, cudaMemsetAsync(s->d_ct->cand_ct, 0, sizeof(s->d_ct->cand_ct), s->stream));
     return run_pyramid(ctx, *s);
 }
 
@@ -571,7 +595,10 @@ extern "C" int ps_run_level_only(ps_ctx* ctx, int slot, int octave, int level)
                                            s->view.oct[0], ctx->dd0, ctx->rows[0], s->stream);
     } else {
         const OctaveView* next = (level == L && octave + 1 < s->num_octaves) ? &s->view.oct[octave + 1] : nullptr;
-        r = launch_blur_level(s->view.oct[octave], level, ctx->rows[level], next, s->stream);
+        CandSink cs;
+        const bool has_sink = level_sink(ctx, *s, octave, level, cs);
+        if (has_sink) PS_CUDA(ctx, cudaMemsetAsync(cs.count, 0, sizeof(int), s->stream));
+        r = launch_blur_level(s->view.oct[octave], level, ctx->rows[level], next, has_sink ? &cs : nullptr, s->stream);
     }
     if (r < 0) return ctx->fail(PS_ERR_ARG, "unsupported filter span");
     ctx->launches += r;

@@ -3,6 +3,7 @@
 #include "popsift_b200.h"
 
 #include <cuda_runtime.h>
+#include <cmath>
 #include <cstdint>
 
 namespace psb {
@@ -10,6 +11,7 @@ namespace psb {
 constexpr int kMaxOctaves = PS_MAX_OCTAVES;
 constexpr int kMaxPlanes  = PS_GAUSS_LEVELS + 3;   // L+3 <= 15
 constexpr int kOriBins    = 36;                    // reference sift_constants.h:41
+constexpr int kMaxLevels  = PS_GAUSS_LEVELS;
 
 // A candidate from the DoG scan (reference InitialExtremum, sift_extremum.h:25-39, without
 // the grid-filter fields).
@@ -28,12 +30,16 @@ struct Counters {
     int work_ori;              // work-stealing cursors
     int work_desc;
     int pad_[3];
+    // DoG samples with |value| >= threshold, appended by the pyramid kernels (see CandSink); may exceed
+    // the list capacity (clamp on use)
+    int cand_ct[kMaxOctaves][kMaxLevels];
 };
 
 // One octave's planes in HBM: linear float32, row pitch a multiple of 32 floats (128 B).
 struct OctaveView {
     float* gauss;       // (levels+3) planes, plane stride = plane
     float* dog;         // (levels+2) planes
+    uint32_t* cand;     // levels candidate lists (x | y << 16), `plane` entries each; list q belongs to DoG plane q+1
     int    w, h;
     int    pitch;       // floats per row
     size_t plane;       // floats per plane = pitch * h
@@ -44,6 +50,17 @@ struct PyramidView {
     OctaveView oct[kMaxOctaves];
     int        num_octaves;
     int        levels;      // L
+    int        cands_filled;   // the pyramid kernels appended the candidate lists of this image
+};
+
+// Where a pyramid kernel reports the DoG samples that pass the peak threshold while it writes the DoG
+// plane: the extrema stage then only visits those (a few per thousand pixels) instead of scanning
+// every plane again.
+struct CandSink {
+    uint32_t* list;     // x | y << 16
+    int*      count;    // device counter (Counters::cand_ct)
+    float     thr;
+    int       cap;
 };
 
 // Small constants consumed by the extrema / orientation / descriptor kernels
@@ -62,6 +79,16 @@ struct Consts {
     int   up_fac;           // int(upscale), reference sift_pyramid.cu:297
 };
 
+// |DoG| below this can never be an extremum (reference s_extrema.cu:425-440: the three modes' pre-test)
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline float extrema_threshold(const Consts& k)
+{
+    // float(0.8) * 2 == float(1.6): the VLFeat and PopSift expressions agree bit for bit
+    return k.sift_mode == PS_MODE_OPENCV ? floorf(k.threshold) : 1.6f * k.threshold;
+}
+
 // ---- launchers (defined in the k_*.cu files); all asynchronous on `st`, return #kernels launched
 
 struct GaussRow { float tap[PS_GAUSS_ALIGN]; int span; };
@@ -73,7 +100,11 @@ int launch_level0_f32(const float* img, size_t img_pitch_floats, int w, int h, f
                       const OctaveView& o0, const GaussRow& dd, const GaussRow& inc0, cudaStream_t st);
 // level l >= 1 of one octave: blur level l-1 -> level l, DoG[l-1] = G[l]-G[l-1]; if next0 != nullptr
 // also writes every second pixel into the next octave's level 0.
-int launch_blur_level(const OctaveView& o, int level, const GaussRow& g, const OctaveView* next, cudaStream_t st);
+// `sink` (optional) receives the threshold-passing samples of the DoG plane; only honoured when
+// blur_level_collects(g) is true.
+int launch_blur_level(const OctaveView& o, int level, const GaussRow& g, const OctaveView* next, const CandSink* sink,
+                      cudaStream_t st);
+bool blur_level_collects(const GaussRow& g);
 
 int launch_find_extrema(const PyramidView& pyr, const Consts& k, InitialExtremum* iext, Counters* ct, cudaStream_t st);
 int launch_orientation(const PyramidView& pyr, const Consts& k, const InitialExtremum* iext, ps_extremum* ext,
