@@ -278,68 +278,92 @@ find_extrema_kernel(PyramidView pyr, Consts k, ScanParams sp, InitialExtremum* _
 
 // ---- candidate-driven scan ---------------------------------------------------------------------
 //
-// The pyramid kernels append every DoG sample with |value| >= threshold to a per-(octave, level) list
-// while they write the plane (CandSink).  On real and synthetic images that is a few samples per
-// thousand, so testing only those against their 26 neighbours (early exit on the first neighbour that
-// beats them) replaces the dense scan's read of every DoG plane: one thread per candidate, grid-stride
-// over the concatenated lists, no host round trip (the counts are read from the device counters).
-// Accepted set and refinement are those of the dense kernel: same comparisons, same refine<MODE>.
+// The pyramid kernels report every DoG pixel pair in which a sample has |value| >= threshold into the
+// list region of the block that produced it (CandSink) while they write the plane.  On real and
+// synthetic images that is a few samples per thousand, so testing only those against their 26
+// neighbours replaces the dense scan's read of every DoG plane.  One block per list region, one thread
+// per sample, grid-stride over the regions of all octaves and levels: no host round trip, no shared
+// memory; the only atomics are the final appends.  Accepted set and refinement are those of the dense
+// kernel: same comparisons, same refine<MODE>.
+constexpr int kScanThreads = 256;
+
+// one octave's DoG planes, by value (a reference to the kernel's PyramidView parameter would make every
+// thread copy the whole structure to local memory)
+struct DogOct { const float* dog; int w, h, pitch, nplanes; size_t plane; };
+
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__device__ __noinline__ void test_candidate(const DogOct ov, const Consts& k, int o, int level, float thr, int x, int y,
+                                            InitialExtremum* __restrict__ iext, Counters* ct)
+{
+    const int W = ov.w, H = ov.h;
+    bool inside = x >= 1 && x <= W - 2 && y >= 1 && y <= H - 2;
+    if (MODE == PS_MODE_OPENCV) inside = inside && !(x < 5 || x >= W - 5) && !(y < 5 || y >= H - 5);
+    if (!inside) return;
+    const float* pc = ov.dog + (size_t)level * ov.plane + (size_t)y * ov.pitch + x;
+    const float c = __ldg(pc);
+    if (!(fabsf(c) >= thr)) return;
+    // strict maximum or strict minimum of the 3x3x3 neighbourhood.  The loads of a plane are issued
+    // together (the test is bound by memory latency, not by instructions); most samples are beaten by an
+    // in-plane neighbour and stop after the first batch.
+    bool ismax = true, ismin = true;
+    auto beat = [&](float n) { ismax = ismax && c > n; ismin = ismin && c < n; };
+    {
+        const float* ra = pc - ov.pitch;
+        const float* rb = pc + ov.pitch;
+        const float n0 = __ldg(pc - 1), n1 = __ldg(pc + 1);
+        const float n2 = __ldg(ra - 1), n3 = __ldg(ra), n4 = __ldg(ra + 1);
+        const float n5 = __ldg(rb - 1), n6 = __ldg(rb), n7 = __ldg(rb + 1);
+        beat(n0); beat(n1); beat(n2); beat(n3); beat(n4); beat(n5); beat(n6); beat(n7);
+    }
+    if (!(ismax || ismin)) return;
+#pragma unroll
+    for (int dz = -1; dz <= 1; dz += 2) {
+        const float* p = dz < 0 ? pc - ov.plane : pc + ov.plane;
+        const float* ra = p - ov.pitch;
+        const float* rb = p + ov.pitch;
+        const float n0 = __ldg(p - 1), n1 = __ldg(p), n2 = __ldg(p + 1);
+        const float n3 = __ldg(ra - 1), n4 = __ldg(ra), n5 = __ldg(ra + 1);
+        const float n6 = __ldg(rb - 1), n7 = __ldg(rb), n8 = __ldg(rb + 1);
+        beat(n0); beat(n1); beat(n2); beat(n3); beat(n4); beat(n5); beat(n6); beat(n7); beat(n8);
+    }
+    if (!(ismax || ismin)) return;
+
+    DogView dv;
+    dv.base = ov.dog; dv.w = W; dv.h = H; dv.pitch = ov.pitch; dv.plane = ov.plane;
+    dv.nplanes = ov.nplanes;
+    InitialExtremum e;
+    e.xpos = e.ypos = e.sigma = 0.f; e.lpos = 0;
+    if (refine<MODE>(dv, k, x, y, level, ov.nplanes, c, e)) {
+        const int idx = atomicAdd(&ct->ext_ct[o], 1);
+        if (idx < k.max_extrema) iext[(size_t)o * k.max_extrema + idx] = e;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kScanThreads, 4)
 cand_extrema_kernel(PyramidView pyr, Consts k, InitialExtremum* __restrict__ iext, Counters* ct)
 {
     const int L = pyr.levels;
-    const int nseg = pyr.num_octaves * L;
-    const int maxlevel = L + 2;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    int seg = -1;
-    long long seg_end = 0, seg_begin = 0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;; i += stride) {
-        while (i >= seg_end) {
-            if (++seg >= nseg) return;
-            const int o = seg / L, q = seg - o * L;
-            const long long cap = (long long)pyr.oct[o].plane;
-            long long n = ct->cand_ct[o][q];
-            if (n > cap) n = cap;
-            seg_begin = seg_end;
-            seg_end += n;
+    const float thr = extrema_threshold(k);
+    int o = 0;
+    long long oct_begin = 0, oct_end = (long long)pyr.oct[0].cand_blocks * L;     // regions of octave o
+    for (long long r = blockIdx.x;; r += gridDim.x) {
+        while (r >= oct_end) {
+            if (++o >= pyr.num_octaves) return;
+            oct_begin = oct_end;
+            oct_end += (long long)pyr.oct[o].cand_blocks * L;
         }
-        const int o = seg / L, q = seg - o * L;
         const OctaveView& ov = pyr.oct[o];
-        const unsigned packed = ov.cand[(size_t)q * ov.plane + (size_t)(i - seg_begin)];
-        const int x = (int)(packed & 0xffffu), y = (int)(packed >> 16);
-        const int W = ov.w, H = ov.h;
-        bool inside = x >= 1 && x <= W - 2 && y >= 1 && y <= H - 2;
-        if (MODE == PS_MODE_OPENCV) inside = inside && !(x < 5 || x >= W - 5) && !(y < 5 || y >= H - 5);
-        if (!inside) continue;
-        const int level = q + 1;                                  // DoG plane of the candidate
-        const float* pc = ov.dog + (size_t)level * ov.plane + (size_t)y * ov.pitch + x;
-        const float c = __ldg(pc);
-        // strict maximum or strict minimum of the 3x3x3 neighbourhood
-        bool ismax = true, ismin = true;
-        auto beat = [&](float n) { ismax = ismax && c > n; ismin = ismin && c < n; };
-        auto row3 = [&](const float* r) { beat(__ldg(r - 1)); beat(__ldg(r)); beat(__ldg(r + 1)); };
-        beat(__ldg(pc - 1)); beat(__ldg(pc + 1));
-        if (!(ismax || ismin)) continue;
-        row3(pc - ov.pitch);
-        if (!(ismax || ismin)) continue;
-        row3(pc + ov.pitch);
-        if (!(ismax || ismin)) continue;
-        const float* pb = pc - ov.plane;
-        row3(pb - ov.pitch); row3(pb); row3(pb + ov.pitch);
-        if (!(ismax || ismin)) continue;
-        const float* pa = pc + ov.plane;
-        row3(pa - ov.pitch); row3(pa); row3(pa + ov.pitch);
-        if (!(ismax || ismin)) continue;
-
-        DogView dv;
-        dv.base = ov.dog; dv.w = W; dv.h = H; dv.pitch = ov.pitch; dv.plane = ov.plane;
-        dv.nplanes = L + 2;
-        InitialExtremum e;
-        e.xpos = e.ypos = e.sigma = 0.f; e.lpos = 0;
-        if (refine<MODE>(dv, k, x, y, level, maxlevel, c, e)) {
-            const int idx = atomicAdd(&ct->ext_ct[o], 1);
-            if (idx < k.max_extrema) iext[(size_t)o * k.max_extrema + idx] = e;
+        const int local = (int)(r - oct_begin);                   // q * cand_blocks + block
+        const int count = min(__ldg(ov.cand_cnt + local), ov.cand_region);
+        if (count == 0) continue;
+        const int level = local / ov.cand_blocks + 1;             // DoG plane of the region's samples
+        DogOct dogv;
+        dogv.dog = ov.dog; dogv.w = ov.w; dogv.h = ov.h; dogv.pitch = ov.pitch; dogv.plane = ov.plane; dogv.nplanes = L + 2;
+        const unsigned* list = ov.cand + (size_t)local * ov.cand_region;
+        for (int e = threadIdx.x; e < 2 * count; e += kScanThreads) {
+            const unsigned packed = __ldg(list + (e >> 1));
+            test_candidate<MODE>(dogv, k, o, level, thr, (int)(packed & 0xffffu) + (e & 1), (int)(packed >> 16), iext, ct);
         }
     }
 }
@@ -355,7 +379,7 @@ template <int MODE>
 int launch_scan(const PyramidView& pyr, const Consts& k, InitialExtremum* iext, Counters* ct, cudaStream_t st)
 {
     if (pyr.cands_filled && !dense_choice()) {
-        cand_extrema_kernel<MODE><<<148 * 8, 256, 0, st>>>(pyr, k, iext, ct);
+        cand_extrema_kernel<MODE><<<148 * 4, kScanThreads, 0, st>>>(pyr, k, iext, ct);
         return 1;
     }
     int launches = 0;

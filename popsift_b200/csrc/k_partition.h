@@ -94,4 +94,21 @@ inline Partition make_partition(int W, int H, int TW, int Q, int slots, bool uni
     return p;
 }
 
+// ---- candidate regions -----------------------------------------------------------------------
+// Every block of a level kernel owns a private region of the level's candidate list, large enough for
+// every pixel pair of its segment (units * Q rows x TW/2 pairs), and a count: reporting a candidate needs
+// a shared-memory counter only, never a global atomic.
+inline int cand_region_cap(const Partition& p, int TW, int Q) { return (p.uh > p.ul ? p.uh : p.ul) * Q * (TW / 2); }
+
+inline long long cand_entries(const Partition& p, int TW, int Q) { return (long long)p.B * cand_region_cap(p, TW, Q); }
+
+// upper bound of cand_entries(make_partition(W, H, ...)) that is monotonic in W and H (memory budget)
+inline long long cand_entry_bound(int W, int H, int TW, int Q, int slots)
+{
+    const long long S = (W + TW - 1) / TW, C = (H + Q - 1) / Q;
+    long long n = slots / S;
+    if (n < 1) n = 1;
+    return (S * (C + C / n + 5) + 4LL * slots + 3 * S) * Q * (TW / 2);
+}
+
 } // namespace psb

@@ -331,6 +331,9 @@ int launch_level0_f32(const float* img, size_t img_pitch_floats, int w, int h, f
 }
 
 bool blur_level_collects(const GaussRow& g) { return use_march() && march_supports(g.span - 1); }
+int cand_blocks_for(int w, int h) { return march_cand_blocks(w, h); }
+int cand_region_for(int w, int h) { return march_cand_region(w, h); }
+long long cand_entry_bound_for(int w, int h) { return march_cand_entry_bound(w, h); }
 
 int launch_blur_level(const OctaveView& o, int level, const GaussRow& g, const OctaveView* next, const CandSink* sink,
                       cudaStream_t st)

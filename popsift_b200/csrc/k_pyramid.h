@@ -10,6 +10,10 @@ struct alignas(16) Taps { float g[PS_GAUSS_ALIGN]; };   // one half-kernel, pass
 int march_blur_level(const OctaveView& o, int level, const Taps& t, int R, float* next0, int next_pitch,
                      const CandSink* sink, cudaStream_t st);
 bool march_supports(int R);
+// candidate list layout of a level kernel over a w x h plane
+int march_cand_blocks(int w, int h);
+int march_cand_region(int w, int h);
+long long march_cand_entry_bound(int w, int h);
 int march_level0_u8(const uint8_t* img, size_t img_pitch, int w, int h, float shift, const OctaveView& o0,
                     const Taps& dd, const Taps& inc0, int R, cudaStream_t st);
 int march_level0_f32(const float* img, size_t img_pitch, int w, int h, float shift, const OctaveView& o0,

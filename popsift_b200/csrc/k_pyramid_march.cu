@@ -199,43 +199,19 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm(
 
 constexpr int QH = Q / 2;   // output rows per thread in the column pass
 
-// Rare path of the column pass: append the threshold-passing DoG samples of a warp's 64 x QH block to
-// the level's candidate list (one atomic per warp).  Bit 2*jj + i of `pm`: sample (x + i, y0 + jj).
-__device__ __noinline__ void append_cands(const CandSink cs, unsigned pm, int x, int y0)
-{
-    const unsigned lane = threadIdx.x & 31;
-    const int n = __popc(pm);
-    int incl = n;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((int)lane >= o) incl += t;
-    }
-    int base = 0;
-    if (lane == 31) base = atomicAdd(cs.count, incl);
-    base = __shfl_sync(0xffffffffu, base, 31);
-    int idx = base + incl - n;
-    while (pm) {
-        const int b = __ffs(pm) - 1;
-        pm &= pm - 1;
-        if (idx < cs.cap) cs.list[idx] = (unsigned)(x + (b & 1)) | ((unsigned)(y0 + (b >> 1)) << 16);
-        ++idx;
-    }
-}
-
-// All 32 lanes of a warp run the whole column pass (lanes right of the image only skip their stores),
-// so the candidate vote can use the full mask.
+// Candidates (CandSink): a lane notes the rows in which one of its two DoG samples passes the peak
+// threshold -- one compare pair and one predicated OR per row in the hot loop -- and afterwards, if it
+// has any, reserves entries of the block's list region with ONE shared-memory atomic and stores them.
 template <int R, bool WRITE_DOG, bool NEXT, bool GUARD, bool CAND>
 __device__ __forceinline__ void col_emit(const f32x2 (&win)[QH + 2 * R], const float* __restrict__ Scur,
                                          const float* __restrict__ Sprev, int jbase, int y_first, int ys, int ye,
                                          float* __restrict__ pd, float* __restrict__ pg, float* __restrict__ pn,
-                                         int pitch, int next_pitch, const Taps& t, const CandSink& sink, int x, int W)
+                                         int pitch, int next_pitch, const Taps& t, const CandSink& sink, int* cand_n, int x, int W)
 {
     using G = Geo<R>;
     const int c2 = 2 * (threadIdx.x & 63);
     const int par = y_first & 1;
     const bool col_in = !GUARD || x < W;            // GUARD: the pair may start right of the image
-    const bool pair_in = !GUARD || x + 1 < W;
     unsigned pm = 0;
 #pragma unroll
     for (int jj = 0; jj < QH; ++jj) {
@@ -260,8 +236,9 @@ __device__ __forceinline__ void col_emit(const f32x2 (&win)[QH + 2 * R], const f
                 const float g0 = __fsub_rn(a0, cs.x), g1 = __fsub_rn(a1, cs.y);
                 *reinterpret_cast<float2*>(pg) = make_float2(g0, g1);
                 if (CAND) {
-                    if (fabsf(g0) >= sink.thr) pm |= 1u << (2 * jj);
-                    if (pair_in && fabsf(g1) >= sink.thr) pm |= 2u << (2 * jj);
+                    // (a pair that straddles the right border may report garbage in its second sample: the
+                    // extrema stage re-tests every sample and ignores border columns)
+                    if (fabsf(g0) >= sink.thr || fabsf(g1) >= sink.thr) pm |= 1u << jj;
                 }
             }
             if (NEXT && ((j & 1) == par)) pn[(size_t)((y_first + j) >> 1) * next_pitch] = a0;
@@ -270,7 +247,16 @@ __device__ __forceinline__ void col_emit(const f32x2 (&win)[QH + 2 * R], const f
         if (WRITE_DOG) pg += pitch;
     }
     if (CAND) {
-        if (__any_sync(0xffffffffu, pm != 0u)) append_cands(sink, pm, x, y_first + jbase);
+        if (pm != 0u) {
+            const int idx = atomicAdd(cand_n, __popc(pm));
+            unsigned* out = sink.list + (size_t)blockIdx.x * sink.region + idx;
+            const int y0 = y_first + jbase;
+            do {
+                const int b = __ffs(pm) - 1;
+                pm &= pm - 1;
+                *out++ = (unsigned)x | ((unsigned)(y0 + b) << 16);
+            } while (pm);
+        }
     }
 }
 
@@ -279,7 +265,7 @@ __device__ __forceinline__ void col_pass(const float* __restrict__ HB, const flo
                                          const float* __restrict__ Sprev, int slot_oldest, int y_first,
                                          int ys, int ye, int x0, int W, float* __restrict__ dst, float* __restrict__ dog,
                                          float* __restrict__ next0, int pitch, int next_pitch, const Taps& t,
-                                         const CandSink& sink = CandSink())
+                                         const CandSink& sink = CandSink(), int* cand_n = nullptr)
 {
     using G = Geo<R>;
     const int c2 = 2 * (threadIdx.x & 63);
@@ -303,15 +289,16 @@ __device__ __forceinline__ void col_pass(const float* __restrict__ HB, const flo
     float* pg = WRITE_DOG ? dog + o : nullptr;
     float* pn = NEXT ? next0 + (x >> 1) : nullptr;
     if (yb >= ys && yb + QH <= ye && x0 + TW <= W)
-        col_emit<R, WRITE_DOG, NEXT, false, CAND>(win, Scur, Sprev, jbase, y_first, ys, ye, pd, pg, pn, pitch, next_pitch, t, sink, x, W);
+        col_emit<R, WRITE_DOG, NEXT, false, CAND>(win, Scur, Sprev, jbase, y_first, ys, ye, pd, pg, pn, pitch, next_pitch, t, sink, cand_n, x, W);
     else
-        col_emit<R, WRITE_DOG, NEXT, true, CAND>(win, Scur, Sprev, jbase, y_first, ys, ye, pd, pg, pn, pitch, next_pitch, t, sink, x, W);
+        col_emit<R, WRITE_DOG, NEXT, true, CAND>(win, Scur, Sprev, jbase, y_first, ys, ye, pd, pg, pn, pitch, next_pitch, t, sink, cand_n, x, W);
 }
 
 template <int R, bool EDGE, bool NEXT, bool CAND>
 __device__ __forceinline__ void march_body(float* __restrict__ smem, const float* __restrict__ src, float* __restrict__ dst,
                                            float* __restrict__ dog, float* __restrict__ next0, int W, int H, int pitch,
-                                           int next_pitch, int x0, int ys, int ye, const Taps& taps, const CandSink& sink)
+                                           int next_pitch, int x0, int ys, int ye, const Taps& taps, const CandSink& sink,
+                                           int* cand_n)
 {
     using G = Geo<R>;
     constexpr int SB = Q * G::SWP;         // floats per staging buffer (buffer b starts at smem + b*SB)
@@ -346,12 +333,13 @@ __device__ __forceinline__ void march_body(float* __restrict__ smem, const float
         int slot_old = slot_in + Q;       // oldest line = the one after the newest
         if (slot_old >= G::RING) slot_old -= G::RING;
         col_pass<R, true, NEXT, CAND>(HB, Scur, Sprev, slot_old, ys - 2 * R + k * Q, ys, ye, x0, W, dst, dog, next0, pitch,
-                                      next_pitch, taps, sink);
+                                      next_pitch, taps, sink, cand_n);
         slot_in = slot_old;
         cur = cur == G::NBUF - 1 ? 0 : cur + 1;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();                      // the next sub-segment reuses the buffers
+    __syncthreads();                      // last column pass finished
+    if (CAND && threadIdx.x == 0) sink.counts[blockIdx.x] = *cand_n;
 }
 
 template <int R, bool NEXT, bool CAND>
@@ -365,8 +353,10 @@ march_level_kernel(const float* __restrict__ src, float* __restrict__ dst, float
     if (!locate(part, blockIdx.x, H, Q, strip, ys, ye)) return;
     const int x0 = strip * TW;
     const bool edge = (x0 - G::RP < 0) || (x0 + TW + G::RP > W);
-    if (!edge) march_body<R, false, NEXT, CAND>(smem, src, dst, dog, next0, W, H, pitch, next_pitch, x0, ys, ye, taps, sink);
-    else       march_body<R, true, NEXT, CAND>(smem, src, dst, dog, next0, W, H, pitch, next_pitch, x0, ys, ye, taps, sink);
+    __shared__ int s_cand_n;                         // candidates of this block so far
+    if (CAND && threadIdx.x == 0) s_cand_n = 0;      // published by the first barrier of the chunk loop
+    if (!edge) march_body<R, false, NEXT, CAND>(smem, src, dst, dog, next0, W, H, pitch, next_pitch, x0, ys, ye, taps, sink, &s_cand_n);
+    else       march_body<R, true, NEXT, CAND>(smem, src, dst, dog, next0, W, H, pitch, next_pitch, x0, ys, ye, taps, sink, &s_cand_n);
 }
 
 // ---- octave 0, level 0 from the input image -----------------------------------------------------
@@ -644,7 +634,7 @@ int run_march(const OctaveView& o, int level, const Taps& t, float* next0, int n
     const float* src = o.gauss + o.plane * (level - 1);
     float* dst = o.gauss + o.plane * level;
     float* dog = o.dog + o.plane * (level - 1);
-    const bool cand = sink && sink->list && o.w <= 65535 && o.h <= 65535;
+    const bool cand = sink && sink->list && o.w <= 65535 && o.h <= 65535 && sink->region == cand_region_cap(part, TW, Q);
     const CandSink cs = cand ? *sink : CandSink();
     if (next0) { if (cand) launch_march<R, true, true>(part, src, dst, dog, next0, o, next_pitch, t, cs, st);
                  else      launch_march<R, true, false>(part, src, dst, dog, next0, o, next_pitch, t, cs, st); }
@@ -678,6 +668,9 @@ int run_march0(const PIX* img, size_t img_pitch, int w, int h, float shift, cons
 } // namespace
 
 bool march_supports(int R) { return R >= 3 && R <= 16; }
+int march_cand_blocks(int w, int h) { return make_partition(w, h).B; }
+int march_cand_region(int w, int h) { return cand_region_cap(make_partition(w, h), TW, Q); }
+long long march_cand_entry_bound(int w, int h) { return cand_entry_bound(w, h, TW, Q, 592); }
 
 int march_blur_level(const OctaveView& o, int level, const Taps& t, int R, float* next0, int next_pitch,
                      const CandSink* sink, cudaStream_t st)

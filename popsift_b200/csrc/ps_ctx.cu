@@ -36,6 +36,8 @@ struct Slot {
     // pyramid
     float*  d_planes = nullptr;
     size_t  planes_floats = 0;
+    int*    cand_cnt = nullptr;    // candidate counts of all octaves, levels and blocks (inside d_planes)
+    size_t  cand_cnt_bytes = 0;
     PyramidView view{};
     // detections
     InitialExtremum* d_iext = nullptr;
@@ -102,7 +104,11 @@ size_t plane_budget(const ps_config& cfg, int w, int h, int levels)
     int32_t W[kMaxOctaves], H[kMaxOctaves];
     const int n = ps_geometry(&cfg, w, h, W, H);
     size_t total = 0;
-    for (int o = 0; o < n; ++o) total += round_up(W[o], 32) * (size_t)H[o] * (size_t)(3 * levels + 5);   // + `levels` candidate lists
+    for (int o = 0; o < n; ++o) {
+        total += round_up(W[o], 32) * (size_t)H[o] * (size_t)(2 * levels + 5);
+        // candidate lists of the `levels` scanned DoG planes + one count per block (<= 4096 blocks... generous)
+        total += ((size_t)cand_entry_bound_for(W[o], H[o]) + 8192) * (size_t)levels;
+    }
     return total;
 }
 
@@ -122,8 +128,17 @@ int build_view(ps_ctx* ctx, Slot& s, int w, int h)
         v.plane = (size_t)v.pitch * v.h;
         v.gauss = s.d_planes + off;  off += v.plane * (L + 3);
         v.dog = s.d_planes + off;    off += v.plane * (L + 2);
-        v.cand = reinterpret_cast<uint32_t*>(s.d_planes + off);  off += v.plane * L;
+        v.cand_blocks = cand_blocks_for(v.w, v.h);
+        v.cand_region = cand_region_for(v.w, v.h);
+        v.cand = reinterpret_cast<uint32_t*>(s.d_planes + off);  off += (size_t)v.cand_blocks * v.cand_region * L;
     }
+    // all block counts in one piece: zeroed with one memset per image
+    s.cand_cnt = reinterpret_cast<int*>(s.d_planes + off);
+    for (int o = 0; o < s.num_octaves; ++o) {
+        OctaveView& v = s.view.oct[o];
+        v.cand_cnt = reinterpret_cast<int*>(s.d_planes + off);  off += (size_t)v.cand_blocks * L;
+    }
+    s.cand_cnt_bytes = (size_t)(reinterpret_cast<int*>(s.d_planes + off) - s.cand_cnt) * sizeof(int);
     if (off > s.planes_floats) return ctx->fail(PS_ERR_TOO_LARGE, "%dx%d exceeds the slot's plane memory", w, h);
     s.view.num_octaves = s.num_octaves;
     s.view.levels = L;
@@ -148,10 +163,10 @@ static bool level_sink(ps_ctx* ctx, Slot& s, int o, int l, CandSink& cs)
     const int L = ctx->levels;
     if (!s.view.cands_filled || l < 2 || l > L + 1) return false;
     const OctaveView& v = s.view.oct[o];
-    cs.list = v.cand + (size_t)(l - 2) * v.plane;
-    cs.count = &s.d_ct->cand_ct[o][l - 2];
+    cs.list = v.cand + (size_t)(l - 2) * v.cand_blocks * v.cand_region;
+    cs.counts = v.cand_cnt + (size_t)(l - 2) * v.cand_blocks;
     cs.thr = extrema_threshold(ctx->k);
-    cs.cap = (int)(v.plane < (size_t)0x7fffffff ? v.plane : (size_t)0x7fffffff);
+    cs.region = v.cand_region;
     return true;
 }
 
@@ -214,6 +229,7 @@ static int submit_common(ps_ctx* ctx, Slot& s)
     const bool tm = ctx->timing;
     int rc;
     PS_CUDA(ctx, cudaMemsetAsync(s.d_ct, 0, sizeof(Counters), s.stream));
+    PS_CUDA(ctx, cudaMemsetAsync(s.cand_cnt, 0, s.cand_cnt_bytes, s.stream));
     if (tm) PS_CUDA(ctx, cudaEventRecord(s.ev[1], s.stream));
     if ((rc = run_pyramid(ctx, s)) != PS_OK) return rc;
     if (tm) PS_CUDA(ctx, cudaEventRecord(s.ev[2], s.stream));
@@ -573,8 +589,8 @@ extern "C" int ps_run_pyramid_only(ps_ctx* ctx, int slot)
     if (!s) return PS_ERR_ARG;
     if (!s->submitted) return ctx->fail(PS_ERR_STATE, "ps_run_pyramid_only: nothing submitted");
     PS_CUDA(ctx, cudaSetDevice(ctx->device));
-    // a repeated pyramid appends its candidates again: start from empty lists like a submit does
-    PS_CUDA(ctx, cudaMemsetAsync(s->d_ct->cand_ct, 0, sizeof(s->d_ct->cand_ct), s->stream));
+    // start from empty candidate tiles like a submit does
+    PS_CUDA(ctx, cudaMemsetAsync(s->cand_cnt, 0, s->cand_cnt_bytes, s->stream));
     return run_pyramid(ctx, *s);
 }
 
@@ -597,7 +613,8 @@ extern "C" int ps_run_level_only(ps_ctx* ctx, int slot, int octave, int level)
         const OctaveView* next = (level == L && octave + 1 < s->num_octaves) ? &s->view.oct[octave + 1] : nullptr;
         CandSink cs;
         const bool has_sink = level_sink(ctx, *s, octave, level, cs);
-        if (has_sink) PS_CUDA(ctx, cudaMemsetAsync(cs.count, 0, sizeof(int), s->stream));
+        if (has_sink)
+            PS_CUDA(ctx, cudaMemsetAsync(cs.counts, 0, sizeof(int) * (size_t)s->view.oct[octave].cand_blocks, s->stream));
         r = launch_blur_level(s->view.oct[octave], level, ctx->rows[level], next, has_sink ? &cs : nullptr, s->stream);
     }
     if (r < 0) return ctx->fail(PS_ERR_ARG, "unsupported filter span");

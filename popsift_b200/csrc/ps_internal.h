@@ -30,16 +30,17 @@ struct Counters {
     int work_ori;              // work-stealing cursors
     int work_desc;
     int pad_[3];
-    // DoG samples with |value| >= threshold, appended by the pyramid kernels (see CandSink); may exceed
-    // the list capacity (clamp on use)
-    int cand_ct[kMaxOctaves][kMaxLevels];
 };
 
 // One octave's planes in HBM: linear float32, row pitch a multiple of 32 floats (128 B).
 struct OctaveView {
     float* gauss;       // (levels+3) planes, plane stride = plane
     float* dog;         // (levels+2) planes
-    uint32_t* cand;     // levels candidate lists (x | y << 16), `plane` entries each; list q belongs to DoG plane q+1
+    // candidate lists of the `levels` scanned DoG planes (see CandSink): level q (DoG plane q+1), block b of
+    // the level kernel owns entries [(q*cand_blocks + b) * cand_region, +cand_cnt[q*cand_blocks + b])
+    uint32_t* cand;
+    int*   cand_cnt;
+    int    cand_blocks, cand_region;
     int    w, h;
     int    pitch;       // floats per row
     size_t plane;       // floats per plane = pitch * h
@@ -53,14 +54,15 @@ struct PyramidView {
     int        cands_filled;   // the pyramid kernels appended the candidate lists of this image
 };
 
-// Where a pyramid kernel reports the DoG samples that pass the peak threshold while it writes the DoG
-// plane: the extrema stage then only visits those (a few per thousand pixels) instead of scanning
-// every plane again.
+// Where a pyramid kernel reports the DoG pixel pairs (x even) in which a sample passes the peak
+// threshold while it writes the DoG plane: the extrema stage then only visits those (a few per thousand
+// pixels) instead of scanning every plane again.  Each block of the kernel owns a private region of the
+// list and a count (zeroed per image), so the kernel needs a shared-memory counter but no global atomic.
 struct CandSink {
-    uint32_t* list;     // x | y << 16
-    int*      count;    // device counter (Counters::cand_ct)
+    uint32_t* list;     // blocks x region entries: x | y << 16 of the pair's left pixel
+    int*      counts;   // blocks
     float     thr;
-    int       cap;
+    int       region;   // entries per block
 };
 
 // Small constants consumed by the extrema / orientation / descriptor kernels
@@ -105,6 +107,11 @@ int launch_level0_f32(const float* img, size_t img_pitch_floats, int w, int h, f
 int launch_blur_level(const OctaveView& o, int level, const GaussRow& g, const OctaveView* next, const CandSink* sink,
                       cudaStream_t st);
 bool blur_level_collects(const GaussRow& g);
+// layout of the candidate lists of one w x h plane (k_partition.h): blocks, entries per block, and a
+// monotonic upper bound of blocks * entries (memory budget)
+int cand_blocks_for(int w, int h);
+int cand_region_for(int w, int h);
+long long cand_entry_bound_for(int w, int h);
 
 int launch_find_extrema(const PyramidView& pyr, const Consts& k, InitialExtremum* iext, Counters* ct, cudaStream_t st);
 int launch_orientation(const PyramidView& pyr, const Consts& k, const InitialExtremum* iext, ps_extremum* ext,

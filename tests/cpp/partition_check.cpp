@@ -16,12 +16,22 @@ int main()
                 const int S = (W + TW - 1) / TW;
                 if (p.strips != S || p.B < 1) { std::printf("FAIL strips/B W=%d H=%d\n", W, H); return 1; }
                 if (S <= slots && p.uh > 4 && p.B > slots) { std::printf("FAIL wave W=%d H=%d B=%d\n", W, H, p.B); return 1; }
+                if (psb::cand_entries(p, TW, Q) > psb::cand_entry_bound(W, H, TW, Q, slots)) {
+                    std::printf("FAIL candidate bound W=%d H=%d entries=%lld bound=%lld\n", W, H, psb::cand_entries(p, TW, Q),
+                                psb::cand_entry_bound(W, H, TW, Q, slots));
+                    return 1;
+                }
                 std::vector<int> cover((size_t)S * H, 0);
                 for (int b = 0; b < p.B; ++b) {
                     int strip = -1, ys = 0, ye = 0;
                     if (!psb::locate(p, b, H, Q, strip, ys, ye)) continue;
                     if (strip < 0 || strip >= S || ys < 0 || ye > H || ys >= ye || (ys % Q) != 0) {
                         std::printf("FAIL range W=%d H=%d b=%d strip=%d ys=%d ye=%d\n", W, H, b, strip, ys, ye);
+                        return 1;
+                    }
+                    // a block's candidate region holds every pixel pair of its segment
+                    if ((long long)(ye - ys) * (TW / 2) > psb::cand_region_cap(p, TW, Q)) {
+                        std::printf("FAIL region W=%d H=%d b=%d\n", W, H, b);
                         return 1;
                     }
                     for (int y = ys; y < ye; ++y) ++cover[(size_t)strip * H + y];
