@@ -339,32 +339,84 @@ __device__ __noinline__ void test_candidate(const DogOct ov, const Consts& k, in
     }
 }
 
+// Exclusive prefix sum of the list regions' counts (single block; every thread's loads are in flight at
+// once): sample t of the image then belongs to the region g with prefix[g] <= t/2 < prefix[g+1].
+__global__ void __launch_bounds__(1024)
+cand_prefix_kernel(const int* __restrict__ counts, int n, int* __restrict__ prefix)
+{
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int PER = 16;
+    for (int base = 0; base < n; base += 1024 * PER) {
+        const int first = base + threadIdx.x * PER;
+        int c[PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) c[j] = first + j < n ? max(counts[first + j], 0) : 0;
+        int sum = 0;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) sum += c[j];
+        int v = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane >= d) v += t;
+        }
+        if (lane == 31) warp_sums[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            int s = warp_sums[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, s, d);
+                if (lane >= d) s += t;
+            }
+            warp_sums[lane] = s;
+        }
+        __syncthreads();
+        int excl = carry + (warp ? warp_sums[warp - 1] : 0) + v - sum;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            if (first + j < n) prefix[first + j] = excl;
+            excl += c[j];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry += warp_sums[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) prefix[n] = carry;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kScanThreads, 4)
 cand_extrema_kernel(PyramidView pyr, Consts k, InitialExtremum* __restrict__ iext, Counters* ct)
 {
     const int L = pyr.levels;
     const float thr = extrema_threshold(k);
-    int o = 0;
-    long long oct_begin = 0, oct_end = (long long)pyr.oct[0].cand_blocks * L;     // regions of octave o
-    for (long long r = blockIdx.x;; r += gridDim.x) {
-        while (r >= oct_end) {
-            if (++o >= pyr.num_octaves) return;
-            oct_begin = oct_end;
-            oct_end += (long long)pyr.oct[o].cand_blocks * L;
+    const int nreg = pyr.cand_regions;
+    const int* __restrict__ prefix = pyr.cand_prefix;
+    const long long total = 2LL * __ldg(prefix + nreg);           // two samples per reported pair
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const int e = (int)(t >> 1);
+        // region g with prefix[g] <= e < prefix[g + 1]  (consecutive threads mostly share it: the loads broadcast)
+        int lo = 0, hi = nreg;                                   // invariant: prefix[lo] <= e < prefix[hi]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(prefix + mid) <= e) lo = mid; else hi = mid;
         }
+        int o = 0, local = lo;                                    // region -> octave, q * cand_blocks + block
+        while (local >= pyr.oct[o].cand_blocks * L) { local -= pyr.oct[o].cand_blocks * L; ++o; }
         const OctaveView& ov = pyr.oct[o];
-        const int local = (int)(r - oct_begin);                   // q * cand_blocks + block
-        const int count = min(__ldg(ov.cand_cnt + local), ov.cand_region);
-        if (count == 0) continue;
+        const int idx = e - __ldg(prefix + lo);
+        if (idx >= ov.cand_region) continue;                      // never: a region holds every pair of its block
         const int level = local / ov.cand_blocks + 1;             // DoG plane of the region's samples
         DogOct dogv;
         dogv.dog = ov.dog; dogv.w = ov.w; dogv.h = ov.h; dogv.pitch = ov.pitch; dogv.plane = ov.plane; dogv.nplanes = L + 2;
-        const unsigned* list = ov.cand + (size_t)local * ov.cand_region;
-        for (int e = threadIdx.x; e < 2 * count; e += kScanThreads) {
-            const unsigned packed = __ldg(list + (e >> 1));
-            test_candidate<MODE>(dogv, k, o, level, thr, (int)(packed & 0xffffu) + (e & 1), (int)(packed >> 16), iext, ct);
-        }
+        const unsigned packed = __ldg(ov.cand + (size_t)local * ov.cand_region + idx);
+        test_candidate<MODE>(dogv, k, o, level, thr, (int)(packed & 0xffffu) + (int)(t & 1), (int)(packed >> 16), iext, ct);
     }
 }
 
@@ -379,8 +431,9 @@ template <int MODE>
 int launch_scan(const PyramidView& pyr, const Consts& k, InitialExtremum* iext, Counters* ct, cudaStream_t st)
 {
     if (pyr.cands_filled && !dense_choice()) {
+        cand_prefix_kernel<<<1, 1024, 0, st>>>(pyr.cand_cnt_all, pyr.cand_regions, pyr.cand_prefix);
         cand_extrema_kernel<MODE><<<148 * 4, kScanThreads, 0, st>>>(pyr, k, iext, ct);
-        return 1;
+        return 2;
     }
     int launches = 0;
     // levels are evaluated in groups of up to 3 (all of them at once for the default levels = 3)

@@ -19,6 +19,7 @@ namespace psb {
 namespace {
 
 constexpr int WARPS = 4;
+constexpr int kSlice = PS_ORI_SLICE;   // extrema per slice of the descriptor-index scan (ori_scatter_kernel)
 constexpr int HSTRIDE = 33;     // skewed so that the lane-order reduction is conflict-free
 __device__ const float kPi  = 3.14159265358979323846f;
 __device__ const float kPi2 = 2.0f * 3.14159265358979323846f;
@@ -46,7 +47,7 @@ __device__ __forceinline__ int octave_prefix(const Counters* ct, const Consts& k
 
 __global__ void __launch_bounds__(WARPS * 32)
 orientation_kernel(PyramidView pyr, Consts k, const InitialExtremum* __restrict__ iext,
-                   ps_extremum* __restrict__ ext, Counters* ct)
+                   ps_extremum* __restrict__ ext, int* __restrict__ slice_sum, Counters* ct)
 {
     __shared__ float hist[WARPS][kOriBins * HSTRIDE];
     __shared__ float sm_a[WARPS][kOriBins];
@@ -180,73 +181,93 @@ orientation_kernel(PyramidView pyr, Consts k, const InitialExtremum* __restrict_
             }
             e.num_ori = n;
             ext[item] = e;
+            if (n > 0) atomicAdd(&slice_sum[item / kSlice], n);
         }
         __syncwarp();
     }
 }
 
-// Exclusive prefix sum of num_ori over all extrema (single CTA), reverse map, totals.
-__global__ void __launch_bounds__(1024)
-ori_prefix_kernel(int num_octaves, Consts k, ps_extremum* __restrict__ ext, int* __restrict__ feat_to_ext, Counters* ct)
+// Exclusive prefix sum of num_ori over all extrema, reverse map, totals.  The orientation kernel has
+// already added every extremum's num_ori to the sum of its slice of kSlice extrema, so one block per slice
+// only needs the sums of the slices before it: the scan runs on as many SMs as there are slices instead
+// of on one (a single block spent 30 us at 4K on its one SM's memory bandwidth).
+__global__ void __launch_bounds__(kSlice)
+ori_scatter_kernel(int num_octaves, Consts k, ps_extremum* __restrict__ ext, int* __restrict__ feat_to_ext,
+                   const int* __restrict__ slice_sum, Counters* ct)
 {
-    __shared__ int warp_sums[32];
-    __shared__ int carry;
+    __shared__ int warp_sums[kSlice / 32];
+    __shared__ int base_s;
     __shared__ int ps[kMaxOctaves + 1];
-    if (threadIdx.x == 0) { octave_prefix(ct, k, num_octaves, ps); carry = 0; }
+    if (threadIdx.x == 0) octave_prefix(ct, k, num_octaves, ps);
     __syncthreads();
     const int total = ps[num_octaves];
+    const int b = blockIdx.x;
+    const int first = b * kSlice;
+    if (first >= total && b != 0) return;                       // block-uniform
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    bool overflow = false;
-    for (int base = 0; base < total; base += 1024) {
-        const int i = base + threadIdx.x;
-        const int n = i < total ? ext[i].num_ori : 0;
-        int v = n;
+
+    // descriptors before this slice
+    int part = 0;
+    for (int j = threadIdx.x; j < b; j += kSlice) part += slice_sum[j];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, v, d);
-            if (lane >= d) v += t;
-        }
-        if (lane == 31) warp_sums[warp] = v;
-        __syncthreads();
-        if (warp == 0) {
-            int s = warp_sums[lane];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, s, d);
-                if (lane >= d) s += t;
-            }
-            warp_sums[lane] = s;
-        }
-        __syncthreads();
-        const int excl = carry + (warp ? warp_sums[warp - 1] : 0) + v - n;
-        if (i < total) {
-            int nn = n;
-            if (excl + nn > k.desc_capacity) { nn = max(0, k.desc_capacity - excl); overflow = true; ext[i].num_ori = nn; }
-            ext[i].idx_ori = min(excl, k.desc_capacity);
-            for (int r = 0; r < nn; ++r) feat_to_ext[excl + r] = i;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) carry += warp_sums[31];
-        __syncthreads();
-    }
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_down_sync(0xffffffffu, part, d);
+    if (lane == 0) warp_sums[warp] = part;
+    __syncthreads();
     if (threadIdx.x == 0) {
+        int s = 0;
+        for (int w = 0; w < kSlice / 32; ++w) s += warp_sums[w];
+        base_s = s;
+    }
+    __syncthreads();
+    const int base = base_s;
+    __syncthreads();                                            // warp_sums is reused below
+
+    const int i = first + threadIdx.x;
+    const int n = i < total ? ext[i].num_ori : 0;
+    int v = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += t;
+    }
+    if (lane == 31) warp_sums[warp] = v;
+    __syncthreads();
+    int before = 0, block_total = 0;
+#pragma unroll
+    for (int w = 0; w < kSlice / 32; ++w) {
+        const int ws = warp_sums[w];
+        if (w < warp) before += ws;
+        block_total += ws;
+    }
+    const int excl = base + before + v - n;
+    if (i < total) {
+        int nn = n;
+        if (excl + nn > k.desc_capacity) {
+            nn = max(0, k.desc_capacity - excl);
+            ext[i].num_ori = nn;
+            atomicOr(&ct->overflow, 2);
+        }
+        ext[i].idx_ori = min(excl, k.desc_capacity);
+        for (int r = 0; r < nn; ++r) feat_to_ext[excl + r] = i;
+    }
+    const int last = total > 0 ? (total - 1) / kSlice : 0;
+    if (b == last && threadIdx.x == 0) {
         ct->ext_total = total;
-        ct->ori_total = min(carry, k.desc_capacity);
+        ct->ori_total = min(base + block_total, k.desc_capacity);
         int raw = 0;
         for (int o = 0; o < num_octaves; ++o) raw += min(ct->ext_ct[o], k.max_extrema);
         if (raw > total) atomicOr(&ct->overflow, 1);
     }
-    if (overflow) atomicOr(&ct->overflow, 2);
 }
 
 } // namespace
 
 int launch_orientation(const PyramidView& pyr, const Consts& k, const InitialExtremum* iext, ps_extremum* ext,
-                       int* feat_to_ext, Counters* ct, cudaStream_t st)
+                       int* feat_to_ext, int* slice_sum, Counters* ct, cudaStream_t st)
 {
     // fixed grid: 148 SMs x 8 resident CTAs of 4 warps; warps stride over the device-side count
-    orientation_kernel<<<148 * 8, WARPS * 32, 0, st>>>(pyr, k, iext, ext, ct);
-    ori_prefix_kernel<<<1, 1024, 0, st>>>(pyr.num_octaves, k, ext, feat_to_ext, ct);
+    orientation_kernel<<<148 * 8, WARPS * 32, 0, st>>>(pyr, k, iext, ext, slice_sum, ct);
+    ori_scatter_kernel<<<k.ext_capacity / kSlice + 1, kSlice, 0, st>>>(pyr.num_octaves, k, ext, feat_to_ext, slice_sum, ct);
     return 2;
 }
 

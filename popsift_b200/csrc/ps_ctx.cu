@@ -46,6 +46,7 @@ struct Slot {
     ps_descriptor*   d_desc = nullptr;
     int*             d_f2e = nullptr;
     Counters*        d_ct = nullptr;
+    int*             d_ori_slice = nullptr;   // num_ori sums per PS_ORI_SLICE extrema (k_orient.cu)
     Counters*        h_ct = nullptr;   // pinned
     // pinned result staging (grown on demand)
     ps_feature*    h_feat = nullptr;  size_t h_feat_cap = 0;
@@ -107,7 +108,7 @@ size_t plane_budget(const ps_config& cfg, int w, int h, int levels)
     for (int o = 0; o < n; ++o) {
         total += round_up(W[o], 32) * (size_t)H[o] * (size_t)(2 * levels + 5);
         // candidate lists of the `levels` scanned DoG planes + one count per block (<= 4096 blocks... generous)
-        total += ((size_t)cand_entry_bound_for(W[o], H[o]) + 8192) * (size_t)levels;
+        total += ((size_t)cand_entry_bound_for(W[o], H[o]) + 16384) * (size_t)levels + 16;
     }
     return total;
 }
@@ -139,6 +140,9 @@ int build_view(ps_ctx* ctx, Slot& s, int w, int h)
         v.cand_cnt = reinterpret_cast<int*>(s.d_planes + off);  off += (size_t)v.cand_blocks * L;
     }
     s.cand_cnt_bytes = (size_t)(reinterpret_cast<int*>(s.d_planes + off) - s.cand_cnt) * sizeof(int);
+    s.view.cand_cnt_all = s.cand_cnt;
+    s.view.cand_regions = (int)(s.cand_cnt_bytes / sizeof(int));
+    s.view.cand_prefix = reinterpret_cast<int*>(s.d_planes + off);  off += (size_t)s.view.cand_regions + 1;
     if (off > s.planes_floats) return ctx->fail(PS_ERR_TOO_LARGE, "%dx%d exceeds the slot's plane memory", w, h);
     s.view.num_octaves = s.num_octaves;
     s.view.levels = L;
@@ -230,12 +234,13 @@ static int submit_common(ps_ctx* ctx, Slot& s)
     int rc;
     PS_CUDA(ctx, cudaMemsetAsync(s.d_ct, 0, sizeof(Counters), s.stream));
     PS_CUDA(ctx, cudaMemsetAsync(s.cand_cnt, 0, s.cand_cnt_bytes, s.stream));
+    PS_CUDA(ctx, cudaMemsetAsync(s.d_ori_slice, 0, sizeof(int) * ((size_t)ctx->k.ext_capacity / PS_ORI_SLICE + 1), s.stream));
     if (tm) PS_CUDA(ctx, cudaEventRecord(s.ev[1], s.stream));
     if ((rc = run_pyramid(ctx, s)) != PS_OK) return rc;
     if (tm) PS_CUDA(ctx, cudaEventRecord(s.ev[2], s.stream));
     int n = launch_find_extrema(s.view, ctx->k, s.d_iext, s.d_ct, s.stream);
     if (tm) PS_CUDA(ctx, cudaEventRecord(s.ev[3], s.stream));
-    n += launch_orientation(s.view, ctx->k, s.d_iext, s.d_ext, s.d_f2e, s.d_ct, s.stream);
+    n += launch_orientation(s.view, ctx->k, s.d_iext, s.d_ext, s.d_f2e, s.d_ori_slice, s.d_ct, s.stream);
     if (tm) PS_CUDA(ctx, cudaEventRecord(s.ev[4], s.stream));
     n += launch_descriptors(s.view, ctx->k, s.d_ext, s.d_f2e, s.d_desc, s.d_ct, s.stream);
     n += launch_prep_features(ctx->k, s.d_ext, s.d_feat, s.d_ct, s.stream);
@@ -267,7 +272,7 @@ extern "C" void ps_destroy(ps_ctx* ctx)
     cudaSetDevice(ctx->device);
     for (Slot& s : ctx->slots) {
         if (s.stream) cudaStreamSynchronize(s.stream);
-        cudaFree(s.d_img); cudaFreeHost(s.h_img); cudaFree(s.d_planes); cudaFree(s.d_iext); cudaFree(s.d_ext);
+        cudaFree(s.d_img); cudaFreeHost(s.h_img); cudaFree(s.d_planes); cudaFree(s.d_iext); cudaFree(s.d_ext); cudaFree(s.d_ori_slice);
         cudaFree(s.d_feat); cudaFree(s.d_desc); cudaFree(s.d_f2e); cudaFree(s.d_ct); cudaFreeHost(s.h_ct);
         cudaFreeHost(s.h_feat); cudaFreeHost(s.h_desc);
         for (auto& e : s.ev) if (e) cudaEventDestroy(e);
@@ -348,6 +353,7 @@ extern "C" ps_ctx* ps_create(int device, const ps_config* cfg, int max_w, int ma
         PS_TRY(cudaMalloc(&s.d_desc, sizeof(ps_descriptor) * (size_t)k.desc_capacity));
         PS_TRY(cudaMalloc(&s.d_f2e, sizeof(int) * (size_t)k.desc_capacity));
         PS_TRY(cudaMalloc(&s.d_ct, sizeof(Counters)));
+        PS_TRY(cudaMalloc(&s.d_ori_slice, sizeof(int) * ((size_t)k.ext_capacity / PS_ORI_SLICE + 1)));
         PS_TRY(cudaHostAlloc(&s.h_ct, sizeof(Counters), cudaHostAllocDefault));
         for (auto& ev : s.ev) PS_TRY(cudaEventCreate(&ev));
         PS_TRY(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));

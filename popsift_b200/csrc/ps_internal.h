@@ -52,6 +52,11 @@ struct PyramidView {
     int        num_octaves;
     int        levels;      // L
     int        cands_filled;   // the pyramid kernels appended the candidate lists of this image
+    // the block counts of all octaves (oct[o].cand_cnt, contiguous in octave order), their number and the
+    // array their exclusive prefix sum is written to (cand_regions + 1 entries)
+    int*       cand_cnt_all;
+    int*       cand_prefix;
+    int        cand_regions;
 };
 
 // Where a pyramid kernel reports the DoG pixel pairs (x even) in which a sample passes the peak
@@ -114,8 +119,10 @@ int cand_region_for(int w, int h);
 long long cand_entry_bound_for(int w, int h);
 
 int launch_find_extrema(const PyramidView& pyr, const Consts& k, InitialExtremum* iext, Counters* ct, cudaStream_t st);
+// slice_sum: ext_capacity / PS_ORI_SLICE + 1 ints, zeroed per image
+#define PS_ORI_SLICE 256
 int launch_orientation(const PyramidView& pyr, const Consts& k, const InitialExtremum* iext, ps_extremum* ext,
-                       int* feat_to_ext, Counters* ct, cudaStream_t st);
+                       int* feat_to_ext, int* slice_sum, Counters* ct, cudaStream_t st);
 int launch_descriptors(const PyramidView& pyr, const Consts& k, const ps_extremum* ext, const int* feat_to_ext,
                        ps_descriptor* desc, Counters* ct, cudaStream_t st);
 int launch_prep_features(const Consts& k, const ps_extremum* ext, ps_feature* feat, const Counters* ct, cudaStream_t st);
