@@ -24,13 +24,6 @@ constexpr int HSTRIDE = 33;     // skewed so that the lane-order reduction is co
 __device__ const float kPi  = 3.14159265358979323846f;
 __device__ const float kPi2 = 2.0f * 3.14159265358979323846f;
 
-__device__ __forceinline__ float plane_at(const float* pl, int w, int h, int pitch, int x, int y)
-{
-    x = min(max(x, 0), w - 1);
-    y = min(max(y, 0), h - 1);
-    return __ldg(pl + (size_t)y * pitch + x);
-}
-
 // total number of extrema and the octave prefix, from the raw per-octave counters
 __device__ __forceinline__ int octave_prefix(const Counters* ct, const Consts& k, int num_octaves, int* ps /*[kMaxOctaves+1]*/)
 {
@@ -87,21 +80,29 @@ orientation_kernel(PyramidView pyr, Consts k, const InitialExtremum* __restrict_
         const int hy = ymax - ymin + 1;
         const int loops = (wx > 0 && hy > 0) ? wx * hy : 0;
 
+        // Sample i of the window is row i / wx, column i % wx, and belongs to lane i % 32 (that assignment
+        // and the order within a lane fix the summation order of the histogram).  The lane walks its
+        // samples with a running (row, column) instead of a division per sample; the window lies inside
+        // [1, w-2] x [1, h-2], so the four neighbours need no clamping; hypotf / atan2f / expf only run
+        // for samples inside the circle.
+        int xx = xmin + lane, yy = ymin;
+        while (xx > xmax && wx > 0) { xx -= wx; ++yy; }
         for (int i = lane; i < loops; i += 32) {
-            const int yy = i / wx + ymin;
-            const int xx = i - (i / wx) * wx + xmin;
-            const float gdx = __fsub_rn(plane_at(pl, w, h, ov.pitch, xx + 1, yy), plane_at(pl, w, h, ov.pitch, xx - 1, yy));
-            const float gdy = __fsub_rn(plane_at(pl, w, h, ov.pitch, xx, yy + 1), plane_at(pl, w, h, ov.pitch, xx, yy - 1));
-            const float grad = hypotf(gdx, gdy);
-            const float theta = atan2f(gdy, gdx);
             const float ddx = __fsub_rn((float)xx, x), ddy = __fsub_rn((float)yy, y);
             const int sq_dist = (int)__fmaf_rn(ddx, ddx, __fmul_rn(ddy, ddy));
             if (sq_dist <= sq_thres) {
+                const float* p = pl + (yy * ov.pitch + xx);         // a plane holds < 2^31 floats
+                const float gdx = __fsub_rn(__ldg(p + 1), __ldg(p - 1));
+                const float gdy = __fsub_rn(__ldg(p + ov.pitch), __ldg(p - ov.pitch));
+                const float grad = hypotf(gdx, gdy);
+                const float theta = atan2f(gdy, gdx);
                 const float weight = __fmul_rn(grad, expf(__fmul_rn((float)sq_dist, factor)));
                 int bidx = (int)roundf(__fdividef(__fmul_rn((float)kOriBins, __fadd_rn(theta, kPi)), kPi2));
                 if (bidx == kOriBins) bidx = 0;
                 if (bidx >= 0 && bidx < kOriBins) H[bidx * HSTRIDE + lane] += weight;
             }
+            xx += 32;
+            while (xx > xmax) { xx -= wx; ++yy; }
         }
         __syncwarp();
         // reduce the 32 lane-private copies of each bin, lanes in order
