@@ -43,7 +43,7 @@ sys.path.insert(0, ROOT)
 
 W, H = 3840, 2160
 OCTAVES, LEVELS = 5, 3
-FRAMES_PER_STEP = 8
+FRAMES_PER_STEP = 32     # long enough that the 4-slot pipeline spends most of a step in steady state
 SLOTS = 4
 BYTES_PER_OCTAVE_PIXEL = 4 * (3 * LEVELS + 8)     # 68 B
 METRIC = "Mpixels/s SIFT extract @ 3840x2160 gray"
@@ -127,6 +127,13 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm), "samples_total": n_all}
+
+
+# one `ncu --set full --clock-control none` capture of tools/one_frame.py 3840 2160 5 1 (round 1, after the
+# last kernel change); per frame / per octave-0 level launch
+NCU_SOURCE = "profiles/r01_ncu_full_frame_4k.csv"
+NCU_PYRAMID_DRAM_BYTES = 2215795712
+NCU_LEVEL_DRAM_BYTES = 367469568
 
 
 def measured_peak():
@@ -310,13 +317,19 @@ def run_ours(args, rank, world, local_rank):
                 "api": "popsift_b200.api.PopSift.enqueue -> SiftJob.get (C ABI ps_submit_u8/ps_counts/ps_download), pinned host frames"},
         "roofline": {"bound": "hbm", "stage": "pyramid (all launches of one frame)", "achieved": alg_bytes_frame / (pyr * 1e-3) / 1e9,
                      "peak": peak, "unit": "GB/s", "frac": alg_bytes_frame / (pyr * 1e-3) / 1e9 / peak, "peak_source": peak_src,
-                     "algorithmic_bytes": alg_bytes_frame, "ms": pyr, "traffic": None,
-                     "dominant_kernel": {"name": "blur_level_kernel (octave 0, levels 1..5, avg per launch)",
+                     "algorithmic_bytes": alg_bytes_frame, "ms": pyr,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of the 26 pyramid launches of one frame, one
+                     # `ncu --set full` capture (profiles/r01_ncu_full_frame_4k.csv); below the algorithmic bytes
+                     # because part of every plane is still dirty in the 126 MB L2 when its consumer starts
+                     "traffic": NCU_PYRAMID_DRAM_BYTES, "traffic_source": NCU_SOURCE,
+                     "dominant_kernel": {"name": "march_level_kernel (octave 0, levels 1..5: blur + DoG, avg per launch)",
                                          "algorithmic_bytes": dom_bytes, "ms": dom,
-                                         "achieved": dom_bytes / (dom * 1e-3) / 1e9, "frac": dom_bytes / (dom * 1e-3) / 1e9 / peak}},
+                                         "achieved": dom_bytes / (dom * 1e-3) / 1e9, "frac": dom_bytes / (dom * 1e-3) / 1e9 / peak,
+                                         "traffic": NCU_LEVEL_DRAM_BYTES}},
         "clocks": clocks,
     }
-    out.update(cpu_baselines(frames[0]))
+    if world == 1:      # reported baselines: rank 0 at N=1 only (torchrun pins OMP_NUM_THREADS=1)
+        out.update(cpu_baselines(frames[0]))
     return out
 
 
@@ -411,7 +424,7 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
-        torch.distributed.init_process_group("nccl")
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     out = run_ours(args, rank, world, local_rank)
     if out is not None:
         print(json.dumps(out), flush=True)

@@ -27,9 +27,11 @@ thread_local std::string g_create_error;
 
 struct Slot {
     cudaStream_t stream = nullptr;
-    cudaStream_t side = nullptr;      // levels L+1, L+2 of an octave run here, beside the next octave
+    // levels L+1, L+2 of octave o run on side[o % kSides], beside the next octaves
+    static constexpr int kSides = 1;     // (two side streams measured 3 % slower at 4K: the big launches fight for the SMs)
+    cudaStream_t side[kSides] = {};
     cudaEvent_t  ev_fork[kMaxOctaves] = {};
-    cudaEvent_t  ev_join = nullptr;
+    cudaEvent_t  ev_join[kSides] = {};
     // input
     uint8_t* d_img = nullptr;      // max_w*max_h*4 bytes (u8 or f32 images)
     uint8_t* h_img = nullptr;      // pinned staging, same size
@@ -196,19 +198,20 @@ int run_pyramid(ps_ctx* ctx, Slot& s)
                              ctx->dd0, ctx->rows[0], s.stream);
     if (r < 0) return ctx->fail(PS_ERR_ARG, "unsupported level-0 filter span %d", ctx->dd0.span);
     n += r;
-    bool forked = false;
+    bool forked[Slot::kSides] = {};
     for (int o = 0; o < s.num_octaves; ++o) {
         const bool last = (o + 1 == s.num_octaves);
         for (int l = 1; l < L + 3; ++l) {
             const OctaveView* next = (l == L && !last) ? &s.view.oct[o + 1] : nullptr;
             cudaStream_t st = s.stream;
             if (fork && !last && l > L) {
+                const int sd = o % Slot::kSides;
                 if (l == L + 1) {
                     PS_CUDA(ctx, cudaEventRecord(s.ev_fork[o], s.stream));
-                    PS_CUDA(ctx, cudaStreamWaitEvent(s.side, s.ev_fork[o], 0));
-                    forked = true;
+                    PS_CUDA(ctx, cudaStreamWaitEvent(s.side[sd], s.ev_fork[o], 0));
+                    forked[sd] = true;
                 }
-                st = s.side;
+                st = s.side[sd];
             }
             CandSink cs;
             const bool has_sink = level_sink(ctx, s, o, l, cs);
@@ -217,10 +220,11 @@ int run_pyramid(ps_ctx* ctx, Slot& s)
             n += r;
         }
     }
-    if (forked) {
-        PS_CUDA(ctx, cudaEventRecord(s.ev_join, s.side));
-        PS_CUDA(ctx, cudaStreamWaitEvent(s.stream, s.ev_join, 0));
-    }
+    for (int sd = 0; sd < Slot::kSides; ++sd)
+        if (forked[sd]) {
+            PS_CUDA(ctx, cudaEventRecord(s.ev_join[sd], s.side[sd]));
+            PS_CUDA(ctx, cudaStreamWaitEvent(s.stream, s.ev_join[sd], 0));
+        }
     ctx->launches += n;
     PS_CUDA(ctx, cudaGetLastError());
     return PS_OK;
@@ -278,8 +282,8 @@ extern "C" void ps_destroy(ps_ctx* ctx)
         for (auto& e : s.ev) if (e) cudaEventDestroy(e);
         if (s.done) cudaEventDestroy(s.done);
         for (auto& e : s.ev_fork) if (e) cudaEventDestroy(e);
-        if (s.ev_join) cudaEventDestroy(s.ev_join);
-        if (s.side) cudaStreamDestroy(s.side);
+        for (auto& e : s.ev_join) if (e) cudaEventDestroy(e);
+        for (auto& st : s.side) if (st) cudaStreamDestroy(st);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     delete ctx;
@@ -340,9 +344,9 @@ extern "C" ps_ctx* ps_create(int device, const ps_config* cfg, int max_w, int ma
     for (Slot& s : ctx->slots) {
 #define PS_TRY(call) if ((e = (call)) != cudaSuccess) { std::string m = #call; ps_destroy(ctx); return bail(m.c_str(), e); }
         PS_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-        PS_TRY(cudaStreamCreateWithFlags(&s.side, cudaStreamNonBlocking));
+        for (auto& st : s.side) PS_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         for (auto& ev : s.ev_fork) PS_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        PS_TRY(cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming));
+        for (auto& ev : s.ev_join) PS_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         PS_TRY(cudaMalloc(&s.d_img, (size_t)max_w * max_h * 4));
         PS_TRY(cudaHostAlloc(&s.h_img, (size_t)max_w * max_h * 4, cudaHostAllocDefault));
         PS_TRY(cudaMalloc(&s.d_planes, planes * sizeof(float)));

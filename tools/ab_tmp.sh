@@ -1,6 +1,5 @@
 set -u
-O=gpurun_out/ab17; mkdir -p $O
-python -m pytest tests/test_gpu_parity.py -m gpu -q --tb=short 2>&1 | grep -E "AssertionError|passed|failed|assert|Error" | cut -c1-600
-python tools/pyr_time.py 2>&1 | sed -n 2,3p
-ncu --metrics gpu__time_duration.sum,sm__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__cycles_active.avg,sm__cycles_active.max,sm__cycles_elapsed.avg --clock-control none -c 60 --csv --log-file $O/launches.csv python tools/one_frame.py 3840 2160 5 1 > $O/ncu.log 2>&1; tail -1 $O/ncu.log
-python bench.py --steps 5 --warmup 3 > $O/bench.json 2> $O/bench.err; cat $O/bench.json | head -c 300
+O=gpurun_out/mg2; mkdir -p $O
+nvidia-smi -L
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > $O/bench_n2.json 2> $O/bench_n2.err; echo rc=$?; tail -c 1500 $O/bench_n2.json; tail -3 $O/bench_n2.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > $O/bench_ref_n2.json 2> $O/bench_ref_n2.err; echo rc=$?; tail -c 300 $O/bench_ref_n2.json
