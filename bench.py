@@ -44,7 +44,7 @@ sys.path.insert(0, ROOT)
 W, H = 3840, 2160
 OCTAVES, LEVELS = 5, 3
 FRAMES_PER_STEP = 32     # long enough that the 4-slot pipeline spends most of a step in steady state
-SLOTS = 4
+SLOTS = int(os.environ.get("POPSIFT_BENCH_SLOTS", "4"))     # images in flight per GPU
 BYTES_PER_OCTAVE_PIXEL = 4 * (3 * LEVELS + 8)     # 68 B
 METRIC = "Mpixels/s SIFT extract @ 3840x2160 gray"
 

@@ -116,6 +116,7 @@ descriptor_kernel(PyramidView pyr, Consts k, const ps_extremum* __restrict__ ext
         const float ang = e.orientation[min(max(d - e.idx_ori, 0), PS_MAX_ORI - 1)];
         const OctaveView& ov = pyr.oct[e.octave];
         const int width = ov.w, height = ov.h, pitch = ov.pitch;
+        const long long pitch_l = pitch;
         const int lvl = min(max(e.lpos, 0), pyr.levels + 2);
         const float* pl = ov.gauss + (size_t)lvl * ov.plane;
 
@@ -191,18 +192,16 @@ descriptor_kernel(PyramidView pyr, Consts k, const ps_extremum* __restrict__ ext
                     if (!(fabsf(rx) < 2.5f && fabsf(ry) < 2.5f)) continue;
                     const float* p = pl + (ii * pitch + jj);             // interior pixel: neighbours exist; a plane is < 2^31 floats
                     const float gdx = __fsub_rn(__ldg(p + 1), __ldg(p - 1));
-                    const float gdy = __fsub_rn(__ldg(p + pitch), __ldg(p - pitch));
+                    const float gdy = __fsub_rn(__ldg(p + pitch_l), __ldg(p - pitch_l));
                     const float mod = fast_sqrt(__fmaf_rn(gdx, gdx, __fmul_rn(gdy, gdy)));
-                    float th = fast_atan2(gdy, gdx);
                     // exp(-(rx^2 + ry^2) / 8); the exponent stays above -2.3, no range handling needed
                     const float ww = fast_ex2(__fmul_rn(__fmaf_rn(ry, ry, __fmul_rn(rx, rx)), -0.125f * 1.4426950408889634f));
-                    th = __fsub_rn(th, ang);
-                    th = __fadd_rn(th, th < 0.0f ? dPi2 : 0.0f);
-                    th = __fsub_rn(th, th >= dPi2 ? dPi2 : 0.0f);
-                    const float tth = __fmul_ru(th, d4RPi);
+                    // orientation relative to the keypoint in bin units; any multiple of 8 bins is the same
+                    // orientation, so the value is not wrapped: floor_bits keeps floor(tth) mod 8 in its low bits
+                    const float tth = __fmul_rn(__fsub_rn(fast_atan2(gdy, gdx), ang), d4RPi);
                     const unsigned fb = floor_bits(tth);
-                    const float do0 = __fsub_rn(tth, floor_val(fb));           // tth may be negative: the bins wrap mod 8
-                    const int b0 = fb & 7, b1 = (fb + 1) & 7;
+                    const float do0 = __fsub_rn(tth, floor_val(fb));
+                    const unsigned b0 = fb & 7u, b1 = (fb + 1u) & 7u;
                     const float wm = __fmul_rn(__fmul_rn(ww, mod), kFix);
                     const float w1 = __fmul_rn(do0, wm), w0 = __fsub_rn(wm, w1);
                     // the (at most) 2x2 cells whose bilinear window covers this pixel
@@ -213,10 +212,10 @@ descriptor_kernel(PyramidView pyr, Consts k, const ps_extremum* __restrict__ ext
                     const float ax1 = __fsub_rn(fx, floor_val(bx));                     // in [0,1)
                     const float ay1 = __fsub_rn(fy, floor_val(by));
                     const float ax0 = __fsub_rn(1.0f, ax1), ay0 = __fsub_rn(1.0f, ay1);
-                    unsigned* hb = H + ((cy0 << 2) + cx0) * 8;            // cell (cx0, cy0); may be out of range
                     // rx + 2.5 can round up to exactly 5.0 (cell 4): every cell index is range-checked on both sides
                     const bool x0ok = (unsigned)cx0 < 4u, x1ok = (unsigned)(cx0 + 1) < 4u;
                     const bool y0ok = (unsigned)cy0 < 4u, y1ok = (unsigned)(cy0 + 1) < 4u;
+                    unsigned* hb = H + ((cy0 << 2) + cx0) * 8;            // cell (cx0, cy0); may be out of range
                     if (x0ok && y0ok) {
                         const float wc = __fmul_rn(ax0, ay0);
                         atomicAdd(hb + b0, fix_bits(w0, wc));

@@ -1,5 +1,10 @@
 set -u
-O=gpurun_out/mg2; mkdir -p $O
-nvidia-smi -L
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > $O/bench_n2.json 2> $O/bench_n2.err; echo rc=$?; tail -c 1500 $O/bench_n2.json; tail -3 $O/bench_n2.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > $O/bench_ref_n2.json 2> $O/bench_ref_n2.err; echo rc=$?; tail -c 300 $O/bench_ref_n2.json
+O=gpurun_out/ab19; mkdir -p $O
+python -m pytest tests/test_gpu_parity.py -m gpu -q --tb=short 2>&1 | grep -E "AssertionError|passed|failed|assert|Error" | cut -c1-600
+for S in 4 6 8; do
+POPSIFT_BENCH_SLOTS=$S python bench.py --steps 5 --warmup 3 > $O/bench_s$S.json 2> $O/bench.err; python - <<PY
+import json
+j=json.load(open("$O/bench_s$S.json")); print("slots $S value", round(j["value"]), "e2e", round(j["e2e"]["value"]), "frac", round(j["roofline"]["frac"],3))
+PY
+done
+ncu --metrics gpu__time_duration.sum,sm__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active -k regex:descriptor --clock-control none -c 1 --csv --log-file $O/desc.csv python tools/one_frame.py 3840 2160 5 1 > $O/ncu.log 2>&1; grep -E "duration|inst_executed" $O/desc.csv | cut -d, -f13-
