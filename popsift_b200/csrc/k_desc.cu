@@ -43,7 +43,7 @@ __device__ __forceinline__ float tree_down(float v)
     return v;
 }
 
-constexpr int DWARPS = 4;     // warps that share one descriptor (one CTA per descriptor in flight)
+constexpr int DWARPS = 4;     // warps that share one descriptor (one CTA per descriptor in flight); == histogram copies
 constexpr int DTHREADS = DWARPS * 32;
 // a bin can reach ~8e4 (232 fully weighted pixels of gradient magnitude 360): 17 integer bits; one
 // contribution stays below 360 * 2^14 < 2^23, so float -> fixed point is a single FFMA onto 2^23
@@ -95,7 +95,11 @@ descriptor_kernel(PyramidView pyr, Consts k, const ps_extremum* __restrict__ ext
     // 128 bins in 32-bit fixed point (15 fractional bits): integer shared-memory atomics are
     // native (ATOMS.ADD) whereas float ones are compare-and-swap loops, and integer sums do not depend
     // on the order of the adds -> run-to-run deterministic descriptors
-    __shared__ __align__(16) unsigned H[128];
+    // kCopies copies of the histogram, selected by lane % kCopies and skewed by 8 banks each: neighbouring
+    // lanes that add to the same (cell, bin) -- the common case along a row of samples -- hit different
+    // banks instead of serialising on one word; the copies are summed before normalisation
+    constexpr int kCopies = 4, kHStride = 128 + 8;
+    __shared__ __align__(16) unsigned H[kCopies * kHStride];
     __shared__ int next_d;
     // per row of the support: x = candidates before the row (exclusive prefix), y = first column - x
     __shared__ int2 row_tab[DTHREADS + 1];
@@ -120,7 +124,7 @@ descriptor_kernel(PyramidView pyr, Consts k, const ps_extremum* __restrict__ ext
         const int lvl = min(max(e.lpos, 0), pyr.levels + 2);
         const float* pl = ov.gauss + (size_t)lvl * ov.plane;
 
-        if (warp == 0) *reinterpret_cast<uint4*>(H + 4 * lane) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(H + warp * kHStride + 4 * lane) = make_uint4(0u, 0u, 0u, 0u);       // DWARPS == kCopies
 
         const float x = e.xpos, y = e.ypos;
         const float SBP = fabsf(__fmul_rn(3.0f, e.sigma));
@@ -177,8 +181,27 @@ descriptor_kernel(PyramidView pyr, Consts k, const ps_extremum* __restrict__ ext
                 __syncthreads();
                 const int n = row_tab[DTHREADS].x;
 
-                int row = 0, cur_off = row_tab[0].y, next_pre = row_tab[1].x;
-                for (int i = threadIdx.x; i < n; i += DTHREADS) {
+                // Hand-out of the n candidates.  32 consecutive candidates are neighbours in a row: they fall
+                // into the same cell and, where the image is smooth, the same orientation bin, so a warp that
+                // took 32 consecutive ones serialised ~8 lanes per shared-memory atomic (ncu: 7.7 wavefronts
+                // per ATOMS, LSU data pipe 81 % busy).  Instead the candidate list is cut into kBands bands
+                // (distant rows -> different cells) and every group of 32/kBands lanes of a warp works in its own
+                // band: still whole 32-byte sectors per group for the gradient loads.
+                constexpr int kBands = 4, kTeam = DTHREADS / kBands;          // threads per band
+                const int nq = (n + kBands - 1) / kBands;
+                const int band = lane / (32 / kBands);
+                const int band_end = min(n, (band + 1) * nq);
+                int i = band * nq + warp * (32 / kBands) + (lane & (32 / kBands - 1));
+                int row = 0, cur_off = 0, next_pre = 0;
+                if (i < band_end) {
+                    int lo = 0, hi = DTHREADS;                          // last row with row_tab[row].x <= i
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (row_tab[mid].x <= i) lo = mid; else hi = mid;
+                    }
+                    row = lo; cur_off = row_tab[lo].y; next_pre = row_tab[lo + 1].x;
+                }
+                for (; i < band_end; i += kTeam) {
                     while (i >= next_pre) {
                         ++row;
                         cur_off = row_tab[row].y;
@@ -215,7 +238,7 @@ descriptor_kernel(PyramidView pyr, Consts k, const ps_extremum* __restrict__ ext
                     // rx + 2.5 can round up to exactly 5.0 (cell 4): every cell index is range-checked on both sides
                     const bool x0ok = (unsigned)cx0 < 4u, x1ok = (unsigned)(cx0 + 1) < 4u;
                     const bool y0ok = (unsigned)cy0 < 4u, y1ok = (unsigned)(cy0 + 1) < 4u;
-                    unsigned* hb = H + ((cy0 << 2) + cx0) * 8;            // cell (cx0, cy0); may be out of range
+                    unsigned* hb = H + (lane & (kCopies - 1)) * kHStride + ((cy0 << 2) + cx0) * 8;   // cell (cx0, cy0); may be out of range
                     if (x0ok && y0ok) {
                         const float wc = __fmul_rn(ax0, ay0);
                         atomicAdd(hb + b0, fix_bits(w0, wc));
@@ -242,7 +265,12 @@ descriptor_kernel(PyramidView pyr, Consts k, const ps_extremum* __restrict__ ext
         }
         __syncthreads();
         if (warp == 0) {
-            const uint4 hv = *reinterpret_cast<const uint4*>(H + 4 * lane);
+            uint4 hv = *reinterpret_cast<const uint4*>(H + 4 * lane);
+#pragma unroll
+            for (int c = 1; c < kCopies; ++c) {
+                const uint4 t = *reinterpret_cast<const uint4*>(H + c * kHStride + 4 * lane);
+                hv.x += t.x; hv.y += t.y; hv.z += t.z; hv.w += t.w;
+            }
             float4 v = make_float4((float)hv.x * kUnfix, (float)hv.y * kUnfix, (float)hv.z * kUnfix, (float)hv.w * kUnfix);
             if (k.norm_mode == PS_NORM_ROOTSIFT) {
                 float sum = __fadd_rn(__fadd_rn(__fadd_rn(v.x, v.y), v.z), v.w);
