@@ -51,7 +51,7 @@ __device__ const float kFix = 16384.0f;
 __device__ const float kUnfix = 1.0f / 16384.0f;
 __device__ const float kMagic = 8388608.0f;      // 2^23
 
-// atan2 to 3.5e-7 rad: one reciprocal, a degree-6 minimax polynomial in a^2 on [0,1] and three
+// atan2 to < 1e-6 rad (tests/test_host_cpu.py): one reciprocal, a degree-6 minimax polynomial in a^2 on [0,1] and three
 // selects (atan2f is ~40 instructions).  The orientation only feeds a linear interpolation between
 // two bins, so the error moves a normalised descriptor by < 1e-6.
 __device__ __forceinline__ float fast_rcp(float v) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }

@@ -159,3 +159,45 @@ def test_march_partition_covers_every_row_once():
     assert out.stdout.startswith("OK"), out.stdout
     # the 4K workload fills all 592 slots of one wave
     assert "B=592" in out.stdout, out.stdout
+
+
+def test_descriptor_fast_math_bounds():
+    """The descriptor kernel (k_desc.cu) replaces atan2f and the float->int conversions by cheaper forms.
+    float32 emulation of the same formulas: the atan2 polynomial stays within 1e-6 rad of atan2, and the
+    magic-number floor / fixed-point conversions are exact on their whole input range."""
+    rng = np.random.default_rng(5)
+    f32 = np.float32
+    # fast_atan2: a = min/max, degree-6 polynomial in a^2 (coefficients as in k_desc.cu)
+    coef = [0.006811764091253281, -0.03360414132475853, 0.07962359488010406, -0.1323333978652954,
+            0.19807815551757812, -0.3331736922264099, 0.9999961256980896]
+    y = rng.uniform(-255, 255, 200000).astype(f32)
+    x = rng.uniform(-255, 255, 200000).astype(f32)
+    ax, ay = np.abs(x), np.abs(y)
+    mx, mn = np.maximum(ax, ay), np.minimum(ax, ay)
+    a = np.where(mx > f32(1e-30), mn / np.where(mx > 0, mx, 1), f32(0)).astype(f32)
+    s = (a * a).astype(f32)
+    p = np.full_like(a, f32(coef[0]))
+    for c in coef[1:]:
+        p = (p * s + f32(c)).astype(f32)
+    r = (p * a).astype(f32)
+    r = np.where(ay > ax, f32(1.57079632679489662) - r, r).astype(f32)
+    r = np.where(x < 0, f32(3.14159265358979323846) - r, r).astype(f32)
+    r = np.copysign(r, y)
+    err = np.abs(r.astype(np.float64) - np.arctan2(y.astype(np.float64), x.astype(np.float64)))
+    assert err.max() < 1e-6, err.max()
+    # floor_bits: v + 1.5 * 2^23 rounded DOWN keeps floor(v) in the low mantissa bits (two's complement)
+    v = np.concatenate([rng.uniform(-40, 40, 100000), np.arange(-16, 17), np.arange(-16, 17) - 1e-4]).astype(f32)
+    magic = np.float64(12582912.0)
+    summed = np.floor(v.astype(np.float64) + magic)              # exact real sum, then round toward -inf to an integer ulp
+    bits = summed.astype(f32).view(np.uint32)
+    assert np.array_equal(summed.astype(f32).astype(np.float64), summed)   # representable: ulp is 1 in [2^23, 2^24)
+    fl = np.floor(v.astype(np.float64)).astype(np.int64)
+    assert np.array_equal((bits & 7).astype(np.int64), fl & 7)
+    assert np.array_equal(summed - magic, fl.astype(np.float64))
+    # fix_bits: round(w * c) for 0 <= w * c < 2^23 through fma(w, c, 2^23)
+    w = rng.uniform(0, 360 * 16384, 100000).astype(f32)
+    c = rng.uniform(0, 1, 100000).astype(f32)
+    prod = w.astype(np.float64) * c.astype(np.float64)
+    fixed = (np.rint(prod + 8388608.0).astype(f32).view(np.uint32) & 0x7FFFFF).astype(np.float64)
+    assert np.array_equal(fixed, np.rint(prod))
+    assert (360.0 * 16384) < 2 ** 23
