@@ -9,6 +9,7 @@ import hashlib
 import json
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -20,6 +21,7 @@ from popsift_b200.synth import make_frame, write_pgm
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
 G = os.path.join(HERE, "golden")
 REF = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "ref_dump")
 F1_MIN, L2_MAX = 0.99, 1e-3
@@ -248,3 +250,41 @@ def test_popsift_demo_cli(tmp_path):
     assert all(len(l.split()) == 133 for l in lines)
     assert "Number of feature points: %d number of feature descriptors: %d" % (feats.getFeatureCount(), feats.getDescriptorCount()) in r.stderr
     ps.uninit()
+
+
+def _counts_in_subprocess(env_extra, w, h):
+    """feature / descriptor counts of make_frame(w, h, 7) from tools/one_frame.py in a fresh process (the
+    library reads its A/B switches once per process)."""
+    env = dict(os.environ, **env_extra)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "one_frame.py"), str(w), str(h), "4", "1"],
+                         env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    nf, nd = out.stdout.split()[-2:]
+    return int(nf), int(nd)
+
+
+def test_fallback_paths_give_the_same_counts():
+    """The candidate-driven extrema stage (default), the dense DoG scan and the tile pyramid kernels are
+    three routes to the same extrema: identical feature and descriptor counts on a 1080p frame."""
+    w, h = 1920, 1080
+    base = _counts_in_subprocess({}, w, h)
+    assert base[0] > 1000
+    assert _counts_in_subprocess({"POPSIFT_B200_DENSE_SCAN": "1"}, w, h) == base
+    assert _counts_in_subprocess({"POPSIFT_B200_TILE_KERNELS": "1"}, w, h) == base
+    assert _counts_in_subprocess({"POPSIFT_B200_UNIFORM": "1", "POPSIFT_B200_FORK": "0"}, w, h) == base
+
+
+def test_float_images_track_the_byte_path():
+    """PopSift::FloatImages (reference popsift.h:163, values in [0,1]): the same frame as float32 / 255 goes
+    through the general level-0 kernel (bilinear blend in fp32 instead of the 8-bit texture arithmetic), so
+    the planes differ in the last bits only and the keypoints must be (almost) the same."""
+    w, h = 640, 480
+    img = make_frame(w, h, 11)
+    cfg = mk_cfg("vlfeat", "classic")
+    ps8, f8 = run_gpu(img, cfg)
+    psf = api.PopSift(cfg, imode=api.PopSift.FloatImages, max_width=w, max_height=h, slots=1)
+    ff = psf.enqueue(w, h, (img.astype(np.float32) / np.float32(255.0))).get()
+    assert abs(ff.getFeatureCount() - f8.getFeatureCount()) <= max(3, f8.getFeatureCount() // 50)
+    r = compare.report(*ff.keypoints(), *f8.keypoints())
+    assert r["f1"] >= 0.95, r
+    ps8.uninit(); psf.uninit()
