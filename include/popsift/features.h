@@ -77,15 +77,28 @@ using Features = FeaturesHost;
 
 std::ostream& operator<<(std::ostream& ostr, const FeaturesHost& feature);
 
-/// Device-resident results (Config::MatchingMode).  Not part of this round's hot path
-/// (SURVEY.md 8f rank 1): the type exists so that callers compile; getDev() reports an error.
+/// Device-resident results (Config::MatchingMode; reference features.h:104-122): Feature records,
+/// descriptors and the descriptor -> feature reverse map live in device memory owned by this object;
+/// Feature::desc[] are device pointers into getDescriptors().  The brute-force matcher
+/// (FeaturesDev::match) is not part of this library yet.
 class FeaturesDev : public FeaturesBase
 {
+    Feature*    _ext;
+    Descriptor* _ori;
+    int*        _rev;   // the reverse map from descriptors to extrema
+
 public:
-    FeaturesDev() = default;
-    Feature*    getFeatures() { return nullptr; }
-    Descriptor* getDescriptors() { return nullptr; }
-    int*        getReverseMap() { return nullptr; }
+    FeaturesDev();
+    FeaturesDev(int num_ext, int num_ori);
+    ~FeaturesDev() override;
+
+    void reset(int num_ext, int num_ori);
+
+    void match(FeaturesDev* other);     // throws: not implemented
+
+    Feature*    getFeatures() { return _ext; }
+    Descriptor* getDescriptors() { return _ori; }
+    int*        getReverseMap() { return _rev; }
 };
 
 } // namespace popsift

@@ -98,5 +98,6 @@ private:
     int       _last_init_h{};
     ImageMode _image_mode;
     int       _device;
+    popsift::Config::ProcessingMode _proc_mode{popsift::Config::ExtractingMode};
     bool      _isInit{true};
 };

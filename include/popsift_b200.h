@@ -142,6 +142,16 @@ int ps_counts(ps_ctx* ctx, int slot, int32_t* n_feat, int32_t* n_desc);
  * copies n_feat Feature records and n_desc descriptors to the caller's arrays; Feature::desc[]
  * are host pointers into `desc`. */
 int ps_download(ps_ctx* ctx, int slot, ps_feature* feat, ps_descriptor* desc);
+/* replaces Pyramid::clone_device_descriptors (reference sift_pyramid.cu:324-362), the result path of
+ * Config::MatchingMode: copies the slot's n_feat Feature records, n_desc descriptors and the
+ * descriptor -> feature reverse map into caller-owned DEVICE arrays (sizes from ps_counts);
+ * Feature::desc[] are device pointers into `d_desc`.  Nothing is copied to the host. */
+int ps_download_dev(ps_ctx* ctx, int slot, ps_feature* d_feat, ps_descriptor* d_desc, int32_t* d_rev);
+/* device memory for ps_download_dev results (thin wrappers of cudaMalloc / cudaFree on the current
+ * device) and a blocking device -> host copy for callers without a CUDA toolchain */
+void* ps_dev_alloc(size_t bytes);
+void  ps_dev_free(void* p);
+int   ps_dev_to_host(void* dst_host, const void* src_dev, size_t bytes);
 /* page-locked host memory for images and results (thin wrappers of cudaHostAlloc / cudaFreeHost).
  * ps_submit_* and ps_download detect page-locked buffers and copy straight from / into them; pageable
  * buffers are staged through the slot's own pinned buffers (one extra host memcpy). */

@@ -50,7 +50,8 @@ assert FEATURE_DTYPE.itemsize == 72 and EXTREMUM_DTYPE.itemsize == 44
 EXPORTS = ["ps_abi_version", "ps_config_default", "ps_gauss_tables_compute", "ps_geometry", "ps_create", "ps_destroy",
            "ps_last_error", "ps_submit_u8", "ps_submit_f32", "ps_submit_dev_u8", "ps_counts", "ps_download",
            "ps_sync", "ps_debug_plane", "ps_debug_extrema", "ps_slot_geometry", "ps_set_timing", "ps_stage_ms",
-           "ps_launch_count", "ps_slot_stream", "ps_run_pyramid_only", "ps_run_level_only", "ps_host_alloc", "ps_host_free"]
+           "ps_launch_count", "ps_slot_stream", "ps_run_pyramid_only", "ps_run_level_only", "ps_host_alloc", "ps_host_free",
+           "ps_download_dev", "ps_dev_alloc", "ps_dev_free", "ps_dev_to_host"]
 
 _lib = None
 
@@ -93,6 +94,11 @@ def load_library():
     L.ps_host_alloc.restype = C.c_void_p
     L.ps_host_alloc.argtypes = [C.c_size_t]
     L.ps_host_free.argtypes = [C.c_void_p]
+    L.ps_download_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ps_dev_alloc.restype = C.c_void_p
+    L.ps_dev_alloc.argtypes = [C.c_size_t]
+    L.ps_dev_free.argtypes = [C.c_void_p]
+    L.ps_dev_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     _lib = L
     return L
 
@@ -279,18 +285,69 @@ class Features:
                 fh.write("%g %g %g 0 %g %s \n" % (f["x"], f["y"], sigval, sigval, ds))
 
 
+class FeaturesDev:
+    """FeaturesDev (reference src/popsift/features.h:104-122): Feature records, descriptors and the
+    descriptor -> feature reverse map in DEVICE memory owned by this object (Config.MatchingMode).
+    getFeatures / getDescriptors / getReverseMap return raw device addresses."""
+
+    def __init__(self, lib, n_feat: int, n_desc: int):
+        self._lib, self._nf, self._nd = lib, n_feat, n_desc
+        self._pf = lib.ps_dev_alloc(max(n_feat, 1) * 72)
+        self._pd = lib.ps_dev_alloc(max(n_desc, 1) * 512)
+        self._pr = lib.ps_dev_alloc(max(n_desc, 1) * 4)
+        if not (self._pf and self._pd and self._pr):
+            raise PopSiftError("Failed to allocate device memory for features")
+
+    def getFeatureCount(self): return self._nf
+    def getDescriptorCount(self): return self._nd
+    size = getFeatureCount
+    def getFeatures(self): return self._pf
+    def getDescriptors(self): return self._pd
+    def getReverseMap(self): return self._pr
+
+    def match(self, other):
+        raise PopSiftError("FeaturesDev.match (brute-force matcher) is not implemented")
+
+    def to_host(self):
+        """(features, descriptors, reverse map) copied to numpy arrays; desc_ptr still holds DEVICE addresses"""
+        feat = np.zeros(self._nf, FEATURE_DTYPE)
+        desc = np.zeros((self._nd, 128), np.float32)
+        rev = np.zeros(self._nd, np.int32)
+        for arr, ptr in ((feat, self._pf), (desc, self._pd), (rev, self._pr)):
+            if arr.nbytes and self._lib.ps_dev_to_host(arr.ctypes.data, ptr, arr.nbytes) != 0:
+                raise PopSiftError("device -> host copy failed")
+        return feat, desc, rev
+
+    def __del__(self):
+        lib = getattr(self, "_lib", None)
+        if lib is not None:
+            for p in (self._pf, self._pd, self._pr):
+                if p:
+                    lib.ps_dev_free(p)
+            self._pf = self._pd = self._pr = None
+
+
 class SiftJob:
     """SiftJob (reference src/popsift/popsift.h:44-100): get() blocks until the features are there."""
 
     def __init__(self, owner: "PopSift", slot: int):
         self._owner, self._slot, self._result = owner, slot, None
 
-    def get(self) -> Features:
+    def getBase(self):
         if self._result is None:
             self._result = self._owner._collect(self._slot)
         return self._result
 
+    def get(self) -> Features:
+        """host features (None under Config.MatchingMode, like the reference's dynamic_cast)"""
+        r = self.getBase()
+        return r if isinstance(r, Features) else None
+
     getHost = get
+
+    def getDev(self) -> "FeaturesDev":
+        r = self.getBase()
+        return r if isinstance(r, FeaturesDev) else None
 
 
 class PopSift:
@@ -304,6 +361,7 @@ class PopSift:
         self._lib = load_library()
         self._config = config or Config()
         self._imode, self._device, self._nslots = imode, device, slots
+        self._mode = mode
         self._ctx = None
         self._max = (max_width, max_height)
         self._next = 0
@@ -336,7 +394,7 @@ class PopSift:
         slot = self._next
         self._next = (self._next + 1) % self._nslots
         if self._busy[slot] is not None:
-            self._busy[slot].get()       # FIFO: the slot's previous job completes first
+            self._busy[slot].getBase()   # FIFO: the slot's previous job completes first
         fn = self._lib.ps_submit_u8 if self._imode == self.ByteImages else self._lib.ps_submit_f32
         self._keep = img
         self._check(fn(self._ctx, slot, img.ctypes.data, w, h))
@@ -347,6 +405,11 @@ class PopSift:
     def _collect(self, slot: int) -> Features:
         nf, nd = C.c_int32(), C.c_int32()
         self._check(self._lib.ps_counts(self._ctx, slot, C.byref(nf), C.byref(nd)))
+        if self._mode == Config.MatchingMode:
+            fd = FeaturesDev(self._lib, nf.value, nd.value)
+            self._check(self._lib.ps_download_dev(self._ctx, slot, fd.getFeatures(), fd.getDescriptors(), fd.getReverseMap()))
+            self._busy[slot] = None
+            return fd
         blk = None
         for i, b in enumerate(self._pool):
             if b.n_feat >= nf.value and b.n_desc >= nd.value:

@@ -3,6 +3,7 @@
 //   x y 1/sigma^2 0 1/sigma^2 d0 .. d127
 #include "popsift/features.h"
 #include "pinned_pool.h"
+#include "popsift_b200.h"
 
 #include <cmath>
 #include <cstdlib>
@@ -35,6 +36,36 @@ void FeaturesHost::reset(int num_ext, int num_ori)
     if (!_ext || !_ori) throw std::runtime_error("Runtime error:\n    Failed to (re)allocate memory for downloading features");
     setFeatureCount(num_ext);
     setDescriptorCount(num_ori);
+}
+
+// ---- FeaturesDev (reference features.cu:127-163): device arrays through the C ABI's allocator
+
+FeaturesDev::FeaturesDev() : _ext(nullptr), _ori(nullptr), _rev(nullptr) {}
+FeaturesDev::FeaturesDev(int num_ext, int num_ori) : _ext(nullptr), _ori(nullptr), _rev(nullptr) { reset(num_ext, num_ori); }
+
+FeaturesDev::~FeaturesDev()
+{
+    ps_dev_free(_ext);
+    ps_dev_free(_ori);
+    ps_dev_free(_rev);
+}
+
+void FeaturesDev::reset(int num_ext, int num_ori)
+{
+    ps_dev_free(_ext); _ext = nullptr;
+    ps_dev_free(_ori); _ori = nullptr;
+    ps_dev_free(_rev); _rev = nullptr;
+    _ext = static_cast<Feature*>(ps_dev_alloc((size_t)(num_ext > 0 ? num_ext : 1) * sizeof(Feature)));
+    _ori = static_cast<Descriptor*>(ps_dev_alloc((size_t)(num_ori > 0 ? num_ori : 1) * sizeof(Descriptor)));
+    _rev = static_cast<int*>(ps_dev_alloc((size_t)(num_ori > 0 ? num_ori : 1) * sizeof(int)));
+    if (!_ext || !_ori || !_rev) throw std::runtime_error("Runtime error:\n    Failed to allocate device memory for features");
+    setFeatureCount(num_ext);
+    setDescriptorCount(num_ori);
+}
+
+void FeaturesDev::match(FeaturesDev* /*other*/)
+{
+    throw std::runtime_error("popsift_b200: FeaturesDev::match (brute-force matcher) is not implemented");
 }
 
 void FeaturesHost::pin() {}

@@ -66,11 +66,7 @@ popsift::FeaturesBase* SiftJob::getBase()
 }
 popsift::FeaturesHost* SiftJob::getHost() { return dynamic_cast<popsift::FeaturesHost*>(getBase()); }
 popsift::FeaturesHost* SiftJob::get() { return getHost(); }
-popsift::FeaturesDev* SiftJob::getDev()
-{
-    getBase();
-    throw std::runtime_error("popsift_b200: device-resident results (Config::MatchingMode) are not implemented yet");
-}
+popsift::FeaturesDev* SiftJob::getDev() { return dynamic_cast<popsift::FeaturesDev*>(getBase()); }
 
 // ---------------------------------------------------------------- PopSift::Pipe
 
@@ -112,6 +108,18 @@ PopSift::PopSift(ImageMode imode, int device) : _pipe(new Pipe), _image_mode(imo
             int rc = ps_counts(p->ctx, s, &nf, &nd);
             if (rc != PS_OK && rc != PS_ERR_OVERFLOW) { fail_job(job, ps_last_error(p->ctx)); return; }
             if (rc == PS_ERR_OVERFLOW) std::cerr << "popsift_b200 warning: " << ps_last_error(p->ctx) << std::endl;
+            if (_proc_mode == Config::MatchingMode) {
+                // device-resident results (reference popsift.cpp:346-383, sift_pyramid.cu:324-362)
+                popsift::FeaturesDev* fd = nullptr;
+                try {
+                    fd = new popsift::FeaturesDev(nf, nd);
+                    rc = ps_download_dev(p->ctx, s, reinterpret_cast<ps_feature*>(fd->getFeatures()),
+                                         reinterpret_cast<ps_descriptor*>(fd->getDescriptors()), fd->getReverseMap());
+                    if (rc != PS_OK) { delete fd; fail_job(job, ps_last_error(p->ctx)); return; }
+                } catch (const std::exception& e) { delete fd; fail_job(job, e.what()); return; }
+                job->setFeatures(fd);
+                return;
+            }
             popsift::FeaturesHost* fh = nullptr;
             try {
                 fh = new popsift::FeaturesHost(nf, nd);
@@ -173,8 +181,7 @@ PopSift::PopSift(ImageMode imode, int device) : _pipe(new Pipe), _image_mode(imo
 PopSift::PopSift(const Config& config, Config::ProcessingMode mode, ImageMode imode, int device)
     : PopSift(imode, device)
 {
-    if (mode != Config::ExtractingMode)
-        std::cerr << "popsift_b200 warning: MatchingMode is not implemented; running in ExtractingMode" << std::endl;
+    _proc_mode = mode;
     configure(config);
 }
 

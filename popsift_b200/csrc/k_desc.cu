@@ -323,7 +323,27 @@ __global__ void prep_features_kernel(Consts k, const ps_extremum* __restrict__ e
     }
 }
 
+// ps_download_dev: the copied Feature records get device pointers into the copied descriptor array
+// (the reference's prep_features does this for its device clone, sift_pyramid.cu:324-330)
+__global__ void fix_feature_pointers_kernel(ps_feature* __restrict__ feat, ps_descriptor* __restrict__ desc, int n)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int first = feat[i].pad_;
+        const int num = feat[i].num_ori;
+        feat[i].pad_ = 0;
+#pragma unroll
+        for (int r = 0; r < PS_MAX_ORI; ++r) feat[i].desc[r] = r < num ? desc + first + r : nullptr;
+    }
+}
+
 } // namespace
+
+int launch_fix_feature_pointers(ps_feature* feat, ps_descriptor* desc, int n, cudaStream_t st)
+{
+    if (n <= 0) return 0;
+    fix_feature_pointers_kernel<<<(n + 255) / 256, 256, 0, st>>>(feat, desc, n);
+    return 1;
+}
 
 int launch_descriptors(const PyramidView& pyr, const Consts& k, const ps_extremum* ext, const int* feat_to_ext,
                        ps_descriptor* desc, Counters* ct, cudaStream_t st)

@@ -525,6 +525,47 @@ extern "C" int ps_download(ps_ctx* ctx, int slot, ps_feature* feat, ps_descripto
     return PS_OK;
 }
 
+extern "C" int ps_download_dev(ps_ctx* ctx, int slot, ps_feature* d_feat, ps_descriptor* d_desc, int32_t* d_rev)
+{
+    Slot* s = get_slot(ctx, slot);
+    if (!s) return PS_ERR_ARG;
+    if (!s->submitted) return ctx->fail(PS_ERR_STATE, "ps_download_dev: nothing submitted to slot %d", slot);
+    PS_CUDA(ctx, cudaSetDevice(ctx->device));
+    PS_CUDA(ctx, cudaEventSynchronize(s->done));
+    const size_t nf = (size_t)s->h_ct->ext_total, nd = (size_t)s->h_ct->ori_total;
+    if (nf == 0) return PS_OK;
+    if (!d_feat || (nd && (!d_desc || !d_rev))) return ctx->fail(PS_ERR_ARG, "ps_download_dev: null output array");
+    PS_CUDA(ctx, cudaMemcpyAsync(d_feat, s->d_feat, nf * sizeof(ps_feature), cudaMemcpyDeviceToDevice, s->stream));
+    if (nd) {
+        PS_CUDA(ctx, cudaMemcpyAsync(d_desc, s->d_desc, nd * sizeof(ps_descriptor), cudaMemcpyDeviceToDevice, s->stream));
+        PS_CUDA(ctx, cudaMemcpyAsync(d_rev, s->d_f2e, nd * sizeof(int32_t), cudaMemcpyDeviceToDevice, s->stream));
+    }
+    ctx->launches += launch_fix_feature_pointers(d_feat, d_desc, (int)nf, s->stream);
+    PS_CUDA(ctx, cudaGetLastError());
+    PS_CUDA(ctx, cudaStreamSynchronize(s->stream));
+    return PS_OK;
+}
+
+extern "C" void* ps_dev_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+extern "C" void ps_dev_free(void* p)
+{
+    if (p) cudaFree(p);
+}
+
+extern "C" int ps_dev_to_host(void* dst_host, const void* src_dev, size_t bytes)
+{
+    if (bytes == 0) return PS_OK;
+    if (!dst_host || !src_dev) return PS_ERR_ARG;
+    if (cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return PS_ERR_CUDA; }
+    return PS_OK;
+}
+
 extern "C" int ps_debug_plane(ps_ctx* ctx, int slot, int octave, int level, int which, float* out)
 {
     Slot* s = get_slot(ctx, slot);

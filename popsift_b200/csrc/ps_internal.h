@@ -126,5 +126,7 @@ int launch_orientation(const PyramidView& pyr, const Consts& k, const InitialExt
 int launch_descriptors(const PyramidView& pyr, const Consts& k, const ps_extremum* ext, const int* feat_to_ext,
                        ps_descriptor* desc, Counters* ct, cudaStream_t st);
 int launch_prep_features(const Consts& k, const ps_extremum* ext, ps_feature* feat, const Counters* ct, cudaStream_t st);
+// device copy of the Feature records: desc[] become pointers into `desc` (first index is in pad_)
+int launch_fix_feature_pointers(ps_feature* feat, ps_descriptor* desc, int n, cudaStream_t st);
 
 } // namespace psb

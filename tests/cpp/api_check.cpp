@@ -52,5 +52,22 @@ int main(int argc, char** argv)
     try { std::vector<float> fi((size_t)w * h, 0.f); sift.enqueue(w, h, fi.data()); } catch (const std::runtime_error&) { threw = true; }
     if (!threw) return 5;
     sift.uninit();
+
+    // Config::MatchingMode: results stay on the device (reference popsift.h:79-86, features.h:104-122)
+    {
+        PopSift msift(config, popsift::Config::MatchingMode, PopSift::ByteImages, 0);
+        SiftJob* job = msift.enqueue(w, h, img.data());
+        popsift::FeaturesDev* fd = job->getDev();
+        if (!fd) return 6;
+        if (fd->getFeatureCount() <= 0 || fd->getDescriptorCount() < fd->getFeatureCount()) return 7;
+        if (!fd->getFeatures() || !fd->getDescriptors() || !fd->getReverseMap()) return 8;
+        bool nomatch = false;
+        try { fd->match(fd); } catch (const std::runtime_error&) { nomatch = true; }
+        if (!nomatch) return 9;
+        std::printf("dev %d %d\n", fd->getFeatureCount(), fd->getDescriptorCount());
+        delete fd;
+        delete job;
+        msift.uninit();
+    }
     return 0;
 }

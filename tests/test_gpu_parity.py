@@ -232,6 +232,8 @@ def test_cpp_dropin_api_matches_c_abi(tmp_path):
         nf, nd, cs = line.split()
         assert (int(nf), int(nd)) == want
         assert abs(float(cs) - s) < 1e-3 * max(1.0, abs(s))
+    # Config::MatchingMode through the C++ API: same counts, device-resident
+    assert out[3].split() == ["dev", str(want[0]), str(want[1])], out[3]
     ps.uninit()
 
 
@@ -288,3 +290,40 @@ def test_float_images_track_the_byte_path():
     r = compare.report(*ff.keypoints(), *f8.keypoints())
     assert r["f1"] >= 0.95, r
     ps8.uninit(); psf.uninit()
+
+
+def test_matching_mode_device_results_equal_host_results():
+    """Config::MatchingMode (reference popsift.cpp:346-383, sift_pyramid.cu:324-362): SiftJob::getDev returns
+    device-resident features, descriptors and the descriptor -> feature reverse map.  Read back, they must be
+    the host results of ExtractingMode, with Feature::desc[] pointing into the device descriptor array."""
+    w, h = 640, 480
+    img = make_frame(w, h, 4)
+    cfg = mk_cfg("vlfeat", "classic")
+    ps, fh = run_gpu(img, cfg)
+    pm = api.PopSift(cfg, mode=api.Config.MatchingMode, max_width=w, max_height=h, slots=2)
+    job = pm.enqueue(w, h, img)
+    assert job.get() is None                      # like the reference's dynamic_cast to FeaturesHost
+    fd = job.getDev()
+    assert fd.getFeatureCount() == fh.getFeatureCount() and fd.getDescriptorCount() == fh.getDescriptorCount()
+    feat, desc, rev = fd.to_host()
+    # extrema may be emitted in a different order by the two runs: compare as sorted (feature, orientation) rows
+    def rows(feat, desc, didx):
+        out = []
+        for i, f in enumerate(feat):
+            for k in range(int(f["num_ori"])):
+                out.append((f["x"], f["y"], f["sigma"], f["ori"][k]) + tuple(desc[didx[i, k]]))
+        return np.array(sorted(out), dtype=np.float64)
+    base = fd.getDescriptors()
+    didx = np.full((len(feat), 4), -1, np.int64)
+    for k in range(4):
+        m = feat["num_ori"] > k
+        didx[m, k] = (feat["desc_ptr"][m, k].astype(np.int64) - base) // 512
+        assert np.all(feat["desc_ptr"][~m, k] == 0)
+    assert didx.max() < len(desc) and (didx[didx >= 0] >= 0).all()
+    assert np.array_equal(rows(feat, desc, didx), rows(fh.feat, fh.desc, fh.desc_idx))
+    # reverse map: descriptor d belongs to feature rev[d], which lists it among its orientations
+    for d in range(len(desc)):
+        assert d in didx[rev[d]]
+    with pytest.raises(api.PopSiftError):
+        fd.match(fd)
+    ps.uninit(); pm.uninit()
