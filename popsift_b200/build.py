@@ -33,6 +33,8 @@ API_CHECK = os.path.join(BIN_DIR, "api_check")
 API_CHECK_SRC = os.path.join(ROOT, "tests", "cpp", "api_check.cpp")
 PART_CHECK = os.path.join(BIN_DIR, "partition_check")
 PART_CHECK_SRC = os.path.join(ROOT, "tests", "cpp", "partition_check.cpp")
+PGM_CHECK = os.path.join(BIN_DIR, "pgmread_check")
+PGM_CHECK_SRC = os.path.join(ROOT, "tests", "cpp", "pgmread_check.cpp")
 
 
 def _newer(target: str, deps) -> bool:
@@ -89,6 +91,10 @@ def build(verbose: bool = False, force: bool = False) -> str:
     if os.path.exists(PART_CHECK_SRC) and (force or _newer(PART_CHECK, [PART_CHECK_SRC, part_hdr])):
         # host-only sweep of the marching kernels' work partition (no CUDA, no library)
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + CSRC, PART_CHECK_SRC, "-o", PART_CHECK])
+    pgm_src = os.path.join(CSRC, "app", "pgmread.cpp")
+    if os.path.exists(PGM_CHECK_SRC) and (force or _newer(PGM_CHECK, [PGM_CHECK_SRC, pgm_src, os.path.join(CSRC, "app", "pgmread.h")])):
+        # host-only check of popsift-demo's image reader
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(CSRC, "app"), PGM_CHECK_SRC, pgm_src, "-o", PGM_CHECK])
     return LIB
 
 

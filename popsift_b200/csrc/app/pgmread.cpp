@@ -24,9 +24,11 @@ bool next_token(const std::vector<char>& d, size_t& pos, std::string& tok)
     return true;
 }
 
-inline unsigned char to_gray(float r, float g, float b)
+// colour -> gray exactly as the reference is compiled (RGB2GRAY_IN_INT, reference
+// src/application/pgmread.cpp:17-28,165-169): OpenCV's 14-bit integer weights, truncating cast
+inline unsigned char to_gray(unsigned r, unsigned g, unsigned b)
 {
-    return (unsigned char)(0.298912f * r + 0.586611f * g + 0.114478f * b);
+    return (unsigned char)((4899u * r + 9617u * g + 1868u * b) >> 14);
 }
 
 } // namespace
@@ -71,11 +73,13 @@ unsigned char* readPGMfile(const std::string& filename, int& w, int& h)
     if (chans == 1) {
         for (size_t i = 0; i < (size_t)w * h; i++) out[i] = (type == 5 && maxval < 256) ? (unsigned char)v[i] : scale(v[i]);
     } else {
+        // P3 values are scaled to 8 bits first (reference pgmread.cpp:146-155); P6 samples go into the
+        // weights as stored, 8- or 16-bit, whatever maxval says (:198-246)
+        const bool raw = (type == 6);
         for (size_t i = 0; i < (size_t)w * h; i++) {
-            const bool raw16 = (type == 6 && maxval >= 256);
-            const float r = raw16 ? (float)v[3 * i] : (float)scale(v[3 * i]);
-            const float g = raw16 ? (float)v[3 * i + 1] : (float)scale(v[3 * i + 1]);
-            const float b = raw16 ? (float)v[3 * i + 2] : (float)scale(v[3 * i + 2]);
+            const unsigned r = raw ? (unsigned)v[3 * i] : (unsigned)scale(v[3 * i]);
+            const unsigned g = raw ? (unsigned)v[3 * i + 1] : (unsigned)scale(v[3 * i + 1]);
+            const unsigned b = raw ? (unsigned)v[3 * i + 2] : (unsigned)scale(v[3 * i + 2]);
             out[i] = to_gray(r, g, b);
         }
     }

@@ -201,3 +201,49 @@ def test_descriptor_fast_math_bounds():
     fixed = (np.rint(prod + 8388608.0).astype(f32).view(np.uint32) & 0x7FFFFF).astype(np.float64)
     assert np.array_equal(fixed, np.rint(prod))
     assert (360.0 * 16384) < 2 ** 23
+
+
+def _ref_pgm_gray(kind, maxval, samples, w, h):
+    """What the reference reader returns (reference src/application/pgmread.cpp:126-250, as compiled with
+    RGB2GRAY_IN_INT): P2/P3 values and 16-bit P5 values are scaled by 255.0/maxval (truncating), 8-bit P5
+    bytes are taken as they are, colour becomes (4899 r + 9617 g + 1868 b) >> 14 truncated to 8 bits, and
+    P6 samples enter the weights unscaled (8- or 16-bit)."""
+    s = np.asarray(samples, np.int64)
+    def scale(v):
+        return v if maxval == 255 else (v * 255.0 / maxval).astype(np.int64)
+    if kind == 2:
+        return scale(s).astype(np.uint8)
+    if kind == 5:
+        return s.astype(np.uint8) if maxval < 256 else (s * 255.0 / maxval).astype(np.int64).astype(np.uint8)
+    rgb = (scale(s) & 0xff if kind == 3 else s).reshape(-1, 3)
+    return ((4899 * rgb[:, 0] + 9617 * rgb[:, 1] + 1868 * rgb[:, 2]) >> 14).astype(np.uint8)
+
+
+@pytest.mark.parametrize("kind,maxval", [(2, 255), (2, 1023), (3, 255), (3, 15), (5, 255), (5, 100), (5, 65535),
+                                         (6, 255), (6, 65535)])
+def test_netpbm_reader_matches_reference_conversions(tmp_path, kind, maxval):
+    """popsift-demo's reader (csrc/app/pgmread.cpp) on generated P2 / P3 / P5 / P6 files, comments included."""
+    import subprocess
+    from popsift_b200 import build as B
+    B.build()
+    rng = np.random.default_rng(kind * 1000 + maxval)
+    w, h = 7, 5
+    ch = 3 if kind in (3, 6) else 1
+    samples = rng.integers(0, maxval + 1, w * h * ch)
+    path = str(tmp_path / "img.pnm")
+    header = ("P%d\n# a comment\n%d %d\n# another\n%d\n" % (kind, w, h, maxval)).encode()
+    with open(path, "wb") as f:
+        f.write(header)
+        if kind in (2, 3):
+            f.write((" ".join(str(int(v)) for v in samples) + "\n").encode())
+        elif maxval < 256:
+            f.write(samples.astype(np.uint8).tobytes())
+        else:
+            f.write(samples.astype("<u2").tobytes())      # the reference reads 16-bit samples in host order
+    out = subprocess.run([B.PGM_CHECK, path], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = out.stdout.split("\n")
+    assert lines[0].split() == [str(w), str(h)]
+    got = np.frombuffer(bytes.fromhex(lines[1]), np.uint8)
+    want = _ref_pgm_gray(kind, maxval, samples, w, h)
+    assert np.array_equal(got, want), (got, want)
