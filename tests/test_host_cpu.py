@@ -247,3 +247,27 @@ def test_netpbm_reader_matches_reference_conversions(tmp_path, kind, maxval):
     got = np.frombuffer(bytes.fromhex(lines[1]), np.uint8)
     want = _ref_pgm_gray(kind, maxval, samples, w, h)
     assert np.array_equal(got, want), (got, want)
+
+
+def test_match_oracle_on_constructed_descriptors():
+    """tests/match_oracle.py (restatement of the reference matcher, groundwork for SURVEY 8f rank 2): right
+    descriptors built from the left ones with known perturbations give known best / second / accept."""
+    import match_oracle as mo
+    rng = np.random.default_rng(3)
+    left = rng.uniform(0, 1, (6, 128)).astype(np.float32)
+    left /= np.linalg.norm(left, axis=1, keepdims=True)
+    right = np.zeros((8, 128), np.float32)
+    perm = [3, 0, 5, 1, 4, 2]
+    for i, p in enumerate(perm):
+        right[i] = left[p] + np.float32(0.01) * rng.standard_normal(128).astype(np.float32)     # near copy of left[p]
+    right[6] = left[0] + np.float32(0.011) * rng.standard_normal(128).astype(np.float32)        # a second near copy of left[0]
+    right[7] = rng.uniform(0, 1, 128).astype(np.float32)
+    m = mo.match(left, right)
+    inv = {p: i for i, p in enumerate(perm)}
+    for l in range(6):
+        assert m[l, 0] == inv[l] or (l == 0 and m[l, 0] in (inv[0], 6))
+    assert set(m[0, :2]) == {inv[0], 6} and m[0, 2] == 0          # two equally good candidates: ratio test rejects
+    assert all(m[l, 2] == 1 for l in range(1, 6))                 # unique near copies: accepted
+    # the matrix-product form agrees on this well-separated set
+    assert np.array_equal(mo.match(left, right, exact_order=False)[:, [0, 2]], m[:, [0, 2]])
+    assert mo.match(left, right[:0]).tolist() == [[0, 0, 0]] * 6
