@@ -18,7 +18,7 @@ Printed JSON (rank 0, one line):
   roofline  pyramid stage: algorithmic bytes per frame (68 B per octave-pixel) / CUDA-event
             time of the pyramid launches of one frame, against the measured HBM peak
             (MEASURED_PEAKS.json); `dominant_kernel` = the octave-0 fused blur+DoG launches alone.
-  cpu_baseline  the CPU oracle port (oracle/sift_oracle.c, OpenMP) timed on one frame of the workload;
+  cpu_baseline  the CPU oracle port (oracle/sift_oracle.c, OpenMP) timed on the first four frames of the workload;
   opencv_cpu    cv2.SIFT on the same frame, all host cores (the CPU baseline north_star names).
 `--impl reference` times the UNMODIFIED reference PopSift (oracle/_ref, CUDA, built from
 /root/reference) on the same frames through its own public API (host buffers in, host features out).
@@ -329,22 +329,30 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks,
     }
     if world == 1:      # reported baselines: rank 0 at N=1 only (torchrun pins OMP_NUM_THREADS=1)
-        out.update(cpu_baselines(frames[0]))
+        out.update(cpu_baselines(frames))
     return out
 
 
-def cpu_baselines(frame):
-    """CPU oracle port + OpenCV SIFT on ONE frame of the workload (bounded sample)."""
+def cpu_baselines(frames, n_oracle=4):
+    """CPU oracle port on the first `n_oracle` frames of the workload (about 10 s on the box's host cores) and
+    OpenCV SIFT on the first frame: bounded samples, reported baselines."""
     res = {}
+    frame = frames[0]
     try:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_lib as ol
         cores = ol.lib().orc_set_threads(0)
         o = ol.Oracle(ol.make_config(octaves=OCTAVES), W, H)
-        t = time.perf_counter(); o.run(frame); dt = time.perf_counter() - t
-        nf, nd = o.features()[0].shape[0], o.features()[1].shape[0]
-        res["cpu_baseline"] = {"value": W * H / dt / 1e6, "unit": "Mpixels/s", "cores": cores, "kind": "port",
-                               "sample": "1 frame 3840x2160 of the same workload, oracle/sift_oracle.c (OpenMP), %.2f s, %d features" % (dt, nf)}
+        sample = frames[:n_oracle]
+        nf = 0
+        t = time.perf_counter()
+        for f in sample:
+            o.run(f)
+            nf += o.features()[0].shape[0]
+        dt = time.perf_counter() - t
+        res["cpu_baseline"] = {"value": len(sample) * W * H / dt / 1e6, "unit": "Mpixels/s", "cores": cores, "kind": "port",
+                               "sample": "%d frames 3840x2160 of the same workload, oracle/sift_oracle.c (OpenMP), %.2f s, %d features"
+                                         % (len(sample), dt, nf)}
         o.close()
     except Exception as e:  # the oracle is test infrastructure; its absence must not hide the GPU numbers
         res["cpu_baseline"] = {"value": None, "unit": "Mpixels/s", "cores": 0, "kind": "port", "sample": "unavailable: %s" % e}
