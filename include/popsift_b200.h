@@ -25,11 +25,12 @@
 extern "C" {
 #endif
 
-#define PS_ABI_VERSION   1
+#define PS_ABI_VERSION   2
 #define PS_MAX_OCTAVES   20   /* reference sift_conf.h:12  MAX_OCTAVES   */
 #define PS_GAUSS_ALIGN   32   /* reference sift_constants.h:37            */
 #define PS_GAUSS_LEVELS  12   /* reference sift_constants.h:38            */
 #define PS_MAX_ORI       4    /* reference sift_constants.h:54            */
+#define PS_MAX_FILTER_GRID 32 /* grid filter: at most 32 x 32 cells        */
 
 typedef enum ps_status {
     PS_OK             =  0,
@@ -46,6 +47,8 @@ enum { PS_GAUSS_VLFEAT_COMPUTE = 0, PS_GAUSS_VLFEAT_RELATIVE = 1, PS_GAUSS_VLFEA
        PS_GAUSS_OPENCV_COMPUTE = 3, PS_GAUSS_FIXED9 = 4, PS_GAUSS_FIXED15 = 5 };
 enum { PS_DESC_LOOP = 0, PS_DESC_ILOOP = 1, PS_DESC_GRID = 2, PS_DESC_IGRID = 3, PS_DESC_NOTILE = 4 };
 enum { PS_NORM_ROOTSIFT = 0, PS_NORM_CLASSIC = 1 };
+enum { PS_SCALE_DIRECT = 0, PS_SCALE_DEFAULT = 1 };                                  /* sift_conf.h:75-80   */
+enum { PS_FILTER_RANDOM = 0, PS_FILTER_LARGEST_FIRST = 1, PS_FILTER_SMALLEST_FIRST = 2 }; /* sift_conf.h:118-125 */
 
 /* The fields of popsift::Config (reference sift_conf.h:29-409) that the kernels consume. */
 typedef struct ps_config {
@@ -58,11 +61,16 @@ typedef struct ps_config {
     float   initial_blur;      /* 0.5                                                      */
     int32_t has_initial_blur;  /* 1                                                        */
     int32_t sift_mode;         /* PS_MODE_*                                                */
-    int32_t gauss_mode;        /* PS_GAUSS_*  (only VLFEAT_COMPUTE is implemented)         */
-    int32_t desc_mode;         /* PS_DESC_*   (all map to LOOP numerics)    */
+    int32_t gauss_mode;        /* PS_GAUSS_*  (only VLFEAT_COMPUTE is implemented; others are REJECTED by ps_create) */
+    int32_t desc_mode;         /* PS_DESC_*   (only LOOP is implemented; others are REJECTED by ps_create)           */
     int32_t norm_mode;         /* PS_NORM_*                                                */
     int32_t norm_multi;        /* descriptor scaled by 2^norm_multi                        */
     int32_t max_extrema;       /* 100000 per octave                                        */
+    /* ABI 2 */
+    int32_t scaling_mode;      /* PS_SCALE_*  (only DEFAULT is implemented; DIRECT is REJECTED by ps_create)         */
+    int32_t filter_max_extrema;/* <= 0: grid filter off (reference sift_conf.cu:30, s_orientation.cu:380-383)        */
+    int32_t filter_grid_size;  /* 2: cells per image side (s_filtergrid.cu:125)                                      */
+    int32_t filter_sort;       /* PS_FILTER_*                                                                        */
 } ps_config;
 
 /* Same bytes as popsift::Descriptor (reference sift_extremum.h:69-72). */

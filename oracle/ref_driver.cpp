@@ -9,6 +9,14 @@
 //           [--log]               reference LogMode::All: raw plane dumps into cwd
 //                                 (dir-octave-dump/, dir-dog-dump/, sift_octave.cu:111-188)
 //           [--bench STEPS WARMUP] time STEPS passes over all frames, print JSON
+//           [--float-mode]        PopSift::FloatImages, pixels = u8 / 256 (reference main.cpp:234)
+//           [--filter-max-extrema N --filter-grid G --filter-sort up|down|random]   grid filter
+//           [--desc-mode loop|iloop|grid|igrid|notile] [--direct-scaling]
+//           [--match]             Config::MatchingMode on exactly two inputs: SiftJob::getDev for both,
+//                                 device results copied back into features.bin.0/.1 (+ "PSR1" reverse map),
+//                                 then FeaturesDev::match (features.cu:282-304), whose device printf lines
+//                                 ("accept feat ..." / "reject feat ...") go to stdout
+//           [--repeat N]          run the whole frame list N times, outputs suffixed .rK (run-to-run jitter)
 //
 // features.bin layout (little endian):
 //   char magic[4]="PSF1"; int32 n_feat; int32 n_desc;
@@ -66,12 +74,42 @@ static void write_features(const std::string& fn, popsift::FeaturesHost* fh)
     fclose(fp);
 }
 
+// device-resident results (Config::MatchingMode) copied back; Feature::desc[] are DEVICE pointers into the
+// descriptor array and become indices; the reverse map follows as "PSR1" n_desc x int32
+static void write_dev_features(const std::string& fn, popsift::FeaturesDev* fd)
+{
+    const int nf = fd->getFeatureCount(), nd = fd->getDescriptorCount();
+    std::vector<popsift::Feature> F(nf);
+    std::vector<popsift::Descriptor> D(nd);
+    std::vector<int> R(nd);
+    cudaMemcpy(F.data(), fd->getFeatures(), sizeof(popsift::Feature) * nf, cudaMemcpyDeviceToHost);
+    cudaMemcpy(D.data(), fd->getDescriptors(), sizeof(popsift::Descriptor) * nd, cudaMemcpyDeviceToHost);
+    cudaMemcpy(R.data(), fd->getReverseMap(), sizeof(int) * nd, cudaMemcpyDeviceToHost);
+    FILE* fp = fopen(fn.c_str(), "wb");
+    if (!fp) { perror("fopen"); exit(2); }
+    fwrite("PSF1", 1, 4, fp); fwrite(&nf, 4, 1, fp); fwrite(&nd, 4, 1, fp);
+    popsift::Descriptor* base = fd->getDescriptors();
+    for (int i = 0; i < nf; i++) {
+        int idx[4];
+        for (int k = 0; k < 4; k++) idx[k] = (k < F[i].num_ori && F[i].desc[k]) ? int(F[i].desc[k] - base) : -1;
+        fwrite(&F[i].debug_octave, 4, 1, fp);
+        fwrite(&F[i].xpos, 4, 1, fp); fwrite(&F[i].ypos, 4, 1, fp); fwrite(&F[i].sigma, 4, 1, fp);
+        fwrite(&F[i].num_ori, 4, 1, fp); fwrite(F[i].orientation, 4, 4, fp); fwrite(idx, 4, 4, fp);
+    }
+    fwrite(D.data(), sizeof(float) * 128, nd, fp);
+    fwrite("PSR1", 1, 4, fp);
+    fwrite(R.data(), 4, nd, fp);
+    fclose(fp);
+}
+
 int main(int argc, char** argv)
 {
     std::vector<std::string> inputs;
     std::string out;
-    bool log = false;
-    int bench_steps = 0, bench_warm = 0, device = 0;
+    bool log = false, float_mode = false, do_match = false, direct_scaling = false;
+    int bench_steps = 0, bench_warm = 0, device = 0, repeat = 1;
+    int filter_max = -1, filter_grid = -1;
+    std::string filter_sort = "", desc_mode = "";
     std::string mode = "popsift", norm = "", gauss = "";
     float downsampling = 1e9f, sigma = -1, threshold = -1, edge = -1, iblur = -1;
     int octaves = -2, levels = -1, norm_multi = -1000;
@@ -94,6 +132,14 @@ int main(int argc, char** argv)
         else if (a == "--initial-blur") iblur = atof(nxt());
         else if (a == "--norm-multi") norm_multi = atoi(nxt());
         else if (a == "--device") device = atoi(nxt());
+        else if (a == "--float-mode") float_mode = true;
+        else if (a == "--match") do_match = true;
+        else if (a == "--direct-scaling") direct_scaling = true;
+        else if (a == "--repeat") repeat = atoi(nxt());
+        else if (a == "--filter-max-extrema") filter_max = atoi(nxt());
+        else if (a == "--filter-grid") filter_grid = atoi(nxt());
+        else if (a == "--filter-sort") filter_sort = nxt();
+        else if (a == "--desc-mode") desc_mode = nxt();
         else if (a == "--bench") { bench_steps = atoi(nxt()); bench_warm = atoi(nxt()); }
         else { fprintf(stderr, "unknown flag %s\n", a.c_str()); return 2; }
     }
@@ -116,19 +162,57 @@ int main(int argc, char** argv)
     if (iblur >= 0) cfg.setInitialBlur(iblur);
     if (norm_multi > -1000) cfg.setNormalizationMultiplier(norm_multi);
     if (log) cfg.setLogMode(popsift::Config::All);
+    if (filter_max >= 0) cfg.setFilterMaxExtrema(filter_max);
+    if (filter_grid >= 0) cfg.setFilterGridSize(filter_grid);
+    if (!filter_sort.empty()) cfg.setFilterSorting(filter_sort);
+    if (!desc_mode.empty()) cfg.setDescMode(desc_mode);
+    if (direct_scaling) cfg.setScalingMode(popsift::Config::ScaleDirect);
 
     std::vector<Frame> frames(inputs.size());
     for (size_t k = 0; k < inputs.size(); k++)
         if (!read_pgm(inputs[k], frames[k])) { fprintf(stderr, "cannot read %s\n", inputs[k].c_str()); return 2; }
 
-    PopSift sift(cfg, popsift::Config::ExtractingMode, PopSift::ByteImages, device);
+    if (do_match) {
+        if (frames.size() != 2) { fprintf(stderr, "--match needs exactly two inputs\n"); return 2; }
+        PopSift msift(cfg, popsift::Config::MatchingMode, PopSift::ByteImages, device);
+        popsift::FeaturesDev* fd[2];
+        for (int k = 0; k < 2; k++) {
+            SiftJob* j = msift.enqueue(frames[k].w, frames[k].h, frames[k].px.data());
+            fd[k] = j->getDev();
+            delete j;
+            fprintf(stderr, "ref_dump: %s -> %d features, %d descriptors (device)\n", inputs[k].c_str(),
+                    fd[k]->getFeatureCount(), fd[k]->getDescriptorCount());
+            if (!out.empty()) write_dev_features(out + "." + std::to_string(k), fd[k]);
+        }
+        fflush(stdout);
+        fd[0]->match(fd[1]);          // device printf -> stdout
+        cudaDeviceSynchronize();
+        fflush(stdout);
+        delete fd[0]; delete fd[1];
+        msift.uninit();
+        return 0;
+    }
+
+    PopSift sift(cfg, popsift::Config::ExtractingMode, float_mode ? PopSift::FloatImages : PopSift::ByteImages, device);
+    std::vector<std::vector<float>> fframes;
+    if (float_mode) {
+        fframes.resize(frames.size());
+        for (size_t k = 0; k < frames.size(); k++) {
+            fframes[k].resize(frames[k].px.size());
+            for (size_t i = 0; i < frames[k].px.size(); i++) fframes[k][i] = float(frames[k].px[i]) / 256.0f;
+        }
+    }
+    auto enqueue = [&](size_t k) -> SiftJob* {
+        return float_mode ? sift.enqueue(frames[k].w, frames[k].h, fframes[k].data())
+                          : sift.enqueue(frames[k].w, frames[k].h, frames[k].px.data());
+    };
 
     if (bench_steps > 0) {
         // one "step" = every frame enqueued, every result fetched (host buffers in, host features out)
         size_t nfeat = 0, ndesc = 0;
         auto pass = [&]() {
             std::vector<SiftJob*> jobs;
-            for (auto& f : frames) jobs.push_back(sift.enqueue(f.w, f.h, f.px.data()));
+            for (size_t k = 0; k < frames.size(); k++) jobs.push_back(enqueue(k));
             nfeat = ndesc = 0;
             for (auto* j : jobs) {
                 if (!j) continue;
@@ -152,8 +236,9 @@ int main(int argc, char** argv)
                px * bench_steps / (ms * 1e-3) / 1e6, nfeat, ndesc);
         fflush(stdout);
     } else {
+        for (int rep = 0; rep < repeat; rep++)
         for (size_t k = 0; k < frames.size(); k++) {
-            SiftJob* j = sift.enqueue(frames[k].w, frames[k].h, frames[k].px.data());
+            SiftJob* j = enqueue(k);
             if (!j) { fprintf(stderr, "enqueue failed\n"); return 3; }
             popsift::FeaturesHost* fh = j->get();
             fprintf(stderr, "ref_dump: %s -> %d features, %d descriptors\n", inputs[k].c_str(),
@@ -161,6 +246,7 @@ int main(int argc, char** argv)
             if (!out.empty()) {
                 std::string fn = out;
                 if (frames.size() > 1) fn += "." + std::to_string(k);
+                if (repeat > 1) fn += ".r" + std::to_string(rep);
                 write_features(fn, fh);
             }
             delete fh; delete j;

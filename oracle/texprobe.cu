@@ -7,6 +7,8 @@
 //
 //   texprobe pairs  out.bin          all 256x256 (a,b) pairs at fraction 0.5 in x, in y,
 //                                    and a 2x2 sample; plus fraction 0 for all 256 values
+//   texprobe fpairs out.bin         float texture (ImageFloat, s_image.cu:262-291): 2x2 blends of a random
+//                                    64x64 float image at a 16x16 grid of fractions, and the fraction quantisation
 //   texprobe coords W H UP out.bin   random WxH u8 image; for rows 0..7 and the last 8,
 //                                    every X in [0,W0) and off in [-16,16]: tex2D at
 //                                    ((X+shift)/W0 -/+ off/W0, (Y+shift)/H0); writes image + samples
@@ -31,6 +33,27 @@ static cudaTextureObject_t make_tex(unsigned char* d, size_t pitch, int w, int h
     rd.res.pitch2D.devPtr = d;
     rd.res.pitch2D.desc.f = cudaChannelFormatKindUnsigned;
     rd.res.pitch2D.desc.x = 8;
+    rd.res.pitch2D.pitchInBytes = pitch;
+    rd.res.pitch2D.width = w;
+    rd.res.pitch2D.height = h;
+    cudaTextureObject_t t; CK(cudaCreateTextureObject(&t, &rd, &td, 0));
+    return t;
+}
+
+// float texture exactly as ImageFloat::createTexture configures it (s_image.cu:262-291):
+// normalized coordinates, bilinear, clamp, cudaReadModeElementType, one 32-bit float channel
+static cudaTextureObject_t make_tex_f32(float* d, size_t pitch, int w, int h)
+{
+    cudaTextureDesc td; memset(&td, 0, sizeof(td));
+    td.normalizedCoords = 1;
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+    td.readMode = cudaReadModeElementType;
+    td.filterMode = cudaFilterModeLinear;
+    cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
+    rd.resType = cudaResourceTypePitch2D;
+    rd.res.pitch2D.devPtr = d;
+    rd.res.pitch2D.desc.f = cudaChannelFormatKindFloat;
+    rd.res.pitch2D.desc.x = 32;
     rd.res.pitch2D.pitchInBytes = pitch;
     rd.res.pitch2D.width = w;
     rd.res.pitch2D.height = h;
@@ -116,6 +139,40 @@ int main(int argc, char** argv)
         run(t4, xy3);
         fclose(fp);
         printf("texprobe pairs: done\n");
+        return 0;
+    }
+    if (!strcmp(argv[1], "fpairs")) {
+        // 64x64 float image (power-of-two size: normalized -> texel coordinates are exact).  Left half of
+        // the values are k/256 (what popsift-demo --float-mode feeds, main.cpp:234), right half random
+        // 24-bit floats in [0,1).  Samples: for texel (i,j) in [8,40)x[8,40) and fractions (a,b)/256 with
+        // a,b in {0,17,...,255}: tex2D at ((i+0.5+a/256)/64, (j+0.5+b/256)/64); then the same texels at the
+        // finer fractions a/1024 (b = 0) to see how the fraction is quantised.
+        const int W = 64, H = 64;
+        std::vector<float> img(size_t(W) * H);
+        srand(12345);
+        for (int y = 0; y < H; y++) for (int x = 0; x < W; x++)
+            img[size_t(y) * W + x] = x < W / 2 ? float(rand() & 255) / 256.0f : float(rand() & 0xffffff) / 16777216.0f;
+        float* d; size_t pitch; CK(cudaMallocPitch((void**)&d, &pitch, W * sizeof(float), H));
+        CK(cudaMemcpy2D(d, pitch, img.data(), W * sizeof(float), W * sizeof(float), H, cudaMemcpyHostToDevice));
+        cudaTextureObject_t t = make_tex_f32(d, pitch, W, H);
+        std::vector<float2> q;
+        for (int j = 8; j < 40; j++) for (int i = 8; i < 40; i++)
+            for (int b = 0; b < 256; b += 17) for (int a = 0; a < 256; a += 17)
+                q.push_back(make_float2((i + 0.5f + a / 256.0f) / W, (j + 0.5f + b / 256.0f) / H));
+        const int n1 = int(q.size());
+        for (int j = 8; j < 12; j++) for (int i = 8; i < 40; i++)
+            for (int a = 0; a < 1024; a++) q.push_back(make_float2((i + 0.5f + a / 1024.0f) / W, (j + 0.5f) / H));
+        const int n2 = int(q.size()) - n1;
+        float2* dq; float* dout; CK(cudaMalloc(&dq, q.size() * sizeof(float2))); CK(cudaMalloc(&dout, q.size() * 4));
+        CK(cudaMemcpy(dq, q.data(), q.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        fetch<<<(int(q.size()) + 255) / 256, 256>>>(t, dq, dout, int(q.size()));
+        CK(cudaDeviceSynchronize());
+        std::vector<float> o(q.size()); CK(cudaMemcpy(o.data(), dout, q.size() * 4, cudaMemcpyDeviceToHost));
+        FILE* fp = fopen(argv[2], "wb");
+        int hdr[4] = { W, H, n1, n2 };
+        fwrite(hdr, 4, 4, fp); fwrite(img.data(), 4, img.size(), fp); fwrite(o.data(), 4, o.size(), fp);
+        fclose(fp);
+        printf("texprobe fpairs: %d + %d samples\n", n1, n2);
         return 0;
     }
     if (!strcmp(argv[1], "coords")) {

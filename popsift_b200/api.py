@@ -24,6 +24,7 @@ MODE = {"popsift": 0, "opencv": 1, "vlfeat": 2}
 NORM = {"rootsift": 0, "RootSift": 0, "classic": 1}
 GAUSS = {"vlfeat": 0, "vlfeat-hw-interpolated": 1, "relative": 1, "vlfeat-direct": 2, "opencv": 3, "fixed9": 4, "fixed15": 5}
 DESC = {"loop": 0, "iloop": 1, "grid": 2, "igrid": 3, "notile": 4}
+FILTER_SORT = {"random": 0, "down": 1, "up": 2}
 STAGES = ("h2d", "pyramid", "extrema", "orientation", "descriptors", "total")
 
 
@@ -32,7 +33,8 @@ class PsConfig(C.Structure):
                 ("threshold", C.c_float), ("upscale", C.c_float), ("initial_blur", C.c_float),
                 ("has_initial_blur", C.c_int32), ("sift_mode", C.c_int32), ("gauss_mode", C.c_int32),
                 ("desc_mode", C.c_int32), ("norm_mode", C.c_int32), ("norm_multi", C.c_int32),
-                ("max_extrema", C.c_int32)]
+                ("max_extrema", C.c_int32), ("scaling_mode", C.c_int32), ("filter_max_extrema", C.c_int32),
+                ("filter_grid_size", C.c_int32), ("filter_sort", C.c_int32)]
 
 
 class PsGaussTables(C.Structure):
@@ -120,8 +122,6 @@ class Config:
         load_library().ps_config_default(C.byref(self._c))
         self.verbose = False
         self._log_mode = 0
-        self._filter_max_extrema = -1
-        self._filter_grid_size = 2
         self._print_gauss_tables = False
 
     # public fields of the reference struct
@@ -179,8 +179,21 @@ class Config:
     def setThreshold(self, v): self._c.threshold = float(v)
     def setVerbose(self, on=True): self.verbose = bool(on)
     def setLogMode(self, mode=1): self._log_mode = int(mode)
-    def setFilterMaxExtrema(self, n): self._filter_max_extrema = int(n)
-    def setFilterGridSize(self, n): self._filter_grid_size = int(n)
+    def setFilterMaxExtrema(self, n): self._c.filter_max_extrema = int(n)
+    def setFilterGridSize(self, n): self._c.filter_grid_size = int(n)
+    def getFilterMaxExtrema(self): return self._c.filter_max_extrema
+    def getFilterGridSize(self): return self._c.filter_grid_size
+
+    def setFilterSorting(self, m):
+        if isinstance(m, str):
+            if m not in FILTER_SORT:
+                raise PopSiftError("filter sorting mode must be one of up, down or random")   # reference sift_conf.cu:141
+            m = FILTER_SORT[m]
+        self._c.filter_sort = int(m)
+
+    def setScalingMode(self, m=1):
+        """Config::ScaleDirect = 0, Config::ScaleDefault = 1 (reference sift_conf.h:75-80)"""
+        self._c.scaling_mode = int(m)
     def setPrintGaussTables(self): self._print_gauss_tables = True
 
     def setInitialBlur(self, blur):

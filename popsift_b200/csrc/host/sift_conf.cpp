@@ -96,7 +96,7 @@ const char* Config::getNormModeUsage()
     return "Choice of descriptor normalization modes. Options are: RootSift (L1-like, default), Classic (L2-like)";
 }
 
-bool  Config::getCanFilterExtrema() const { return false; }   // grid filter is out of this round's scope
+bool  Config::getCanFilterExtrema() const { return true; }    // reference: !POPSIFT_DISABLE_GRID_FILTER (sift_conf.cu:257-264)
 bool  Config::hasInitialBlur() const { return _assume_initial_blur; }
 float Config::getInitialBlur() const { return _initial_blur; }
 float Config::getPeakThreshold() const { return _threshold * 0.5f * 255.0f / levels; }
@@ -135,6 +135,11 @@ void Config::toC(ps_config& c) const
     c.norm_mode = (int)_normalization_mode;
     c.norm_multi = _normalization_multiplier;
     c.max_extrema = _max_extrema;
+    c.scaling_mode = _scaling_mode == ScaleDirect ? PS_SCALE_DIRECT : PS_SCALE_DEFAULT;
+    c.filter_max_extrema = _filter_max_extrema;
+    c.filter_grid_size = _filter_grid_size;
+    c.filter_sort = _grid_filter_mode == LargestScaleFirst ? PS_FILTER_LARGEST_FIRST
+                  : _grid_filter_mode == SmallestScaleFirst ? PS_FILTER_SMALLEST_FIRST : PS_FILTER_RANDOM;
 }
 
 } // namespace popsift

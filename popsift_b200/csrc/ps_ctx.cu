@@ -24,6 +24,7 @@ using namespace psb;
 namespace {
 
 thread_local std::string g_create_error;
+constexpr bool kGridFilterBuilt = false;
 
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -308,6 +309,21 @@ extern "C" ps_ctx* ps_create(int device, const ps_config* cfg, int max_w, int ma
     ctx->cfg.levels = std::max(2, cfg->levels);       // reference popsift.cpp:86
     ctx->levels = ctx->cfg.levels;
     if (ctx->cfg.max_extrema < 1) ctx->cfg.max_extrema = 100000;
+    // Options whose numerics are not implemented are refused, never silently replaced by the default path.
+    {
+        const char* why = nullptr;
+        if (ctx->cfg.desc_mode != PS_DESC_LOOP)
+            why = "ps_create: unsupported configuration: descriptor mode other than 'loop' (iloop/grid/igrid/notile are not implemented)";
+        else if (ctx->cfg.scaling_mode != PS_SCALE_DEFAULT)
+            why = "ps_create: unsupported configuration: direct scaling (Config::ScaleDirect) is not implemented";
+        else if (ctx->cfg.sift_mode != PS_MODE_POPSIFT && ctx->cfg.sift_mode != PS_MODE_OPENCV && ctx->cfg.sift_mode != PS_MODE_VLFEAT)
+            why = "ps_create: bad sift mode";
+        else if (ctx->cfg.filter_max_extrema > 0 && !kGridFilterBuilt)
+            why = "ps_create: unsupported configuration: the grid filter (--filter-max-extrema) is not implemented";
+        else if (ctx->cfg.filter_max_extrema > 0 && (ctx->cfg.filter_grid_size < 1 || ctx->cfg.filter_grid_size > PS_MAX_FILTER_GRID))
+            why = "ps_create: unsupported configuration: filter grid size out of range";
+        if (why) { delete ctx; return bail(why, cudaSuccess); }
+    }
     if (ps_gauss_tables_compute(&ctx->cfg, &ctx->tab) != PS_OK) {
         delete ctx;
         return bail("ps_create: unsupported configuration (sigma > 2.0, levels > 12 or gauss mode other than vlfeat)", cudaSuccess);

@@ -60,6 +60,10 @@ extern "C" void ps_config_default(ps_config* c)
     c->norm_mode = PS_NORM_ROOTSIFT;
     c->norm_multi = 0;
     c->max_extrema = 100000;
+    c->scaling_mode = PS_SCALE_DEFAULT;
+    c->filter_max_extrema = -1;
+    c->filter_grid_size = 2;
+    c->filter_sort = PS_FILTER_RANDOM;
 }
 
 extern "C" int ps_gauss_tables_compute(const ps_config* cfg, ps_gauss_tables* out)

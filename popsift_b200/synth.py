@@ -52,6 +52,50 @@ def make_frame(width: int, height: int, seed: int) -> np.ndarray:
     return np.clip(np.rint(img), 0, 255).astype(np.uint8)
 
 
+def affine_warp(img: np.ndarray, A: np.ndarray) -> np.ndarray:
+    """Warp a uint8 image with the 2x3 affine map A (source -> destination pixel coordinates): the
+    destination has the source's size, every destination pixel is the bilinear sample of the source
+    at A^-1 (x, y), clamp-to-edge.  Pure numpy float64, so the same bytes everywhere."""
+    h, w = img.shape
+    M = np.vstack([np.asarray(A, dtype=np.float64), [0.0, 0.0, 1.0]])
+    Mi = np.linalg.inv(M)
+    ys, xs = np.mgrid[0:h, 0:w].astype(np.float64)
+    sx = Mi[0, 0] * xs + Mi[0, 1] * ys + Mi[0, 2]
+    sy = Mi[1, 0] * xs + Mi[1, 1] * ys + Mi[1, 2]
+    sx = np.clip(sx, 0.0, w - 1.0)
+    sy = np.clip(sy, 0.0, h - 1.0)
+    x0 = np.floor(sx).astype(np.int64)
+    y0 = np.floor(sy).astype(np.int64)
+    x1 = np.minimum(x0 + 1, w - 1)
+    y1 = np.minimum(y0 + 1, h - 1)
+    fx, fy = sx - x0, sy - y0
+    f = img.astype(np.float64)
+    top = f[y0, x0] * (1.0 - fx) + f[y0, x1] * fx
+    bot = f[y1, x0] * (1.0 - fx) + f[y1, x1] * fx
+    return np.clip(np.rint(top * (1.0 - fy) + bot * fy), 0, 255).astype(np.uint8)
+
+
+def affine_set(width: int = 800, height: int = 640, seed: int = 31):
+    """Stand-in for the Oxford affine-covariant sets (BASELINE.json configs[4]; the PGMs are not
+    available offline): image 1 = make_frame(seed), images 2..6 = image 1 under known
+    affine maps about the image centre -- "boat"-like zoom + rotation (k = 1..3) and "graffiti"-like
+    viewpoint shear (k = 4, 5).  Returns [(image, A_k)] with A_1 = identity; A maps image-1 pixel
+    coordinates to image-k coordinates."""
+    base = make_frame(width, height, seed)
+    cx, cy = (width - 1) / 2.0, (height - 1) / 2.0
+    out = [(base, np.array([[1.0, 0.0, 0.0], [0.0, 1.0, 0.0]]))]
+    params = [(1.12, 10.0, 0.0), (1.30, 25.0, 0.0), (0.80, -40.0, 0.0), (1.0, 0.0, 0.25), (0.9, 15.0, 0.45)]
+    for scale, deg, shear in params:
+        th = np.deg2rad(deg)
+        R = scale * np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+        S = np.array([[1.0, shear], [0.0, 1.0 / (1.0 + shear)]])      # foreshortening along y with a shear in x
+        L = R @ S
+        t = np.array([cx, cy]) - L @ np.array([cx, cy])
+        A = np.hstack([L, t[:, None]])
+        out.append((affine_warp(base, A), A))
+    return out
+
+
 def write_pgm(path: str, img: np.ndarray) -> None:
     """Binary PGM (P5, maxval 255) as read by the reference's pgmread.cpp:180-197."""
     assert img.dtype == np.uint8 and img.ndim == 2
@@ -83,5 +127,9 @@ def read_pgm(path: str) -> np.ndarray:
 
 if __name__ == "__main__":
     import sys
-    w, h, seed, out = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]
-    write_pgm(out, make_frame(w, h, seed))
+    if sys.argv[1] == "affine":          # python -m popsift_b200.synth affine OUT_PREFIX  -> OUT_PREFIX1..6.pgm
+        for k, (im, _A) in enumerate(affine_set(), 1):
+            write_pgm("%s%d.pgm" % (sys.argv[2], k), im)
+    else:
+        w, h, seed, out = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]
+        write_pgm(out, make_frame(w, h, seed))

@@ -23,14 +23,14 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(L, name), "libpopsift_b200.so does not export %s" % name
     assert declared == set(api.EXPORTS)
-    assert L.ps_abi_version() == 1
+    assert L.ps_abi_version() == 2
 
 
 def test_struct_sizes_match_reference_layouts():
     # popsift::Feature is 72 bytes, Descriptor 512
     assert api.FEATURE_DTYPE.itemsize == 72
     assert api.EXTREMUM_DTYPE.itemsize == 44
-    assert C.sizeof(api.PsConfig) == 14 * 4
+    assert C.sizeof(api.PsConfig) == 18 * 4      # ABI 2: + scaling mode and the three grid-filter fields
 
 
 CFGS = [dict(), dict(downsampling=0), dict(levels=4), dict(sigma=1.2, levels=5), dict(initial_blur=0.0),
