@@ -135,8 +135,12 @@ const char* ps_last_error(const ps_ctx* ctx);
 
 /* replaces SiftJob::setImg/Image::load + Pyramid::step1 + step2
  * (reference popsift.cpp:293-344,432-437; s_image.cu:69-77; sift_pyramid.cu:227-240):
- * copies the host image (pageable or pinned) to the device and enqueues every kernel of the
- * hot path on the slot's stream.  Returns without waiting for the GPU. */
+ * copies the host image to the device and enqueues every kernel of the hot path on the slot's
+ * stream.  Returns without waiting for the GPU.
+ * Lifetime of `host_img`: a PAGEABLE buffer is copied before the call returns and may be reused or
+ * freed at once.  A PAGE-LOCKED buffer (ps_host_alloc, cudaHostAlloc, cudaHostRegister) is read by an
+ * asynchronous DMA: it must stay valid and unmodified until ps_wait_input(), ps_counts() or ps_sync()
+ * has returned for this slot. */
 int ps_submit_u8 (ps_ctx* ctx, int slot, const uint8_t* host_img, int w, int h);
 /* float images, value range [0,1) (reference popsift.h:62-69, s_image.cu:262-291) */
 int ps_submit_f32(ps_ctx* ctx, int slot, const float* host_img, int w, int h);
@@ -165,6 +169,9 @@ int   ps_dev_to_host(void* dst_host, const void* src_dev, size_t bytes);
  * buffers are staged through the slot's own pinned buffers (one extra host memcpy). */
 void* ps_host_alloc(size_t bytes);
 void  ps_host_free(void* p);
+/* waits until the input image of the slot's last ps_submit_* has been consumed (its host -> device copy
+ * is complete): after this a page-locked input buffer may be reused.  Does not wait for the kernels. */
+int ps_wait_input(ps_ctx* ctx, int slot);
 /* waits for the slot's stream without reading anything */
 int ps_sync(ps_ctx* ctx, int slot);
 

@@ -181,11 +181,56 @@ float orc_tex_u8(const uint8_t* img, int w, int h, float rx, float ry)
     return (float)r16 / 65535.0f;
 }
 
+/* What tex2D<float> returns for the reference's FLOAT input texture (ImageFloat, s_image.cu:262-291:
+ * pitch2D float, normalized coords, linear filter, clamp, cudaReadModeElementType).  MEASURED on a B200
+ * with `texprobe fpairs` (262 144 2x2 blends of a random float image at a 16x16 grid of fractions, and the
+ * fraction quantisation at 1/1024 steps; tests/golden/texture_float.npz):
+ *   - coordinate / 8-bit fraction as for the 8-bit texture (fraction rounded half-up to 1/256);
+ *   - the four weights are 8-BIT: w11 = round(ax*ay/256) (half-up), w10 = ax - w11, w01 = ay - w11,
+ *     w00 = 256 - ax - ay + w11  (they always sum to 256);
+ *   - result = (w00*t00 + w10*t10 + w01*t01 + w11*t11) / 256 evaluated EXACTLY and rounded once to float,
+ *     ties away from zero.  0 mismatches over the 262 144 samples.
+ * The sum is formed in long double (64-bit mantissa): exact for four 9-bit x 24-bit products whose
+ * exponents span less than 2^31, which covers image data. */
+float orc_tex_f32(const float* img, int w, int h, float rx, float ry)
+{
+    float fx = rx * (float)w - 0.5f;
+    float fy = ry * (float)h - 0.5f;
+    if (fx < -0.5f) fx = -0.5f;
+    if (fx > (float)w - 0.5f) fx = (float)w - 0.5f;
+    if (fy < -0.5f) fy = -0.5f;
+    if (fy > (float)h - 0.5f) fy = (float)h - 0.5f;
+    float flx = floorf(fx), fly = floorf(fy);
+    int ix = (int)flx, iy = (int)fly;
+    int ax = (int)floorf((fx - flx) * 256.0f + 0.5f);
+    int ay = (int)floorf((fy - fly) * 256.0f + 0.5f);
+    if (ax == 256) { ax = 0; ix += 1; }
+    if (ay == 256) { ay = 0; iy += 1; }
+    int x0 = clampi(ix, 0, w - 1), x1 = clampi(ix + 1, 0, w - 1);
+    int y0 = clampi(iy, 0, h - 1), y1 = clampi(iy + 1, 0, h - 1);
+    const int w11 = (ax * ay + 128) >> 8, w10 = ax - w11, w01 = ay - w11, w00 = 256 - ax - ay + w11;
+    const long double sum = (long double)w00 * img[(size_t)y0 * w + x0] + (long double)w10 * img[(size_t)y0 * w + x1]
+                          + (long double)w01 * img[(size_t)y1 * w + x0] + (long double)w11 * img[(size_t)y1 * w + x1];
+    const long double v = sum / 256.0L;
+    /* round to nearest float, ties away from zero */
+    const long double av = v < 0 ? -v : v;
+    float lo = (float)av;                       /* some rounding of av; make it the float just below or equal */
+    if ((long double)lo > av) lo = nextafterf(lo, 0.0f);
+    const float hi = nextafterf(lo, INFINITY);
+    const float r = (av - (long double)lo >= (long double)hi - av) ? hi : lo;
+    return v < 0 ? -r : r;
+}
+
 /* ----------------------------------------------------------------- pyramid */
 
 /* s_pyramid_build_ra.cu:17-55 (normalizedSource::horiz): octave 0, level 0,
- * rows, straight from the input texture; output x255. */
-static void level0_rows(const orc_ctx* c, const uint8_t* img, float* dst)
+ * rows, straight from the input texture; output x255.  `fimg` != NULL: float image (ImageFloat). */
+static inline float tex_any(const orc_ctx* c, const uint8_t* img, const float* fimg, float rx, float ry)
+{
+    return fimg ? orc_tex_f32(fimg, c->w, c->h, rx, ry) : orc_tex_u8(img, c->w, c->h, rx, ry);
+}
+
+static void level0_rows(const orc_ctx* c, const uint8_t* img, const float* fimg, float* dst)
 {
     const int W0 = c->W[0], H0 = c->H[0];
     const int span = c->tab.dd_span0;
@@ -201,11 +246,11 @@ static void level0_rows(const orc_ctx* c, const uint8_t* img, float* dst)
             float out = 0.0f;
             for (int off = span; off > 0; off--) {
                 const float offrel = (float)off / (float)W0;
-                const float v1 = orc_tex_u8(img, c->w, c->h, read_x - offrel, read_y);
-                const float v2 = orc_tex_u8(img, c->w, c->h, read_x + offrel, read_y);
+                const float v1 = tex_any(c, img, fimg, read_x - offrel, read_y);
+                const float v2 = tex_any(c, img, fimg, read_x + offrel, read_y);
                 out = fmaf(v1 + v2, g[off], out);
             }
-            out = fmaf(orc_tex_u8(img, c->w, c->h, read_x, read_y), g[0], out);
+            out = fmaf(tex_any(c, img, fimg, read_x, read_y), g[0], out);
             dst[(size_t)Y * W0 + X] = out * 255.0f;
         }
     }
@@ -249,7 +294,7 @@ static void cols_pass(const float* src, float* dst, int W, int H, const float* g
 }
 
 /* s_pyramid_build.cu:460-594, default arm :547-575, then make_dog :74-92 */
-static void build_pyramid(orc_ctx* c, const uint8_t* img)
+static void build_pyramid(orc_ctx* c, const uint8_t* img, const float* fimg)
 {
     const int L = c->nlev - 3;
     for (int o = 0; o < c->noct; o++) {
@@ -262,7 +307,7 @@ static void build_pyramid(orc_ctx* c, const uint8_t* img)
             const int span = c->tab.inc.span[l];
             if (l == 0) {
                 if (o == 0) {
-                    level0_rows(c, img, interm);
+                    level0_rows(c, img, fimg, interm);
                     cols_pass(interm, dstp, W, H, g, span);
                 } else {
                     /* s_pyramid_build.cu:50-71 get_by_2_pick_every_second from level L of o-1 */
@@ -698,9 +743,15 @@ void orc_destroy(orc_ctx* c)
     free(c->iext); free(c->ext); free(c->desc); free(c);
 }
 
-int orc_run_u8(orc_ctx* c, const uint8_t* img, int stages)
+static int run_stages(orc_ctx* c, const uint8_t* img, const float* fimg, int stages);
+
+int orc_run_u8(orc_ctx* c, const uint8_t* img, int stages) { return run_stages(c, img, NULL, stages); }
+/* float image, values in [0,1] (PopSift::FloatImages, popsift.h:62-69, s_image.cu:207-291) */
+int orc_run_f32(orc_ctx* c, const float* img, int stages) { return run_stages(c, NULL, img, stages); }
+
+static int run_stages(orc_ctx* c, const uint8_t* img, const float* fimg, int stages)
 {
-    if (stages & 1) build_pyramid(c, img);
+    if (stages & 1) build_pyramid(c, img, fimg);
     if (stages & 2) find_extrema(c);
     if (stages & 4) {
         free(c->ext);

@@ -74,6 +74,7 @@ orc_ctx* orc_create(const orc_config* c, int w, int h);
 void     orc_destroy(orc_ctx* ctx);
 /* stage bit mask: 1 pyramid, 2 extrema, 4 orientation, 8 descriptors */
 int      orc_run_u8(orc_ctx* ctx, const uint8_t* img, int stages);
+int      orc_run_f32(orc_ctx* ctx, const float* img, int stages);   /* PopSift::FloatImages */
 int      orc_num_octaves(const orc_ctx* ctx);
 int      orc_octave_dims(const orc_ctx* ctx, int octave, int32_t* W, int32_t* H);
 const float* orc_gauss_plane(const orc_ctx* ctx, int octave, int level);
@@ -86,6 +87,7 @@ int      orc_counts(const orc_ctx* ctx, int32_t* n_feat, int32_t* n_desc);
 int      orc_download(const orc_ctx* ctx, orc_feature* feat, float* desc128);
 /* stand-alone: normalised value the input texture returns (pins the texture model) */
 float    orc_tex_u8(const uint8_t* img, int w, int h, float rx, float ry);
+float    orc_tex_f32(const float* img, int w, int h, float rx, float ry);
 int      orc_set_threads(int n);
 
 #ifdef __cplusplus

@@ -53,7 +53,7 @@ EXPORTS = ["ps_abi_version", "ps_config_default", "ps_gauss_tables_compute", "ps
            "ps_last_error", "ps_submit_u8", "ps_submit_f32", "ps_submit_dev_u8", "ps_counts", "ps_download",
            "ps_sync", "ps_debug_plane", "ps_debug_extrema", "ps_slot_geometry", "ps_set_timing", "ps_stage_ms",
            "ps_launch_count", "ps_slot_stream", "ps_run_pyramid_only", "ps_run_level_only", "ps_host_alloc", "ps_host_free",
-           "ps_download_dev", "ps_dev_alloc", "ps_dev_free", "ps_dev_to_host"]
+           "ps_download_dev", "ps_dev_alloc", "ps_dev_free", "ps_dev_to_host", "ps_wait_input"]
 
 _lib = None
 
@@ -82,6 +82,7 @@ def load_library():
     L.ps_counts.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.ps_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.ps_sync.argtypes = [C.c_void_p, C.c_int]
+    L.ps_wait_input.argtypes = [C.c_void_p, C.c_int]
     L.ps_debug_plane.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     L.ps_debug_extrema.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     L.ps_slot_geometry.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
@@ -251,13 +252,54 @@ class _PinnedBlock:
             self.pf = self.pd = None
 
 
-class Features:
-    """popsift::FeaturesHost (reference src/popsift/features.h:71-102)."""
+class _Pool:
+    """Page-locked result buffers of one PopSift, recycled between images."""
 
-    def __init__(self, feat: np.ndarray, desc: np.ndarray, block=None, pool=None):
+    def __init__(self):
+        self.blocks, self.closed = [], False
+
+    def close(self):
+        self.closed = True
+        while self.blocks:
+            self.blocks.pop().free()
+
+
+class _Lease:
+    """Ties a page-locked block to the numpy arrays that view it: every array handed out has a ctypes
+    buffer as its base, the buffers hold this object, and only when the LAST array is gone does the block
+    go back to its pool (or is freed, if the PopSift it came from has been shut down meanwhile).  So
+    `d = ps.enqueue(...).get().desc` stays valid for as long as `d` lives."""
+
+    def __init__(self, pool: _Pool, block: _PinnedBlock):
+        self._pool, self._block = pool, block
+
+    def __del__(self):
+        blk, self._block = self._block, None
+        if blk is None:
+            return
+        if self._pool.closed:
+            blk.free()
+        else:
+            self._pool.blocks.append(blk)
+
+
+def _leased_views(pool: _Pool, blk: _PinnedBlock, nf: int, nd: int):
+    lease = _Lease(pool, blk)
+    fbuf = (C.c_uint8 * (nf * 72)).from_address(blk.pf)
+    dbuf = (C.c_float * (nd * 128)).from_address(blk.pd)
+    fbuf._lease = dbuf._lease = lease
+    feat = np.frombuffer(fbuf, dtype=FEATURE_DTYPE, count=nf) if nf else np.zeros(0, FEATURE_DTYPE)
+    desc = np.frombuffer(dbuf, dtype=np.float32, count=nd * 128).reshape(nd, 128) if nd else np.zeros((0, 128), np.float32)
+    return feat, desc
+
+
+class Features:
+    """popsift::FeaturesHost (reference src/popsift/features.h:71-102).  `feat` / `desc` view a page-locked
+    buffer that stays alive as long as any array that views it (see _Lease)."""
+
+    def __init__(self, feat: np.ndarray, desc: np.ndarray):
         self.feat = feat
         self.desc = desc
-        self._block, self._pool = block, pool
         base = desc.ctypes.data if len(desc) else 0
         idx = np.full((len(feat), 4), -1, dtype=np.int64)
         for k in range(4):
@@ -268,12 +310,6 @@ class Features:
     def getFeatureCount(self): return len(self.feat)
     def getDescriptorCount(self): return len(self.desc)
     size = getFeatureCount
-
-    def __del__(self):
-        # hand the page-locked buffer back for the next image (like deleting the reference's FeaturesHost)
-        if getattr(self, "_pool", None) is not None and self._block is not None:
-            self._pool.append(self._block)
-            self._block = None
 
     def keypoints(self):
         """rows (x, y, sigma, theta) per (feature, orientation) and the matching descriptors"""
@@ -379,7 +415,8 @@ class PopSift:
         self._max = (max_width, max_height)
         self._next = 0
         self._busy = [None] * slots
-        self._pool = []          # page-locked result buffers, recycled when a Features object dies
+        self._keep = [None] * slots      # the image each slot's DMA may still be reading (page-locked inputs)
+        self._pool = _Pool()     # page-locked result buffers, recycled when the arrays that view them die
         if max_width and max_height:
             self._create(max_width, max_height)
 
@@ -409,7 +446,7 @@ class PopSift:
         if self._busy[slot] is not None:
             self._busy[slot].getBase()   # FIFO: the slot's previous job completes first
         fn = self._lib.ps_submit_u8 if self._imode == self.ByteImages else self._lib.ps_submit_f32
-        self._keep = img
+        self._keep[slot] = img           # released when the slot's next image is submitted (its job has completed by then)
         self._check(fn(self._ctx, slot, img.ctypes.data, w, h))
         job = SiftJob(self, slot)
         self._busy[slot] = job
@@ -424,15 +461,17 @@ class PopSift:
             self._busy[slot] = None
             return fd
         blk = None
-        for i, b in enumerate(self._pool):
+        for i, b in enumerate(self._pool.blocks):
             if b.n_feat >= nf.value and b.n_desc >= nd.value:
-                blk = self._pool.pop(i)
+                blk = self._pool.blocks.pop(i)
                 break
         if blk is None:
             blk = _PinnedBlock(self._lib, int(nf.value * 1.25) + 1024, int(nd.value * 1.25) + 1024)
-        self._check(self._lib.ps_download(self._ctx, slot, blk.pf, blk.pd))
+        rc = self._lib.ps_download(self._ctx, slot, blk.pf, blk.pd)
+        feat, desc = _leased_views(self._pool, blk, nf.value, nd.value)     # from here on the lease owns the block
+        self._check(rc)
         self._busy[slot] = None
-        return Features(blk.feat[:nf.value], blk.desc[:nd.value], blk, self._pool)
+        return Features(feat, desc)
 
     # --- test / benchmark taps ------------------------------------------------------------
     def plane(self, slot, octave, level, dog=False) -> np.ndarray:
@@ -473,8 +512,7 @@ class PopSift:
         if self._ctx:
             self._lib.ps_destroy(self._ctx)
             self._ctx = None
-        while self._pool:
-            self._pool.pop().free()
+        self._pool.close()        # frees the idle blocks; blocks still viewed by arrays are freed when those die
 
     def __del__(self):
         try:

@@ -78,7 +78,10 @@ struct PopSift::Pipe
     bool                      stop = false;
     std::thread               worker;
 
+    // ctx and in_slot belong to the worker thread alone; what configure()/setSlots() need to know about them
+    // is published through `started` (set under `mu` before the first context is created)
     ps_ctx*                   ctx = nullptr;
+    bool                      started = false;
     int                       ctx_w = 0, ctx_h = 0;
     int                       slots = 4;
     std::vector<SiftJob*>     in_slot;
@@ -152,16 +155,25 @@ PopSift::PopSift(ImageMode imode, int device) : _pipe(new Pipe), _image_mode(imo
             if (!p->ctx || w > p->ctx_w || h > p->ctx_h) {
                 finish_all();
                 if (p->ctx) { ps_destroy(p->ctx); p->ctx = nullptr; }
-                if (!p->octaves_fixed) {
-                    // first image fixes the octave count (reference popsift.cpp:118-122)
-                    ps_config c; _config.toC(c);
-                    if (c.octaves < 0) { const int n = ps_geometry(&c, w, h, nullptr, nullptr); if (n > 0) _config.octaves = n; }
-                    p->octaves_fixed = true;
+                ps_config c;
+                int slots;
+                {
+                    // _config and slots are written by configure()/setSlots() on caller threads: read (and fix
+                    // the octave count) under the same mutex; from here on configure() refuses changes
+                    std::lock_guard<std::mutex> lk(p->mu);
+                    p->started = true;
+                    if (!p->octaves_fixed) {
+                        // first image fixes the octave count (reference popsift.cpp:118-122)
+                        _config.toC(c);
+                        if (c.octaves < 0) { const int n = ps_geometry(&c, w, h, nullptr, nullptr); if (n > 0) _config.octaves = n; }
+                        p->octaves_fixed = true;
+                    }
+                    _config.toC(c);
+                    slots = p->slots;
                 }
-                ps_config c; _config.toC(c);
                 p->ctx_w = std::max(w, p->ctx_w); p->ctx_h = std::max(h, p->ctx_h);
-                p->ctx = ps_create(_device, &c, p->ctx_w, p->ctx_h, p->slots);
-                p->in_slot.assign(p->slots, nullptr);
+                p->ctx = ps_create(_device, &c, p->ctx_w, p->ctx_h, slots);
+                p->in_slot.assign(slots, nullptr);
                 p->next_slot = 0;
                 if (!p->ctx) { fail_job(job, ps_last_error(nullptr)); p->ctx_w = p->ctx_h = 0; continue; }
             }
@@ -169,9 +181,16 @@ PopSift::PopSift(ImageMode imode, int device) : _pipe(new Pipe), _image_mode(imo
             finish(s);
             const int rc = job->isFloat() ? ps_submit_f32(p->ctx, s, reinterpret_cast<const float*>(job->pixels()), w, h)
                                           : ps_submit_u8(p->ctx, s, job->pixels(), w, h);
-            if (rc != PS_OK) { fail_job(job, ps_last_error(p->ctx)); continue; }
+            if (rc != PS_OK) {
+                // the copy out of the job's page-locked image may already be queued: let it finish before
+                // the caller can delete the job (and hand its block back to the pool)
+                const std::string msg = ps_last_error(p->ctx);
+                ps_sync(p->ctx, s);
+                fail_job(job, msg);
+                continue;
+            }
             p->in_slot[s] = job;
-            p->next_slot = (s + 1) % p->slots;
+            p->next_slot = (s + 1) % (int)p->in_slot.size();
         }
         finish_all();
         if (p->ctx) { ps_destroy(p->ctx); p->ctx = nullptr; }
@@ -194,7 +213,7 @@ bool PopSift::configure(const Config& config, bool /*force*/)
 {
     Pipe* p = _pipe.get();
     std::lock_guard<std::mutex> lk(p->mu);
-    if (p->ctx != nullptr) return false;     // like the reference: not after the pyramid exists
+    if (p->started) return false;            // like the reference: not after the pyramid exists
     _config = config;
     _config.levels = std::max(2, config.levels);
     return true;
@@ -204,7 +223,7 @@ void PopSift::setSlots(int n)
 {
     Pipe* p = _pipe.get();
     std::lock_guard<std::mutex> lk(p->mu);
-    if (p->ctx == nullptr && n >= 1 && n <= 64) p->slots = n;
+    if (!p->started && n >= 1 && n <= 64) p->slots = n;
 }
 
 void PopSift::uninit()

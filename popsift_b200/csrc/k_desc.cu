@@ -348,13 +348,13 @@ int launch_fix_feature_pointers(ps_feature* feat, ps_descriptor* desc, int n, cu
 int launch_descriptors(const PyramidView& pyr, const Consts& k, const ps_extremum* ext, const int* feat_to_ext,
                        ps_descriptor* desc, Counters* ct, cudaStream_t st)
 {
-    descriptor_kernel<<<148 * 16, DTHREADS, 0, st>>>(pyr, k, ext, feat_to_ext, desc, ct);
+    descriptor_kernel<<<sm_count() * 16, DTHREADS, 0, st>>>(pyr, k, ext, feat_to_ext, desc, ct);
     return 1;
 }
 
 int launch_prep_features(const Consts& k, const ps_extremum* ext, ps_feature* feat, const Counters* ct, cudaStream_t st)
 {
-    prep_features_kernel<<<148, 256, 0, st>>>(k, ext, feat, ct);
+    prep_features_kernel<<<sm_count(), 256, 0, st>>>(k, ext, feat, ct);
     return 1;
 }
 

@@ -432,7 +432,7 @@ int launch_scan(const PyramidView& pyr, const Consts& k, InitialExtremum* iext, 
 {
     if (pyr.cands_filled && !dense_choice()) {
         cand_prefix_kernel<<<1, 1024, 0, st>>>(pyr.cand_cnt_all, pyr.cand_regions, pyr.cand_prefix);
-        cand_extrema_kernel<MODE><<<148 * 4, kScanThreads, 0, st>>>(pyr, k, iext, ct);
+        cand_extrema_kernel<MODE><<<sm_count() * 4, kScanThreads, 0, st>>>(pyr, k, iext, ct);
         return 2;
     }
     int launches = 0;

@@ -6,8 +6,15 @@
 //   * no host round trip: the reference reads the extrema counters back to size its grid
 //     (s_orientation.cu:364-441); here a fixed grid of warps walks the device-side counters;
 //   * all octaves in one launch, 4 keypoints (warps) per CTA instead of 1;
-//   * lane-private histogram bins in shared memory, reduced in lane order -> deterministic
-//     (the reference's shared-memory atomicAdd order is not);
+//   * the histogram is accumulated exactly like the reference's: one warp per keypoint, lane i takes samples
+//     i, i+32, ... and adds its weight with a shared-memory float atomicAdd (ATOMS.CAST.SPIN loop), all
+//     in-circle lanes of an iteration together.  The order in which the hardware serialises lanes that hit
+//     the same bin is fixed for a converged warp (the reference reproduces its own output bit for bit on
+//     the 32 benchmark frames, tests/golden/bench32_parity.json), so the same instruction on the same
+//     lane <-> sample assignment gives the same float sums, hence the same peaks, the same number of
+//     orientations and the same angles.  (Round 1 summed lane-private bins in lane order: 925 of 453 753
+//     keypoints of the benchmark frames then differed in the last bits of an angle, and 7 in the NUMBER of
+//     orientations -- 522 535 vs 522 542 descriptors.);
 //   * top-4 selection by four warp arg-max rounds instead of a 64-wide bitonic sort.
 // Per-sample math is the reference's: hypotf/atan2f gradients of the data plane lpos,
 // weight = grad*expf(int(sq_dist)*__fdividef(-0.5, sigw^2)), bin = round(36*(theta+pi)/2pi),
@@ -20,7 +27,6 @@ namespace {
 
 constexpr int WARPS = 4;
 constexpr int kSlice = PS_ORI_SLICE;   // extrema per slice of the descriptor-index scan (ori_scatter_kernel)
-constexpr int HSTRIDE = 33;     // skewed so that the lane-order reduction is conflict-free
 __device__ const float kPi  = 3.14159265358979323846f;
 __device__ const float kPi2 = 2.0f * 3.14159265358979323846f;
 
@@ -42,7 +48,6 @@ __global__ void __launch_bounds__(WARPS * 32)
 orientation_kernel(PyramidView pyr, Consts k, const InitialExtremum* __restrict__ iext,
                    ps_extremum* __restrict__ ext, int* __restrict__ slice_sum, Counters* ct)
 {
-    __shared__ float hist[WARPS][kOriBins * HSTRIDE];
     __shared__ float sm_a[WARPS][kOriBins];
     __shared__ float sm_b[WARPS][kOriBins];
     __shared__ int   ps[kMaxOctaves + 1];
@@ -52,7 +57,6 @@ orientation_kernel(PyramidView pyr, Consts k, const InitialExtremum* __restrict_
     const int total = ps[pyr.num_octaves];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    float* H = hist[warp];
     float* A = sm_a[warp];
     float* B = sm_b[warp];
 
@@ -65,7 +69,8 @@ orientation_kernel(PyramidView pyr, Consts k, const InitialExtremum* __restrict_
         const int lvl = min(max(ie.lpos, 0), pyr.levels + 2);
         const float* pl = ov.gauss + (size_t)lvl * ov.plane;
 
-        for (int b = 0; b < kOriBins; ++b) H[b * HSTRIDE + lane] = 0.0f;
+        for (int b = lane; b < kOriBins; b += 32) A[b] = 0.0f;
+        __syncwarp();
 
         const float x = ie.xpos, y = ie.ypos, sig = ie.sigma;
         const float sigw = __fmul_rn(1.5f, sig);
@@ -80,36 +85,35 @@ orientation_kernel(PyramidView pyr, Consts k, const InitialExtremum* __restrict_
         const int hy = ymax - ymin + 1;
         const int loops = (wx > 0 && hy > 0) ? wx * hy : 0;
 
-        // Sample i of the window is row i / wx, column i % wx, and belongs to lane i % 32 (that assignment
-        // and the order within a lane fix the summation order of the histogram).  The lane walks its
-        // samples with a running (row, column) instead of a division per sample; the window lies inside
-        // [1, w-2] x [1, h-2], so the four neighbours need no clamping; hypotf / atan2f / expf only run
-        // for samples inside the circle.
+        // Sample i of the window is row i / wx, column i % wx, and belongs to lane i % 32, iteration i / 32
+        // (reference s_orientation.cu:117-163).  The lane walks its samples with a running (row, column)
+        // instead of a division per sample; the window lies inside [1, w-2] x [1, h-2], so the four
+        // neighbours need no clamping; hypotf / atan2f / expf only run for samples inside the circle.
+        // All lanes of an iteration reconverge before the atomic, like the reference's warp does.
         int xx = xmin + lane, yy = ymin;
         while (xx > xmax && wx > 0) { xx -= wx; ++yy; }
-        for (int i = lane; i < loops; i += 32) {
-            const float ddx = __fsub_rn((float)xx, x), ddy = __fsub_rn((float)yy, y);
-            const int sq_dist = (int)__fmaf_rn(ddx, ddx, __fmul_rn(ddy, ddy));
-            if (sq_dist <= sq_thres) {
-                const float* p = pl + (yy * ov.pitch + xx);         // a plane holds < 2^31 floats
-                const float gdx = __fsub_rn(__ldg(p + 1), __ldg(p - 1));
-                const float gdy = __fsub_rn(__ldg(p + ov.pitch), __ldg(p - ov.pitch));
-                const float grad = hypotf(gdx, gdy);
-                const float theta = atan2f(gdy, gdx);
-                const float weight = __fmul_rn(grad, expf(__fmul_rn((float)sq_dist, factor)));
-                int bidx = (int)roundf(__fdividef(__fmul_rn((float)kOriBins, __fadd_rn(theta, kPi)), kPi2));
-                if (bidx == kOriBins) bidx = 0;
-                if (bidx >= 0 && bidx < kOriBins) H[bidx * HSTRIDE + lane] += weight;
+        for (int i0 = 0; i0 < loops; i0 += 32) {
+            int bidx = -1;
+            float weight = 0.0f;
+            if (i0 + lane < loops) {
+                const float ddx = __fsub_rn((float)xx, x), ddy = __fsub_rn((float)yy, y);
+                const int sq_dist = (int)__fmaf_rn(ddx, ddx, __fmul_rn(ddy, ddy));
+                if (sq_dist <= sq_thres) {
+                    const float* p = pl + (yy * ov.pitch + xx);         // a plane holds < 2^31 floats
+                    const float gdx = __fsub_rn(__ldg(p + 1), __ldg(p - 1));
+                    const float gdy = __fsub_rn(__ldg(p + ov.pitch), __ldg(p - ov.pitch));
+                    const float grad = hypotf(gdx, gdy);
+                    const float theta = atan2f(gdy, gdx);
+                    weight = __fmul_rn(grad, expf(__fmul_rn((float)sq_dist, factor)));
+                    bidx = (int)roundf(__fdividef(__fmul_rn((float)kOriBins, __fadd_rn(theta, kPi)), kPi2));
+                    if (bidx == kOriBins) bidx = 0;
+                    if (bidx > kOriBins) bidx = -1;
+                }
+                xx += 32;
+                while (xx > xmax) { xx -= wx; ++yy; }
             }
-            xx += 32;
-            while (xx > xmax) { xx -= wx; ++yy; }
-        }
-        __syncwarp();
-        // reduce the 32 lane-private copies of each bin, lanes in order
-        for (int b = lane; b < kOriBins; b += 32) {
-            float s = 0.0f;
-            for (int l = 0; l < 32; ++l) s = __fadd_rn(s, H[b * HSTRIDE + l]);
-            A[b] = s;
+            __syncwarp();
+            if (bidx >= 0) atomicAdd(&A[bidx], weight);
         }
         __syncwarp();
         // 3 x (box3 ; box3), circular over 36 bins (reference s_orientation.cu:58-68,166-174)
@@ -266,8 +270,8 @@ ori_scatter_kernel(int num_octaves, Consts k, ps_extremum* __restrict__ ext, int
 int launch_orientation(const PyramidView& pyr, const Consts& k, const InitialExtremum* iext, ps_extremum* ext,
                        int* feat_to_ext, int* slice_sum, Counters* ct, cudaStream_t st)
 {
-    // fixed grid: 148 SMs x 8 resident CTAs of 4 warps; warps stride over the device-side count
-    orientation_kernel<<<148 * 8, WARPS * 32, 0, st>>>(pyr, k, iext, ext, slice_sum, ct);
+    // fixed grid: SMs x 8 resident CTAs of 4 warps; warps stride over the device-side count
+    orientation_kernel<<<sm_count() * 8, WARPS * 32, 0, st>>>(pyr, k, iext, ext, slice_sum, ct);
     ori_scatter_kernel<<<k.ext_capacity / kSlice + 1, kSlice, 0, st>>>(pyr.num_octaves, k, ext, feat_to_ext, slice_sum, ct);
     return 2;
 }

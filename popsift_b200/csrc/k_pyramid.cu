@@ -19,6 +19,7 @@
 // All intrinsics are explicit (__fmaf_rn/__fadd_rn/__fmul_rn) so nvcc cannot re-associate.
 #include "ps_internal.h"
 #include "k_pyramid.h"
+#include "k_texture.h"
 
 #include <cstdlib>
 
@@ -225,11 +226,8 @@ level0_kernel(const PIX* __restrict__ img, size_t img_pitch, int w, int h, float
             const unsigned r16 = (num * 257u + 32768u) >> 16;
             s[idx] = __fdiv_rn((float)r16, 65535.0f);
         } else {
-            // float images: fp32 blend with 8-bit weights (texture arithmetic not probed)
-            const float fx = (float)tx.a * (1.0f / 256.0f), fy = (float)ty.a * (1.0f / 256.0f);
-            const float top = __fmaf_rn(fx, (float)r0[tx.i1] - (float)r0[tx.i0], (float)r0[tx.i0]);
-            const float bot = __fmaf_rn(fx, (float)r1[tx.i1] - (float)r1[tx.i0], (float)r1[tx.i0]);
-            s[idx] = __fmaf_rn(fy, bot - top, top);
+            // float images: the float texture's 8-bit-weight blend, rounded once (k_texture.h)
+            s[idx] = tex_blend_f32((float)r0[tx.i0], (float)r0[tx.i1], (float)r1[tx.i0], (float)r1[tx.i1], tx.a, ty.a);
         }
     }
     __syncthreads();
@@ -250,11 +248,7 @@ constexpr size_t tile_smem() { return sizeof(float) * ((TH + 2 * R) * (TW + 2 * 
 template <int R>
 int run_blur(const OctaveView& o, int level, const Taps& t, float* next0, int next_pitch, cudaStream_t st)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(blur_level_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem<R>());
-        attr_set = true;
-    }
+    ensure_smem(blur_level_kernel<R>, tile_smem<R>());
     dim3 grid((o.w + TW - 1) / TW, (o.h + TH - 1) / TH);
     blur_level_kernel<R><<<grid, NT, tile_smem<R>(), st>>>(
         o.gauss + o.plane * (level - 1), o.gauss + o.plane * level, o.dog + o.plane * (level - 1),
@@ -266,11 +260,7 @@ template <int R, typename PIX>
 int run_level0(const PIX* img, size_t img_pitch, int w, int h, float shift, const OctaveView& o0,
                const Taps& dd, const Taps& inc0, cudaStream_t st)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(level0_kernel<R, PIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem<R>());
-        attr_set = true;
-    }
+    ensure_smem(level0_kernel<R, PIX>, tile_smem<R>());
     dim3 grid((o0.w + TW - 1) / TW, (o0.h + TH - 1) / TH);
     level0_kernel<R, PIX><<<grid, NT, tile_smem<R>(), st>>>(img, img_pitch, w, h, shift, o0.gauss, o0.w, o0.h,
                                                             o0.pitch, dd, inc0);
@@ -354,12 +344,9 @@ int launch_blur_level(const OctaveView& o, int level, const GaussRow& g, const O
         case 13: return run_blur<13>(o, level, t, next0, next_pitch, st);
         default: break;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    {
         const int Rm = PS_GAUSS_ALIGN - 2;
-        cudaFuncSetAttribute(blur_level_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(sizeof(float) * ((TH + 2 * Rm) * (TW + 2 * Rm) + (TH + 2 * Rm) * TW)));
-        attr_set = true;
+        ensure_smem(blur_level_generic_kernel, sizeof(float) * ((TH + 2 * Rm) * (TW + 2 * Rm) + (TH + 2 * Rm) * TW));
     }
     const size_t sm = sizeof(float) * ((TH + 2 * R) * (TW + 2 * R) + (TH + 2 * R) * TW);
     dim3 grid((o.w + TW - 1) / TW, (o.h + TH - 1) / TH);

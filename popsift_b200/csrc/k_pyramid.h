@@ -2,7 +2,29 @@
 #pragma once
 #include "ps_internal.h"
 
+#include <mutex>
+#include <set>
+#include <utility>
+
 namespace psb {
+
+// opt in to > 48 KB dynamic shared memory once per (kernel, device); safe from any thread
+template <typename K>
+inline void ensure_smem(K kernel, size_t bytes, bool prefer_max_carveout = false)
+{
+    static std::mutex mu;
+    static std::set<std::pair<const void*, int>> done;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const std::pair<const void*, int> key(reinterpret_cast<const void*>(kernel), dev);
+    std::lock_guard<std::mutex> g(mu);
+    if (done.insert(key).second) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (prefer_max_carveout)
+            cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
+}
+
 
 struct alignas(16) Taps { float g[PS_GAUSS_ALIGN]; };   // one half-kernel, passed by value (constant bank)
 

@@ -20,6 +20,7 @@
 // reference's sm_100 SASS); results are bit-identical to the tile kernels and to the reference.
 #include "ps_internal.h"
 #include "k_pyramid.h"
+#include "k_texture.h"
 #include "k_partition.h"
 
 #include <cstdint>
@@ -429,10 +430,7 @@ __device__ __forceinline__ void level0_body(float* __restrict__ smem, AxisTap* _
                 const unsigned num = wx0 * wy0 * t00 + wx1 * wy0 * t10 + wx0 * wy1 * t01 + wx1 * wy1 * t11;
                 v = unorm16_to_float((num * 257u + 32768u) >> 16);
             } else {
-                const float fx = (float)tx.a * (1.0f / 256.0f), fy = (float)ty.a * (1.0f / 256.0f);
-                const float top = __fmaf_rn(fx, (float)r0[tx.i1] - (float)r0[tx.i0], (float)r0[tx.i0]);
-                const float bot = __fmaf_rn(fx, (float)r1[tx.i1] - (float)r1[tx.i0], (float)r1[tx.i0]);
-                v = __fmaf_rn(fy, bot - top, top);
+                v = tex_blend_f32((float)r0[tx.i0], (float)r0[tx.i1], (float)r1[tx.i0], (float)r1[tx.i1], tx.a, ty.a);
             }
             Scur[j * G::SWP + i] = v;
         }
@@ -589,40 +587,23 @@ bool uniform_choice()
     return v;
 }
 
-Partition make_partition(int W, int H, int slots = 592)     // one wave: 148 SMs x 4 resident CTAs
+Partition make_partition(int W, int H, int slots = 0)     // one wave: SMs x 4 resident CTAs (592 on B200)
 {
-    return psb::make_partition(W, H, TW, Q, slots, uniform_choice());
+    return psb::make_partition(W, H, TW, Q, slots > 0 ? slots : 4 * sm_count(), uniform_choice());
 }
 
 // resident CTAs of the exact-2x level-0 kernel (POPSIFT_B200_L0SLOTS overrides, A/B timing)
 int level0_slots()
 {
-    static const int v = [] { const char* e = getenv("POPSIFT_B200_L0SLOTS"); const int n = e ? atoi(e) : 0; return n > 0 ? n : 148 * 6; }();
-    return v;
-}
-
-// opt in to > 48 KB dynamic shared memory once per (kernel, device)
-template <typename K>
-void ensure_smem(K kernel, size_t bytes)
-{
-    static std::mutex mu;
-    static std::set<std::pair<const void*, int>> done;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    const std::pair<const void*, int> key(reinterpret_cast<const void*>(kernel), dev);
-    std::lock_guard<std::mutex> g(mu);
-    if (done.insert(key).second)
-        {
-        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        }
+    static const int v = [] { const char* e = getenv("POPSIFT_B200_L0SLOTS"); const int n = e ? atoi(e) : 0; return n; }();
+    return v > 0 ? v : 6 * sm_count();
 }
 
 template <int R, bool NEXT, bool CAND>
 void launch_march(const Partition& part, const float* src, float* dst, float* dog, float* next0, const OctaveView& o,
                   int next_pitch, const Taps& t, const CandSink& sink, cudaStream_t st)
 {
-    ensure_smem(march_level_kernel<R, NEXT, CAND>, Geo<R>::smem);
+    ensure_smem(march_level_kernel<R, NEXT, CAND>, Geo<R>::smem, true);
     march_level_kernel<R, NEXT, CAND><<<part.B, NT, Geo<R>::smem, st>>>(src, dst, dog, next0, o.w, o.h, o.pitch, next_pitch,
                                                                         part, t, sink);
 }
@@ -652,14 +633,14 @@ int run_march0(const PIX* img, size_t img_pitch, int w, int h, float shift, cons
                         (reinterpret_cast<uintptr_t>(img) & 3) == 0;
         if (x2) {
             const Partition part = make_partition(o0.w, o0.h, level0_slots());
-            ensure_smem(march_level0x2_kernel<R>, Geo0<R>::smem);
+            ensure_smem(march_level0x2_kernel<R>, Geo0<R>::smem, true);
             march_level0x2_kernel<R><<<part.B, NT, Geo0<R>::smem, st>>>(img, img_pitch, w, h, o0.gauss, o0.w, o0.h, o0.pitch,
                                                                         part, dd, inc0);
             return 1;
         }
     }
     const Partition part = make_partition(o0.w, o0.h);
-    ensure_smem(march_level0_kernel<R, PIX>, Geo<R>::smem);
+    ensure_smem(march_level0_kernel<R, PIX>, Geo<R>::smem, true);
     march_level0_kernel<R, PIX><<<part.B, NT, Geo<R>::smem, st>>>(img, img_pitch, w, h, shift, o0.gauss, o0.w, o0.h,
                                                                   o0.pitch, part, dd, inc0);
     return 1;
@@ -670,7 +651,7 @@ int run_march0(const PIX* img, size_t img_pitch, int w, int h, float shift, cons
 bool march_supports(int R) { return R >= 3 && R <= 16; }
 int march_cand_blocks(int w, int h) { return make_partition(w, h).B; }
 int march_cand_region(int w, int h) { return cand_region_cap(make_partition(w, h), TW, Q); }
-long long march_cand_entry_bound(int w, int h) { return cand_entry_bound(w, h, TW, Q, 592); }
+long long march_cand_entry_bound(int w, int h) { return cand_entry_bound(w, h, TW, Q, 4 * sm_count()); }
 
 int march_blur_level(const OctaveView& o, int level, const Taps& t, int R, float* next0, int next_pitch,
                      const CandSink* sink, cudaStream_t st)

@@ -1,0 +1,30 @@
+// What the B200 texture unit returns for the reference's input textures, as device functions.
+// Measured with oracle/texprobe.cu, restated in oracle/sift_oracle.c (orc_tex_u8 / orc_tex_f32) and pinned
+// by tests/golden/texture_pairs.npz, tests/golden/texture_float.npz.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace psb {
+
+// FLOAT input texture (reference ImageFloat, s_image.cu:262-291: linear filter, cudaReadModeElementType).
+// ax, ay = the 8-bit fractions (0..255).  The hardware blends with 8-BIT weights
+//     w11 = round(ax*ay / 256), w10 = ax - w11, w01 = ay - w11, w00 = 256 - ax - ay + w11
+// and returns (w00*t00 + w10*t10 + w01*t01 + w11*t11) / 256 rounded ONCE to float, ties away from zero
+// (0 mismatches over 393 216 probed samples).  The sum is formed in double: every product is exact, and
+// the sum is exact whenever the four terms span fewer than ~20 binades -- image data does.
+__device__ __forceinline__ float tex_blend_f32(float t00, float t10, float t01, float t11, int ax, int ay)
+{
+    const int w11 = (ax * ay + 128) >> 8, w10 = ax - w11, w01 = ay - w11, w00 = 256 - ax - ay + w11;
+    double s = __dmul_rn((double)w00, (double)t00);
+    s = __fma_rn((double)w10, (double)t10, s);
+    s = __fma_rn((double)w01, (double)t01, s);
+    s = __fma_rn((double)w11, (double)t11, s);
+    s = __dmul_rn(s, 1.0 / 256.0);
+    const double a = fabs(s);
+    const float lo = __double2float_rz(a);                                  // largest float <= a
+    const float hi = __uint_as_float(__float_as_uint(lo) + 1u);             // next float up (a is finite, >= 0)
+    const float r = (__dsub_rn(a, (double)lo) >= __dsub_rn((double)hi, a)) ? hi : lo;
+    return s < 0.0 ? -r : r;
+}
+
+} // namespace psb

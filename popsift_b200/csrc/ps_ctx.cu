@@ -56,6 +56,8 @@ struct Slot {
     ps_descriptor* h_desc = nullptr;  size_t h_desc_cap = 0;
     cudaEvent_t ev[PS_NUM_STAGES + 1] = {};
     cudaEvent_t done = nullptr;
+    cudaEvent_t in_done = nullptr;   // recorded after the host -> device copy of the slot's input image
+    bool in_pending = false;         // in_done has been recorded at least once
     bool submitted = false;
     bool is_float = false;
     int w = 0, h = 0;
@@ -233,6 +235,21 @@ int run_pyramid(ps_ctx* ctx, Slot& s)
 
 } // namespace
 
+int psb::sm_count()
+{
+    static std::mutex mu;
+    static int cached[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return 148; }
+    std::lock_guard<std::mutex> g(mu);
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) { cudaGetLastError(); n = 148; }
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
 static int submit_common(ps_ctx* ctx, Slot& s)
 {
     const bool tm = ctx->timing;
@@ -282,6 +299,7 @@ extern "C" void ps_destroy(ps_ctx* ctx)
         cudaFreeHost(s.h_feat); cudaFreeHost(s.h_desc);
         for (auto& e : s.ev) if (e) cudaEventDestroy(e);
         if (s.done) cudaEventDestroy(s.done);
+        if (s.in_done) cudaEventDestroy(s.in_done);
         for (auto& e : s.ev_fork) if (e) cudaEventDestroy(e);
         for (auto& e : s.ev_join) if (e) cudaEventDestroy(e);
         for (auto& st : s.side) if (st) cudaStreamDestroy(st);
@@ -377,6 +395,7 @@ extern "C" ps_ctx* ps_create(int device, const ps_config* cfg, int max_w, int ma
         PS_TRY(cudaHostAlloc(&s.h_ct, sizeof(Counters), cudaHostAllocDefault));
         for (auto& ev : s.ev) PS_TRY(cudaEventCreate(&ev));
         PS_TRY(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        PS_TRY(cudaEventCreateWithFlags(&s.in_done, cudaEventDisableTiming));
 #undef PS_TRY
     }
     return ctx;
@@ -386,13 +405,16 @@ static bool is_pinned(const void* p);
 
 static int stage_input(ps_ctx* ctx, Slot& s, const void* host_img, size_t bytes)
 {
-    // Pinned caller memory goes straight to the device; pageable memory is staged through the
-    // slot's pinned buffer (the reference always stages: popsift.cpp:392-395 + s_image.cu:75).
+    // Pinned caller memory goes straight to the device (the caller keeps it valid until ps_wait_input /
+    // ps_counts / ps_sync returns for this slot); pageable memory is staged through the slot's pinned
+    // buffer (the reference always stages: popsift.cpp:392-395 + s_image.cu:75) and may be reused as soon
+    // as the call returns.
     const bool pinned = is_pinned(host_img);
     const void* src = host_img;
     if (!pinned) {
-        // the staging buffer may still be in flight for the previous image of this slot
-        PS_CUDA(ctx, cudaStreamSynchronize(s.stream));
+        // the staging buffer is free once the PREVIOUS image's copy has left it -- the submitting thread
+        // never waits for the previous image's kernels
+        if (s.in_pending) PS_CUDA(ctx, cudaEventSynchronize(s.in_done));
         std::memcpy(s.h_img, host_img, bytes);
         src = s.h_img;
     }
@@ -401,6 +423,8 @@ static int stage_input(ps_ctx* ctx, Slot& s, const void* host_img, size_t bytes)
                                        cudaMemcpyHostToDevice, s.stream));
     else
         PS_CUDA(ctx, cudaMemcpyAsync(s.d_img, src, bytes, cudaMemcpyHostToDevice, s.stream));
+    PS_CUDA(ctx, cudaEventRecord(s.in_done, s.stream));
+    s.in_pending = true;
     return PS_OK;
 }
 
@@ -447,6 +471,15 @@ extern "C" int ps_submit_dev_u8(ps_ctx* ctx, int slot, const uint8_t* dev_img, s
     if (ctx->timing) PS_CUDA(ctx, cudaEventRecord(s->ev[0], s->stream));
     PS_CUDA(ctx, cudaMemcpy2DAsync(s->d_img, u8_pitch(w), dev_img, pitch, (size_t)w, (size_t)h, cudaMemcpyDeviceToDevice, s->stream));
     return submit_common(ctx, *s);
+}
+
+extern "C" int ps_wait_input(ps_ctx* ctx, int slot)
+{
+    Slot* s = get_slot(ctx, slot);
+    if (!s) return PS_ERR_ARG;
+    PS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (s->in_pending) PS_CUDA(ctx, cudaEventSynchronize(s->in_done));
+    return PS_OK;
 }
 
 extern "C" int ps_sync(ps_ctx* ctx, int slot)

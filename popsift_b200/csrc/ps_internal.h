@@ -96,6 +96,10 @@ inline float extrema_threshold(const Consts& k)
     return k.sift_mode == PS_MODE_OPENCV ? floorf(k.threshold) : 1.6f * k.threshold;
 }
 
+// multiprocessors of the CURRENT device (cudaDeviceProp::multiProcessorCount, cached per device; 148 on B200):
+// every fixed grid and the one-wave partition of the pyramid kernels are sized from it
+int sm_count();
+
 // ---- launchers (defined in the k_*.cu files); all asynchronous on `st`, return #kernels launched
 
 struct GaussRow { float tap[PS_GAUSS_ALIGN]; int span; };

@@ -59,6 +59,9 @@ def lib():
         L.orc_create.argtypes = [C.POINTER(OrcConfig), C.c_int, C.c_int]
         L.orc_destroy.argtypes = [C.c_void_p]
         L.orc_run_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_run_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_tex_f32.restype = C.c_float
+        L.orc_tex_f32.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float]
         L.orc_num_octaves.argtypes = [C.c_void_p]
         L.orc_octave_dims.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.orc_gauss_plane.restype = C.POINTER(C.c_float)
@@ -115,8 +118,13 @@ class Oracle:
         self.close()
 
     def run(self, img: np.ndarray, stages: int = 15) -> None:
-        img = np.ascontiguousarray(img, dtype=np.uint8)
+        """uint8 image -> ByteImages path; float32 image (values in [0,1]) -> FloatImages path"""
         assert img.shape == (self.h, self.w)
+        if img.dtype == np.float32:
+            img = np.ascontiguousarray(img)
+            lib().orc_run_f32(self.ctx, img.ctypes.data, stages)
+            return
+        img = np.ascontiguousarray(img, dtype=np.uint8)
         lib().orc_run_u8(self.ctx, img.ctypes.data, stages)
 
     @property
@@ -173,8 +181,9 @@ REF_FEATURE_DTYPE = np.dtype([("octave", "<i4"), ("x", "<f4"), ("y", "<f4"), ("s
                               ("num_ori", "<i4"), ("ori", "<f4", (4,)), ("desc_idx", "<i4", (4,))])
 
 
-def read_ref_features(path: str):
-    """features.bin written by oracle/ref_driver.cpp -> (feat[REF_FEATURE_DTYPE], desc[n,128])."""
+def read_ref_features(path: str, with_rev: bool = False):
+    """features.bin written by oracle/ref_driver.cpp -> (feat[REF_FEATURE_DTYPE], desc[n,128]);
+    with_rev: also the descriptor -> feature reverse map that --match runs append ("PSR1")."""
     with open(path, "rb") as f:
         data = f.read()
     assert data[:4] == b"PSF1"
@@ -182,7 +191,12 @@ def read_ref_features(path: str):
     feat = np.frombuffer(data, dtype=REF_FEATURE_DTYPE, count=nf, offset=12).copy()
     off = 12 + nf * REF_FEATURE_DTYPE.itemsize
     desc = np.frombuffer(data, dtype="<f4", count=nd * 128, offset=off).reshape(nd, 128).copy()
-    return feat, desc
+    if not with_rev:
+        return feat, desc
+    off += nd * 512
+    assert data[off:off + 4] == b"PSR1"
+    rev = np.frombuffer(data, dtype="<i4", count=nd, offset=off + 4).copy()
+    return feat, desc, rev
 
 
 def flatten(feat, desc):

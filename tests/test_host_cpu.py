@@ -271,3 +271,41 @@ def test_match_oracle_on_constructed_descriptors():
     # the matrix-product form agrees on this well-separated set
     assert np.array_equal(mo.match(left, right, exact_order=False)[:, [0, 2]], m[:, [0, 2]])
     assert mo.match(left, right[:0]).tolist() == [[0, 0, 0]] * 6
+
+
+def test_result_arrays_keep_their_page_locked_block_alive():
+    """`d = job.get().desc` must stay valid after the Features object is gone.  The arrays' base
+    objects hold a lease on the block; it returns to the pool (or is freed after uninit) only when the last
+    view dies.  Checked with a stand-in allocator, no GPU needed."""
+    import gc
+
+    class FakeLib:
+        def __init__(self):
+            self.live, self.bufs = set(), {}
+
+        def ps_host_alloc(self, n):
+            b = (C.c_uint8 * max(n, 1))()
+            a = C.addressof(b)
+            self.live.add(a); self.bufs[a] = b
+            return a
+
+        def ps_host_free(self, p):
+            self.live.discard(p)
+
+    L = FakeLib()
+    pool = api._Pool()
+    f, d = api._leased_views(pool, api._PinnedBlock(L, 10, 10), 3, 2)
+    row = d[1]
+    del f, d
+    gc.collect()
+    assert pool.blocks == [] and len(L.live) == 2          # still leased: a view is alive
+    row[:] = 1.0                                           # and writable memory
+    del row
+    gc.collect()
+    assert len(pool.blocks) == 1                           # recycled
+    f, d = api._leased_views(pool, pool.blocks.pop(), 0, 0)
+    pool.close()                                           # PopSift.uninit() while a result is still referenced
+    assert len(L.live) == 2
+    del f, d
+    gc.collect()
+    assert not L.live                                      # freed when the last view died
