@@ -12,16 +12,21 @@ no collective ("weak" scaling: per-GPU batch fixed).
 Printed JSON (rank 0, one line):
   value     Mpixels/s of input pixels, whole job, inputs resident in HBM before the timed region
             (ps_submit_dev_u8 -> ps_counts -> ps_download: all kernels + result download).
-  e2e       same metric through the public API (PopSift.enqueue -> SiftJob.get) from pinned HOST
-            buffers: host->device copy of every frame and device->host copy of every result inside
-            the timed region.
+  e2e       same metric through the C++ drop-in API (PopSift::enqueue -> SiftJob::get, popsift_b200/bin/api_bench)
+            from PAGEABLE host frames, driven exactly like the reference arm drives the reference
+            (oracle/ref_driver.cpp --bench): host->device copy of every frame and device->host copy of every
+            result inside the timed region.  `e2e.pinned_ctypes` keeps the round-1 number (Python mirror,
+            page-locked frames) for comparison.
   roofline  pyramid stage: algorithmic bytes per frame (68 B per octave-pixel) / CUDA-event
             time of the pyramid launches of one frame, against the measured HBM peak
             (MEASURED_PEAKS.json); `dominant_kernel` = the octave-0 fused blur+DoG launches alone.
   cpu_baseline  the CPU oracle port (oracle/sift_oracle.c, OpenMP) timed on the first four frames of the workload;
   opencv_cpu    cv2.SIFT on the same frame, all host cores (the CPU baseline north_star names).
 `--impl reference` times the UNMODIFIED reference PopSift (oracle/_ref, CUDA, built from
-/root/reference) on the same frames through its own public API (host buffers in, host features out).
+/root/reference) on the same frames through its own public API (host buffers in, host features out); with
+--gpus N rank 0 starts one reference process per GPU (each on its own per-GPU batch: weak scaling, like our arm) and reports the aggregate.
+Every rank (and every child process it starts) is bound to the CPUs of its GPU's NUMA node before any
+page-locked allocation.
 """
 from __future__ import annotations
 
@@ -47,6 +52,81 @@ FRAMES_PER_STEP = 32     # long enough that the 4-slot pipeline spends most of a
 SLOTS = int(os.environ.get("POPSIFT_BENCH_SLOTS", "4"))     # images in flight per GPU
 BYTES_PER_OCTAVE_PIXEL = 4 * (3 * LEVELS + 8)     # 68 B
 METRIC = "Mpixels/s SIFT extract @ 3840x2160 gray"
+WORKLOAD = ("3840x2160 u8 gray, octaves=5 levels=3, default Config (upscale 2x: octave 0 = 7680x4320), RootSift, desc loop; "
+            "%d frames per step per GPU" % FRAMES_PER_STEP)
+
+
+def gpu_numa_cpus(index):
+    """CPUs of the NUMA node GPU `index` hangs off (sysfs), or None when that cannot be determined."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        dom, rest = bus.split(":", 1)
+        node = int(open("/sys/bus/pci/devices/%s:%s/numa_node" % (dom[-4:], rest)).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        return sorted(cpus) or None
+    except Exception:
+        return None
+
+
+def bind_to_gpu_node(index):
+    """pin this process (its threads and children inherit it) to the GPU's NUMA node; returns what was done"""
+    cpus = gpu_numa_cpus(index)
+    if not cpus:
+        return {"bound": False}
+    try:
+        os.sched_setaffinity(0, cpus)
+        return {"bound": True, "cpus": len(cpus), "first_cpu": cpus[0]}
+    except Exception as e:
+        return {"bound": False, "error": str(e)}
+
+
+def write_frames(frames, td):
+    from popsift_b200.synth import write_pgm
+    paths = []
+    for i, f in enumerate(frames):
+        p = os.path.join(td, "f%d.pgm" % i)
+        write_pgm(p, f)
+        paths.append(p)
+    return paths
+
+
+def run_children(cmds, barrier=None, cpus=None, timeout=1500):
+    """start one benchmark child per command; wait until every child has printed `ready` (warm-up done), release
+    them together through their --go-file, return their JSON lines"""
+    import tempfile as _tf
+    procs = []
+    for i, (cmd, go) in enumerate(cmds):
+        pre = None
+        if cpus and cpus[i]:
+            c = cpus[i]
+            pre = (lambda c=c: os.sched_setaffinity(0, c))
+        procs.append(subprocess.Popen(cmd + ["--go-file", go], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, preexec_fn=pre))
+    for pr in procs:
+        ln = pr.stdout.readline()
+        if ln.strip() != "ready":
+            err = pr.stderr.read()[-300:]
+            for q in procs:
+                q.kill()
+            raise RuntimeError("benchmark child failed before the timed region: %s %s" % (ln.strip(), err))
+    if barrier:
+        barrier()
+    for _cmd, go in cmds:
+        open(go, "w").close()
+    outs = []
+    for pr in procs:
+        out, err = pr.communicate(timeout=timeout)
+        line = [l for l in out.splitlines() if l.startswith("{")]
+        if pr.returncode != 0 or not line:
+            raise RuntimeError("benchmark child failed: %s" % err.strip()[-300:])
+        outs.append(json.loads(line[-1]))
+    return outs
 
 
 def synth_frames(n, rank):
@@ -257,7 +337,7 @@ def run_ours(args, rank, world, local_rank):
     del dev_frames, flush
     torch.cuda.empty_cache()
 
-    # ---------------- end-to-end path through the public API (host buffers) ----------------
+    # ---------------- end-to-end path, Python mirror + page-locked frames (round-1 definition, kept as an extra) ----
     pinned = [torch.from_numpy(f).pin_memory().numpy() for f in frames]
     ps = api.PopSift(cfg, device=local_rank, max_width=W, max_height=H, slots=SLOTS)
 
@@ -274,16 +354,29 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(args.warmup):
         step_e2e()
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
     t0 = time.perf_counter()
-    ecounts = (0, 0)
-    for _ in range(args.steps):
-        ecounts = step_e2e()
-    e1.record()
+    for _ in range(max(2, args.steps // 2)):
+        step_e2e()
     barrier()
-    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+    pinned_wall_ms = (time.perf_counter() - t0) * 1e3 / max(2, args.steps // 2)
     ps.uninit()
+    del pinned
+
+    # ---------------- end-to-end path: the C++ drop-in API from pageable frames (the headline e2e) ----------------
+    exe = os.path.join(ROOT, "popsift_b200", "bin", "api_bench")
+    if not os.path.exists(exe):
+        raise SystemExit("bench.py: %s is missing - build the product first (python -m popsift_b200.build)" % exe)
+    with tempfile.TemporaryDirectory() as td:
+        cmd = [exe, "--octaves", str(OCTAVES), "--levels", str(LEVELS), "--device", str(local_rank), "--slots", str(SLOTS),
+               "--bench", str(args.steps), str(args.warmup)]
+        for pth in write_frames(frames, td):
+            cmd += ["-i", pth]
+        torch.cuda.synchronize()
+        j = run_children([(cmd, os.path.join(td, "go"))], barrier=barrier)[0]
+    e2e_wall_ms = j["total_ms"]
+    ecounts = (j["features_last_step"], j["descriptors_last_step"])
+    if ecounts != counts:
+        raise SystemExit("bench.py: the C++ API leg found %s features/descriptors, the C-ABI leg %s" % (ecounts, counts))
 
     # whole-job aggregate: SUM of pixels, MAX over ranks of the elapsed time (device-timed for `value`;
     # wall clock for e2e, which includes host work by definition)
@@ -291,6 +384,7 @@ def run_ours(args, rank, world, local_rank):
     total_pix, dev_ms = shard.aggregate(npix_step * args.steps, dev_ms, device="cuda")
     _, wall_ms = shard.aggregate(0, wall_ms, device="cuda")
     _, e2e_wall_ms = shard.aggregate(0, e2e_wall_ms, device="cuda")
+    _, pinned_wall_ms = shard.aggregate(0, pinned_wall_ms, device="cuda")
     if rank != 0:
         return None
 
@@ -304,8 +398,7 @@ def run_ours(args, rank, world, local_rank):
         "metric": METRIC, "value": total_pix / (dev_ms * 1e-3) / 1e6, "unit": "Mpixels/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "3840x2160 u8 gray, octaves=5 levels=3, default Config (upscale 2x: octave 0 = 7680x4320), "
-                               "RootSift, desc loop", "frames_per_step_per_gpu": FRAMES_PER_STEP, "slots": SLOTS,
+        "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": FRAMES_PER_STEP, "slots": SLOTS,
                    "sharding": "frames across ranks, no collective",
                    "l2": "working set per frame 3.0 GB of planes >> 126 MB L2; L2 flushed (256 MB fill) before each roofline sample"},
         "wall_ms_per_step": wall_ms / args.steps,
@@ -314,7 +407,10 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": total_pix / (e2e_wall_ms * 1e-3) / 1e6, "unit": "Mpixels/s",
                 "h2d_bytes_per_step": FRAMES_PER_STEP * W * H,
                 "d2h_bytes_per_step": int(ecounts[0] * 72 + ecounts[1] * 512 + FRAMES_PER_STEP * 128),
-                "api": "popsift_b200.api.PopSift.enqueue -> SiftJob.get (C ABI ps_submit_u8/ps_counts/ps_download), pinned host frames"},
+                "api": "C++ drop-in API: PopSift::enqueue -> SiftJob::get -> delete (popsift_b200/bin/api_bench), PAGEABLE std::vector "
+                       "frames, one process per GPU -- the same driver loop as the reference arm's (oracle/ref_driver.cpp --bench)",
+                "pinned_ctypes": {"value": npix_step * world / (pinned_wall_ms * 1e-3) / 1e6, "unit": "Mpixels/s",
+                                  "api": "popsift_b200.api.PopSift.enqueue -> SiftJob.get (Python mirror of the C ABI), page-locked frames"}},
         "roofline": {"bound": "hbm", "stage": "pyramid (all launches of one frame)", "achieved": alg_bytes_frame / (pyr * 1e-3) / 1e9,
                      "peak": peak, "unit": "GB/s", "frac": alg_bytes_frame / (pyr * 1e-3) / 1e9 / peak, "peak_source": peak_src,
                      "algorithmic_bytes": alg_bytes_frame, "ms": pyr,
@@ -327,6 +423,7 @@ def run_ours(args, rank, world, local_rank):
                                          "achieved": dom_bytes / (dom * 1e-3) / 1e9, "frac": dom_bytes / (dom * 1e-3) / 1e9 / peak,
                                          "traffic": NCU_LEVEL_DRAM_BYTES}},
         "clocks": clocks,
+        "numa": NUMA_INFO,
     }
     if world == 1:      # reported baselines: rank 0 at N=1 only (torchrun pins OMP_NUM_THREADS=1)
         out.update(cpu_baselines(frames))
@@ -375,39 +472,46 @@ def cpu_baselines(frames, n_oracle=4):
 
 
 def run_reference(args, rank, world, local_rank):
-    """The unmodified reference (CUDA) through its own API; rank 0 only."""
+    """The unmodified reference (CUDA) through its own API.  Rank 0 alone runs it: one reference process per GPU
+    (`--gpus N`), each on its own batch of frames (weak scaling, like our arm), released together."""
     if rank != 0:
         return None
     exe = os.path.join(ROOT, "oracle", "_ref", "ref_dump")
     if not os.path.exists(exe):
         return {"impl": "reference", "unavailable": "oracle/_ref/ref_dump not built (needs /root/reference at build time)"}
-    from popsift_b200.synth import write_pgm
-    frames = synth_frames(FRAMES_PER_STEP, 0)
-    with tempfile.TemporaryDirectory() as td:
-        cmd = [exe, "--octaves", str(OCTAVES), "--levels", str(LEVELS), "--device", str(local_rank),
-               "--bench", str(args.steps), str(args.warmup)]
-        for i, f in enumerate(frames):
-            p = os.path.join(td, "f%d.pgm" % i)
-            write_pgm(p, f)
-            cmd += ["-i", p]
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=1200)
-    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
-    if r.returncode != 0 or not line:
-        return {"impl": "reference", "unavailable": "ref_dump failed: %s" % (r.stderr.strip()[-200:])}
-    j = json.loads(line[-1])
-    v = j["mpix_per_s"]
-    return {"impl": "reference", "metric": METRIC, "value": v, "unit": "Mpixels/s", "n_gpus": 1, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": j["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+    n = max(1, args.gpus)
+    try:
+        with tempfile.TemporaryDirectory() as td:
+            cmds, cpus = [], []
+            for g in range(n):
+                sub = os.path.join(td, "g%d" % g)
+                os.makedirs(sub)
+                cmd = [exe, "--octaves", str(OCTAVES), "--levels", str(LEVELS), "--device", str(g), "--bench", str(args.steps), str(args.warmup)]
+                for pth in write_frames(synth_frames(FRAMES_PER_STEP, g), sub):
+                    cmd += ["-i", pth]
+                cmds.append((cmd, os.path.join(sub, "go")))
+                cpus.append(gpu_numa_cpus(g))
+            outs = run_children(cmds, cpus=cpus)
+    except Exception as e:
+        return {"impl": "reference", "unavailable": "ref_dump failed: %s" % str(e)[-200:]}
+    total_ms = max(j["total_ms"] for j in outs)
+    px = sum(j["pixels_per_step"] for j in outs) * args.steps
+    v = px / (total_ms * 1e-3) / 1e6
+    return {"impl": "reference", "metric": METRIC, "value": v, "unit": "Mpixels/s", "n_gpus": n, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "3840x2160 u8 gray, octaves=5 levels=3, default Config, RootSift, desc loop",
-                       "frames_per_step_per_gpu": FRAMES_PER_STEP,
-                       "note": "reference PopSift is CUDA-only (no CPU implementation exists); it runs on GPU 0 through "
-                               "PopSift::enqueue/SiftJob::get with host buffers; N>1 is not supported by this arm"},
-            "features_per_step": j["features_last_step"], "descriptors_per_step": j["descriptors_last_step"],
-            "cpu_baseline": {"value": v, "unit": "Mpixels/s", "cores": 2, "kind": "reference",
-                             "sample": "%d frames 3840x2160 per step, unmodified reference libpopsift (oracle/_ref) on the B200, "
-                                       "2 host threads" % FRAMES_PER_STEP},
+            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": FRAMES_PER_STEP,
+                       "note": "reference PopSift is CUDA-only (no CPU implementation exists); one reference process per GPU through "
+                               "PopSift::enqueue/SiftJob::get with pageable host buffers, started together"},
+            "features_per_step": sum(j["features_last_step"] for j in outs), "descriptors_per_step": sum(j["descriptors_last_step"] for j in outs),
+            "per_gpu_mpix_per_s": [j["mpix_per_s"] for j in outs],
+            "cpu_baseline": {"value": v, "unit": "Mpixels/s", "cores": 2 * n, "kind": "reference",
+                             "sample": "%d frames 3840x2160 per step per GPU, unmodified reference libpopsift (oracle/_ref) on %d B200, "
+                                       "2 host threads per GPU" % (FRAMES_PER_STEP, n)},
             "e2e": {"value": v, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+NUMA_INFO = {"bound": False}
 
 
 def main():
@@ -421,6 +525,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    global NUMA_INFO
+    if args.impl == "ours":        # before torch / any page-locked allocation
+        NUMA_INFO = bind_to_gpu_node(local_rank)
     if args.impl == "reference":
         out = run_reference(args, rank, world, local_rank)
         if out is not None:

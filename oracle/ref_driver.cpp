@@ -29,6 +29,7 @@
 #include <cuda_runtime.h>
 
 #include <chrono>
+#include <unistd.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -109,7 +110,7 @@ int main(int argc, char** argv)
     bool log = false, float_mode = false, do_match = false, direct_scaling = false;
     int bench_steps = 0, bench_warm = 0, device = 0, repeat = 1;
     int filter_max = -1, filter_grid = -1;
-    std::string filter_sort = "", desc_mode = "";
+    std::string filter_sort = "", desc_mode = "", go_file = "";
     std::string mode = "popsift", norm = "", gauss = "";
     float downsampling = 1e9f, sigma = -1, threshold = -1, edge = -1, iblur = -1;
     int octaves = -2, levels = -1, norm_multi = -1000;
@@ -140,6 +141,7 @@ int main(int argc, char** argv)
         else if (a == "--filter-grid") filter_grid = atoi(nxt());
         else if (a == "--filter-sort") filter_sort = nxt();
         else if (a == "--desc-mode") desc_mode = nxt();
+        else if (a == "--go-file") go_file = nxt();     // --bench: after the warm-up wait until this file exists
         else if (a == "--bench") { bench_steps = atoi(nxt()); bench_warm = atoi(nxt()); }
         else { fprintf(stderr, "unknown flag %s\n", a.c_str()); return 2; }
     }
@@ -223,6 +225,10 @@ int main(int argc, char** argv)
         };
         for (int w = 0; w < bench_warm; w++) pass();
         cudaDeviceSynchronize();
+        if (!go_file.empty()) {
+            printf("ready\n"); fflush(stdout);
+            while (!std::ifstream(go_file).good()) usleep(200);
+        }
         auto t0 = std::chrono::steady_clock::now();
         for (int s = 0; s < bench_steps; s++) pass();
         cudaDeviceSynchronize();

@@ -9,6 +9,7 @@
 //                                    and a 2x2 sample; plus fraction 0 for all 256 values
 //   texprobe fpairs out.bin         float texture (ImageFloat, s_image.cu:262-291): 2x2 blends of a random
 //                                    64x64 float image at a 16x16 grid of fractions, and the fraction quantisation
+//   texprobe upairs out.bin         the 8-bit texture at general fractions (16x16 grid, random 64x64 image)
 //   texprobe coords W H UP out.bin   random WxH u8 image; for rows 0..7 and the last 8,
 //                                    every X in [0,W0) and off in [-16,16]: tex2D at
 //                                    ((X+shift)/W0 -/+ off/W0, (Y+shift)/H0); writes image + samples
@@ -173,6 +174,33 @@ int main(int argc, char** argv)
         fwrite(hdr, 4, 4, fp); fwrite(img.data(), 4, img.size(), fp); fwrite(o.data(), 4, o.size(), fp);
         fclose(fp);
         printf("texprobe fpairs: %d + %d samples\n", n1, n2);
+        return 0;
+    }
+    if (!strcmp(argv[1], "upairs")) {
+        // the 8-bit texture at GENERAL fractions (the reference's configuration, s_image.cu:138-167): same
+        // sampling pattern as fpairs on a random 64x64 u8 image
+        const int W = 64, H = 64;
+        std::vector<unsigned char> img(size_t(W) * H);
+        srand(4321);
+        for (auto& v : img) v = rand() & 255;
+        unsigned char* d; size_t pitch; CK(cudaMallocPitch((void**)&d, &pitch, W, H));
+        CK(cudaMemcpy2D(d, pitch, img.data(), W, W, H, cudaMemcpyHostToDevice));
+        cudaTextureObject_t t = make_tex(d, pitch, W, H);
+        std::vector<float2> q;
+        for (int j = 8; j < 40; j++) for (int i = 8; i < 40; i++)
+            for (int b = 0; b < 256; b += 17) for (int a = 0; a < 256; a += 17)
+                q.push_back(make_float2((i + 0.5f + a / 256.0f) / W, (j + 0.5f + b / 256.0f) / H));
+        const int n1 = int(q.size());
+        float2* dq; float* dout; CK(cudaMalloc(&dq, q.size() * sizeof(float2))); CK(cudaMalloc(&dout, q.size() * 4));
+        CK(cudaMemcpy(dq, q.data(), q.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        fetch<<<(int(q.size()) + 255) / 256, 256>>>(t, dq, dout, int(q.size()));
+        CK(cudaDeviceSynchronize());
+        std::vector<float> o(q.size()); CK(cudaMemcpy(o.data(), dout, q.size() * 4, cudaMemcpyDeviceToHost));
+        FILE* fp = fopen(argv[2], "wb");
+        int hdr[4] = { W, H, n1, 0 };
+        fwrite(hdr, 4, 4, fp); fwrite(img.data(), 1, img.size(), fp); fwrite(o.data(), 4, o.size(), fp);
+        fclose(fp);
+        printf("texprobe upairs: %d samples\n", n1);
         return 0;
     }
     if (!strcmp(argv[1], "coords")) {

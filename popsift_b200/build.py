@@ -31,6 +31,8 @@ LIB_SOURCES = ["ps_tables.cpp", "ps_ctx.cu", "k_pyramid.cu", "k_pyramid_march.cu
 DEMO_SOURCES = ["app/popsift_demo.cpp", "app/pgmread.cpp"]
 API_CHECK = os.path.join(BIN_DIR, "api_check")
 API_CHECK_SRC = os.path.join(ROOT, "tests", "cpp", "api_check.cpp")
+API_BENCH = os.path.join(BIN_DIR, "api_bench")
+API_BENCH_SRC = os.path.join(ROOT, "tests", "cpp", "api_bench.cpp")
 PART_CHECK = os.path.join(BIN_DIR, "partition_check")
 PART_CHECK_SRC = os.path.join(ROOT, "tests", "cpp", "partition_check.cpp")
 PGM_CHECK = os.path.join(BIN_DIR, "pgmread_check")
@@ -86,6 +88,10 @@ def build(verbose: bool = False, force: bool = False) -> str:
     if os.path.exists(API_CHECK_SRC) and (force or _newer(API_CHECK, [API_CHECK_SRC, LIB] + hdrs)):
         # a plain host compiler is enough for a caller of the C++ API: no CUDA in the translation unit
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"), API_CHECK_SRC, "-o", API_CHECK,
+                               "-L" + LIB_DIR, "-lpopsift_b200", "-Wl,-rpath," + "$ORIGIN/../lib", "-lpthread"])
+    if os.path.exists(API_BENCH_SRC) and (force or _newer(API_BENCH, [API_BENCH_SRC, LIB] + hdrs)):
+        # end-to-end timing through the C++ API from pageable frames (bench.py's e2e leg)
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"), API_BENCH_SRC, "-o", API_BENCH,
                                "-L" + LIB_DIR, "-lpopsift_b200", "-Wl,-rpath," + "$ORIGIN/../lib", "-lpthread"])
     part_hdr = os.path.join(CSRC, "k_partition.h")
     if os.path.exists(PART_CHECK_SRC) and (force or _newer(PART_CHECK, [PART_CHECK_SRC, part_hdr])):

@@ -303,7 +303,7 @@ def test_result_arrays_keep_their_page_locked_block_alive():
     del row
     gc.collect()
     assert len(pool.blocks) == 1                           # recycled
-    f, d = api._leased_views(pool, pool.blocks.pop(), 0, 0)
+    f, d = api._leased_views(pool, pool.blocks.pop(), 1, 1)
     pool.close()                                           # PopSift.uninit() while a result is still referenced
     assert len(L.live) == 2
     del f, d
