@@ -153,10 +153,14 @@ static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ?
  * reference's own coordinate arithmetic at 640x480, 641x479, 3840x2160):
  *   - texel-space coordinate xB = rx*w - 0.5, clamped to [-0.5, w-0.5];
  *     fraction rounded to nearest 1/256;
- *   - texels widened u8 -> unorm16 (x257); 2x2 blend in integer arithmetic,
- *     rounded half-up to a 16-bit value r16;
+ *   - the four blend weights are 8-BIT, like the float texture's (`texprobe upairs`, a 16x16 grid of general
+ *     fractions on a random image, tests/golden/texture_u8_general.npz): w11 = round(ax*ay/256) half-up,
+ *     w10 = ax - w11, w01 = ay - w11, w00 = 256 - ax - ay + w11;
+ *   - texels widened u8 -> unorm16 (x257); blend in integer arithmetic, rounded half-up to a 16-bit r16;
  *   - returned float = (float)r16 / 65535.0f (correctly rounded).
- * 0 mismatches over 6.4 M probed samples (tools/analyze_texprobe.py). */
+ * 0 mismatches over 6.4 M samples at fractions 0 and 1/2 (where the weights are exact products) and over
+ * 262 144 samples at general fractions.  (Round 1 used the 16-bit products of the fractions: identical at
+ * fractions 0 and 1/2, i.e. for every integer up-scale factor, wrong elsewhere.) */
 float orc_tex_u8(const uint8_t* img, int w, int h, float rx, float ry)
 {
     float fx = rx * (float)w - 0.5f;
@@ -175,9 +179,9 @@ float orc_tex_u8(const uint8_t* img, int w, int h, float rx, float ry)
     int y0 = clampi(iy, 0, h - 1), y1 = clampi(iy + 1, 0, h - 1);
     const int64_t t00 = img[(size_t)y0 * w + x0], t10 = img[(size_t)y0 * w + x1];
     const int64_t t01 = img[(size_t)y1 * w + x0], t11 = img[(size_t)y1 * w + x1];
-    const int64_t num = (256 - ax) * (256 - ay) * t00 + ax * (256 - ay) * t10
-                      + (256 - ax) * ay * t01 + ax * ay * t11;   /* weights sum to 65536 */
-    const int64_t r16 = (num * 257 + 32768) >> 16;
+    const int64_t w11 = (ax * ay + 128) >> 8, w10 = ax - w11, w01 = ay - w11, w00 = 256 - ax - ay + w11;
+    const int64_t num = w00 * t00 + w10 * t10 + w01 * t01 + w11 * t11;   /* weights sum to 256 */
+    const int64_t r16 = (num * 257 + 128) >> 8;
     return (float)r16 / 65535.0f;
 }
 
@@ -570,7 +574,8 @@ static void orientation_one(const orc_ctx* c, const iext_t* ie, ext_t* e)
         const int prev = b == 0 ? ORI_NBINS - 1 : b - 1;
         const int next = b == ORI_NBINS - 1 ? 0 : b + 1;
         int pred = sm[b] > fmaxf(sm[prev], sm[next]);
-        const float num = pred ? 3.0f * sm[prev] - 4.0f * sm[b] + 1.0f * sm[next] : 0.0f;
+        /* reference SASS (ori_par): num = hn + fma(hp, 3, hc * -4) -- nvcc contracts the first two products */
+        const float num = pred ? sm[next] + fmaf(sm[prev], 3.0f, sm[b] * -4.0f) : 0.0f;
         const float denB = pred ? 2.0f * (sm[prev] - 2.0f * sm[b] + sm[next]) : 1.0f;
         const float newbin = num / denB;
         pred = pred && newbin >= 0.0f && newbin <= 2.0f;

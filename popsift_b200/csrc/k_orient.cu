@@ -21,6 +21,8 @@
 // 3x(box3, box3) smoothing, parabola refinement, peaks >= 0.8*best, theta = fma(2pi*bin, 1/36, -pi).
 #include "ps_internal.h"
 
+#include <cstdlib>
+
 namespace psb {
 
 namespace {
@@ -34,9 +36,10 @@ __device__ const float kPi2 = 2.0f * 3.14159265358979323846f;
 __device__ __forceinline__ int octave_prefix(const Counters* ct, const Consts& k, int num_octaves, int* ps /*[kMaxOctaves+1]*/)
 {
     int total = 0;
+    const int* counts = ct->filtered ? ct->ext_ct_f : ct->ext_ct;      // after the grid filter: the survivors
     for (int o = 0; o < num_octaves; ++o) {
         ps[o] = total;
-        int c = min(ct->ext_ct[o], k.max_extrema);
+        int c = min(counts[o], k.max_extrema);
         if (total + c > k.ext_capacity) c = k.ext_capacity - total;
         total += c;
     }
@@ -44,10 +47,15 @@ __device__ __forceinline__ int octave_prefix(const Counters* ct, const Consts& k
     return total;
 }
 
+// ATOMIC = true: histogram by shared float atomics like the reference (default); false: lane-private bins summed in
+// lane order (POPSIFT_B200_ORI_LANESUM=1; run-to-run deterministic by construction, ~20 % faster, not the reference's sums)
+template <bool ATOMIC>
 __global__ void __launch_bounds__(WARPS * 32)
-orientation_kernel(PyramidView pyr, Consts k, const InitialExtremum* __restrict__ iext,
+orientation_kernel(PyramidView pyr, Consts k, const InitialExtremum* __restrict__ iext_all, const InitialExtremum* __restrict__ iext_f,
                    ps_extremum* __restrict__ ext, int* __restrict__ slice_sum, Counters* ct)
 {
+    const InitialExtremum* __restrict__ iext = ct->filtered ? iext_f : iext_all;
+    __shared__ float hist[ATOMIC ? 1 : WARPS][ATOMIC ? 1 : kOriBins * 33];     // lane-private bins (stride 33: conflict-free)
     __shared__ float sm_a[WARPS][kOriBins];
     __shared__ float sm_b[WARPS][kOriBins];
     __shared__ int   ps[kMaxOctaves + 1];
@@ -69,7 +77,9 @@ orientation_kernel(PyramidView pyr, Consts k, const InitialExtremum* __restrict_
         const int lvl = min(max(ie.lpos, 0), pyr.levels + 2);
         const float* pl = ov.gauss + (size_t)lvl * ov.plane;
 
-        for (int b = lane; b < kOriBins; b += 32) A[b] = 0.0f;
+        float* Hp = hist[ATOMIC ? 0 : warp];
+        if (ATOMIC) { for (int b = lane; b < kOriBins; b += 32) A[b] = 0.0f; }
+        else        { for (int b = 0; b < kOriBins; ++b) Hp[b * 33 + lane] = 0.0f; }
         __syncwarp();
 
         const float x = ie.xpos, y = ie.ypos, sig = ie.sigma;
@@ -112,10 +122,22 @@ orientation_kernel(PyramidView pyr, Consts k, const InitialExtremum* __restrict_
                 xx += 32;
                 while (xx > xmax) { xx -= wx; ++yy; }
             }
-            __syncwarp();
-            if (bidx >= 0) atomicAdd(&A[bidx], weight);
+            if (ATOMIC) {
+                __syncwarp();
+                if (bidx >= 0) atomicAdd(&A[bidx], weight);
+            } else if (bidx >= 0) {
+                Hp[bidx * 33 + lane] += weight;
+            }
         }
         __syncwarp();
+        if (!ATOMIC) {
+            for (int b = lane; b < kOriBins; b += 32) {
+                float sum = 0.0f;
+                for (int l = 0; l < 32; ++l) sum = __fadd_rn(sum, Hp[b * 33 + l]);
+                A[b] = sum;
+            }
+            __syncwarp();
+        }
         // 3 x (box3 ; box3), circular over 36 bins (reference s_orientation.cu:58-68,166-174)
         for (int it = 0; it < 3; ++it) {
             for (int b = lane; b < kOriBins; b += 32) {
@@ -139,7 +161,9 @@ orientation_kernel(PyramidView pyr, Consts k, const InitialExtremum* __restrict_
                 const int pv = b == 0 ? kOriBins - 1 : b - 1, nx = b == kOriBins - 1 ? 0 : b + 1;
                 const float hp = A[pv], hc = A[b], hn = A[nx];
                 bool pred = hc > fmaxf(hp, hn);
-                const float num = pred ? 3.0f * hp - 4.0f * hc + 1.0f * hn : 0.0f;
+                // the reference's SASS evaluates 3*hp - 4*hc + 1*hn as  hn + fma(hp, 3, hc * -4)  (nvcc contracts the first
+                // two products; cuobjdump of ori_par: FMUL R6 = hc*-4; FFMA R6 = hp*3 + R6; FADD R0 = hn + R6)
+                const float num = pred ? __fadd_rn(hn, __fmaf_rn(hp, 3.0f, __fmul_rn(hc, -4.0f))) : 0.0f;
                 const float den = pred ? 2.0f * (hp - 2.0f * hc + hn) : 1.0f;
                 const float newbin = __fdividef(num, den);
                 pred = pred && newbin >= 0.0f && newbin <= 2.0f;
@@ -260,18 +284,21 @@ ori_scatter_kernel(int num_octaves, Consts k, ps_extremum* __restrict__ ext, int
         ct->ext_total = total;
         ct->ori_total = min(base + block_total, k.desc_capacity);
         int raw = 0;
-        for (int o = 0; o < num_octaves; ++o) raw += min(ct->ext_ct[o], k.max_extrema);
+        const int* counts = ct->filtered ? ct->ext_ct_f : ct->ext_ct;
+        for (int o = 0; o < num_octaves; ++o) raw += min(counts[o], k.max_extrema);
         if (raw > total) atomicOr(&ct->overflow, 1);
     }
 }
 
 } // namespace
 
-int launch_orientation(const PyramidView& pyr, const Consts& k, const InitialExtremum* iext, ps_extremum* ext,
+int launch_orientation(const PyramidView& pyr, const Consts& k, const InitialExtremum* iext, const InitialExtremum* iext_f, ps_extremum* ext,
                        int* feat_to_ext, int* slice_sum, Counters* ct, cudaStream_t st)
 {
     // fixed grid: SMs x 8 resident CTAs of 4 warps; warps stride over the device-side count
-    orientation_kernel<<<sm_count() * 8, WARPS * 32, 0, st>>>(pyr, k, iext, ext, slice_sum, ct);
+    static const bool lanesum = [] { const char* e = getenv("POPSIFT_B200_ORI_LANESUM"); return e && e[0] == '1'; }();
+    if (lanesum) orientation_kernel<false><<<sm_count() * 8, WARPS * 32, 0, st>>>(pyr, k, iext, iext_f, ext, slice_sum, ct);
+    else         orientation_kernel<true><<<sm_count() * 8, WARPS * 32, 0, st>>>(pyr, k, iext, iext_f, ext, slice_sum, ct);
     ori_scatter_kernel<<<k.ext_capacity / kSlice + 1, kSlice, 0, st>>>(pyr.num_octaves, k, ext, feat_to_ext, slice_sum, ct);
     return 2;
 }

@@ -221,10 +221,7 @@ level0_kernel(const PIX* __restrict__ img, size_t img_pitch, int w, int h, float
         if (sizeof(PIX) == 1) {
             const unsigned t00 = (unsigned)r0[tx.i0], t10 = (unsigned)r0[tx.i1];
             const unsigned t01 = (unsigned)r1[tx.i0], t11 = (unsigned)r1[tx.i1];
-            const unsigned wx1 = tx.a, wx0 = 256u - wx1, wy1 = ty.a, wy0 = 256u - wy1;
-            const unsigned num = wx0 * wy0 * t00 + wx1 * wy0 * t10 + wx0 * wy1 * t01 + wx1 * wy1 * t11;
-            const unsigned r16 = (num * 257u + 32768u) >> 16;
-            s[idx] = __fdiv_rn((float)r16, 65535.0f);
+            s[idx] = __fdiv_rn((float)tex_blend_u8(t00, t10, t01, t11, tx.a, ty.a), 65535.0f);
         } else {
             // float images: the float texture's 8-bit-weight blend, rounded once (k_texture.h)
             s[idx] = tex_blend_f32((float)r0[tx.i0], (float)r0[tx.i1], (float)r1[tx.i0], (float)r1[tx.i1], tx.a, ty.a);

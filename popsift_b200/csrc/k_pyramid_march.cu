@@ -1,20 +1,22 @@
 // Stage 1, fast path -- "column-marching" fused Gaussian level kernel for sm_100a.
 //
-// One CTA owns a strip of TW=128 output columns and marches down a segment of rows in chunks of
-// Q=16 rows.  Per chunk:
-//   1. the Q new source rows (+ horizontal halo, clamp-to-edge) are staged in shared memory; they
-//      were prefetched into registers with 128-bit loads while the previous chunk was computed;
+// One CTA (128 threads) owns a strip of TW=128 output columns and marches down a segment of rows in
+// chunks of Q=16 rows.  Per chunk:
+//   1. the Q new source rows (+ horizontal halo) are staged in shared memory by the TMA unit: ONE elected
+//      thread issues one cp.async.bulk.tensor.2d (box = padded strip width x 16 rows, SASS UTMALDG) per
+//      chunk, NBUF-2 chunks ahead, completion on an mbarrier per staging buffer.  No thread computes copy
+//      addresses or issues per-piece copies.  The tensor map's out-of-bounds zero fill covers the left /
+//      right image border (the halo columns are then patched to clamp-to-edge in shared memory); the few
+//      chunks that touch the top / bottom border are staged row by row with 1-D bulk copies from the
+//      clamped row addresses (UBLKCP), on the same mbarrier;
 //   2. row pass: thread = (row, 16-column group); a 16+2R wide register window is loaded with
-//      conflict-free LDS.128 (row stride == 4 mod 32) and produces 16 outputs -> ring buffer HB of
-//      row-filtered lines (Q+2R lines);
-//   3. column pass: thread = column; the whole ring column (Q+2R values) is loaded once into
-//      registers and produces the Q output rows that lag the input by R rows: level l, DoG[l-1]
-//      (= out - centre source, still in the staging buffers) and, for level L, the 2:1 decimated
-//      level 0 of the next octave.
+//      conflict-free LDS.128 (row stride with an odd number of float4 -- the TMA box is that wide) and
+//      produces 16 outputs -> ring buffer HB of row-filtered lines (Q+2R lines);
+//   3. column pass: thread = (pair of adjacent columns, 8 rows); the 8+2R ring lines are loaded once and every
+//      tap is one packed FFMA2; the outputs lag the input by R rows: level l, DoG[l-1] (= out - centre
+//      source, still in the staging buffers) and, for level L, the 2:1 decimated level 0 of the next octave.
 // Every source row is read from HBM once (+2R warm-up rows per segment), every output written once;
-// the row-filtered intermediate never leaves shared memory.  Shared-memory traffic is ~11 floats
-// per pixel at R=13 instead of ~60 for a one-output-per-thread stencil, which is what keeps the
-// FP32 pipe (4R+2 dependent-order FMA/ADD per pixel, fixed by the parity contract) fed.
+// the row-filtered intermediate never leaves shared memory.
 //
 // The floating-point evaluation order is exactly the one documented in k_pyramid.cu (taken from the
 // reference's sm_100 SASS); results are bit-identical to the tile kernels and to the reference.
@@ -22,6 +24,8 @@
 #include "k_pyramid.h"
 #include "k_texture.h"
 #include "k_partition.h"
+
+#include <cuda.h>          // CUtensorMap (types only: the encoder is fetched through the runtime, no libcuda link)
 
 #include <cstdint>
 #include <cstdlib>
@@ -52,73 +56,69 @@ struct Geo {
     static constexpr int NBUF = (R <= 8) ? 4 : 3;
     static constexpr int AHEAD = NBUF - 2;
     static constexpr int RING = Q + 2 * R;              // lines in the ring buffer
-    static constexpr int V4 = Q * SW / 4;               // float4 per staged chunk
-    static constexpr int PF = (V4 + NT - 1) / NT;       // float4 prefetch registers per thread
     static constexpr size_t smem = sizeof(float) * (NBUF * Q * SWP + RING * HBW);   // staging buffers + ring
     static_assert(R <= Q, "centre rows must still be in the two staging buffers");
+    static_assert((Q * SWP * sizeof(float)) % 128 == 0, "staging buffers stay 128-byte aligned (TMA destination)");
+    static_assert(SWP <= 256, "TMA box dimension");
 };
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
-// ---- staging: source rows -> shared (cp.async) ------------------------------------------------
-//
-// The 16-byte piece a thread moves in slot k of a chunk is the same (row j_k, column group i4_k) for
-// every chunk, so its global offset (relative to the chunk's first row) and its shared-memory offset
-// are computed once per CTA.  Strips that touch the left or right image border (EDGE) skip the pieces
-// that start outside the image and patch the missing halo columns in shared memory afterwards
-// (clamp-to-edge), so they cost one extra barrier per chunk instead of a scalar gather.
+// ---- staging: source rows -> shared (TMA) ----------------------------------------------------------
 
-template <int R>
-struct StageMap {
-    int goff[Geo<R>::PF];     // j*pitch + (x0 - RP + 4*i4)   (floats)
-    int soff[Geo<R>::PF];     // j*SWP + 4*i4                 (floats)
-    unsigned live;            // bit k: slot k exists for this thread and starts inside the image
-};
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-template <int R, bool EDGE>
-__device__ __forceinline__ void make_stage_map(StageMap<R>& m, int pitch, int x0, int W)
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
 {
-    using G = Geo<R>;
-    m.live = 0;
-#pragma unroll
-    for (int k = 0; k < G::PF; ++k) {
-        const int e = threadIdx.x + k * NT;
-        const int j = e / (G::SW / 4);
-        const int i4 = e - j * (G::SW / 4);
-        const int gx = x0 - G::RP + 4 * i4;
-        m.goff[k] = j * pitch + gx;
-        m.soff[k] = j * G::SWP + 4 * i4;
-        if (e < G::V4 && (!EDGE || (gx >= 0 && gx < W))) m.live |= 1u << k;
-    }
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+// one box of the source plane -> shared; coordinates may lie outside the tensor (zero fill)
+__device__ __forceinline__ void tma_load_2d(float* dst, const CUtensorMap* map, int x, int y, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+// one contiguous piece (16-byte aligned, multiple of 16 bytes) -> shared
+__device__ __forceinline__ void bulk_load_1d(float* dst, const float* src, unsigned bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ void cp_async16(float* s, const float* g)
-{
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(s);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(g) : "memory");
-}
-
-// asynchronous global->shared copy of one chunk; rows outside the image clamp to the border rows
+// Stage chunk rows [iy, iy+Q) x columns [x0-RP, x0-RP+SWP) of `src` into S (row stride SWP); called by ONE thread.
+// Interior chunks: one tensor copy (the box is SWP wide so that the shared-memory row stride is the conflict-free one;
+// columns outside [0, W) arrive as zeros).  Chunks that cross the top / bottom border: Q row copies from the
+// clamped rows, clipped to the row's storage (columns >= W hold padding; both cases are patched by patch_halo).
 template <int R, bool EDGE>
-__device__ __forceinline__ void stage_async(const StageMap<R>& m, const float* __restrict__ src, int H, int pitch, int iy,
-                                            float* __restrict__ S)
+__device__ __forceinline__ void stage_tma(const CUtensorMap* map, const float* __restrict__ src, int H, int pitch, int x0, int iy,
+                                          float* __restrict__ S, uint64_t* bar)
 {
     using G = Geo<R>;
     if (iy >= 0 && iy + Q <= H) {
-        const float* base = src + (long long)iy * pitch;
-#pragma unroll
-        for (int k = 0; k < G::PF; ++k) {
-            const bool whole = !EDGE && (k + 1) * NT <= G::V4;      // slot k exists for every thread
-            if (whole || (m.live >> k & 1)) cp_async16(S + m.soff[k], base + m.goff[k]);
-        }
+        mbar_expect_tx(bar, (unsigned)(Q * G::SWP * sizeof(float)));
+        tma_load_2d(S, map, x0 - G::RP, iy, bar);
     } else {
-#pragma unroll
-        for (int k = 0; k < G::PF; ++k)
-            if (m.live >> k & 1) {
-                const int j = (threadIdx.x + k * NT) / (G::SW / 4);
-                const int gy = clampi(iy + j, 0, H - 1);
-                cp_async16(S + m.soff[k], src + (long long)gy * pitch + (m.goff[k] - j * pitch));
-            }
+        const int gx0 = EDGE ? max(x0 - G::RP, 0) : x0 - G::RP;
+        const int gx1 = EDGE ? min(x0 - G::RP + G::SW, pitch) : x0 - G::RP + G::SW;
+        const unsigned bytes = (unsigned)(gx1 - gx0) * (unsigned)sizeof(float);
+        mbar_expect_tx(bar, (unsigned)Q * bytes);
+#pragma unroll 1
+        for (int j = 0; j < Q; ++j) {
+            const int gy = clampi(iy + j, 0, H - 1);
+            bulk_load_1d(S + j * G::SWP + (gx0 - (x0 - G::RP)), src + (long long)gy * pitch + gx0, bytes, bar);
+        }
     }
 }
 
@@ -142,6 +142,8 @@ __device__ __forceinline__ void patch_halo(float* __restrict__ S, int x0, int W)
         const int ce = min(cl + R, G::SW - 1);
         for (int c = cl + 1 + u; c <= ce; c += NT / Q) row[c] = v;
     }
+    // these generic-proxy writes precede a later TMA write into the same buffer
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
 // ---- row pass: stage -> ring ------------------------------------------------------------------
@@ -296,7 +298,8 @@ __device__ __forceinline__ void col_pass(const float* __restrict__ HB, const flo
 }
 
 template <int R, bool EDGE, bool NEXT, bool CAND>
-__device__ __forceinline__ void march_body(float* __restrict__ smem, const float* __restrict__ src, float* __restrict__ dst,
+__device__ __forceinline__ void march_body(float* __restrict__ smem, uint64_t* __restrict__ full, const CUtensorMap* map,
+                                           const float* __restrict__ src, float* __restrict__ dst,
                                            float* __restrict__ dog, float* __restrict__ next0, int W, int H, int pitch,
                                            int next_pitch, int x0, int ys, int ye, const Taps& taps, const CandSink& sink,
                                            int* cand_n)
@@ -307,24 +310,24 @@ __device__ __forceinline__ void march_body(float* __restrict__ smem, const float
     float* HB = smem + G::NBUF * SB;
     const int nchunks = (ye - ys + 2 * R + Q - 1) / Q;
 
-    StageMap<R> map;
-    make_stage_map<R, EDGE>(map, pitch, x0, W);
-    // staging of chunks k+1 .. k+AHEAD overlaps the computation of chunk k
-    auto issue = [&](int k) { stage_async<R, EDGE>(map, src, H, pitch, ys - R + k * Q, smem + (k % G::NBUF) * SB); };
+    // staging of chunks k+1 .. k+AHEAD overlaps the computation of chunk k; thread 0 is the producer
+    auto issue = [&](int k) {
+        stage_tma<R, EDGE>(map, src, H, pitch, x0, ys - R + k * Q, smem + (k % G::NBUF) * SB, full + (k % G::NBUF));
+    };
+    if (threadIdx.x == 0) {
 #pragma unroll
-    for (int k = 0; k < AHEAD; ++k) {
-        if (k < nchunks) issue(k);
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        for (int k = 0; k < AHEAD; ++k)
+            if (k < nchunks) issue(k);
     }
     int slot_in = 0;                     // ring slot of the chunk's first input row
     int cur = 0;                         // staging buffer of chunk k
+    unsigned parity = 0;                 // phase of full[cur]: flips every time cur wraps
     for (int k = 0; k < nchunks; ++k) {
         float* Scur = smem + cur * SB;
         float* Sprev = smem + (cur == 0 ? G::NBUF - 1 : cur - 1) * SB;
-        asm volatile("cp.async.wait_group %0;" :: "n"(AHEAD - 1) : "memory");
-        __syncthreads();                  // chunk k staged; column pass k-1 finished (ring + buffer of chunk k-2 are free)
-        if (k + AHEAD < nchunks) issue(k + AHEAD);
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        mbar_wait(full + cur, parity);    // chunk k has landed
+        __syncthreads();                  // column pass k-1 finished (ring + buffer of chunk k-2 are free)
+        if (threadIdx.x == 0 && k + AHEAD < nchunks) issue(k + AHEAD);
         if (EDGE) {
             patch_halo<R>(Scur, x0, W);
             __syncthreads();
@@ -336,28 +339,40 @@ __device__ __forceinline__ void march_body(float* __restrict__ smem, const float
         col_pass<R, true, NEXT, CAND>(HB, Scur, Sprev, slot_old, ys - 2 * R + k * Q, ys, ye, x0, W, dst, dog, next0, pitch,
                                       next_pitch, taps, sink, cand_n);
         slot_in = slot_old;
-        cur = cur == G::NBUF - 1 ? 0 : cur + 1;
+        if (cur == G::NBUF - 1) { cur = 0; parity ^= 1u; } else ++cur;
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();                      // last column pass finished
     if (CAND && threadIdx.x == 0) sink.counts[blockIdx.x] = *cand_n;
 }
 
 template <int R, bool NEXT, bool CAND>
 __global__ void __launch_bounds__(NT, 4)
-march_level_kernel(const float* __restrict__ src, float* __restrict__ dst, float* __restrict__ dog,
-                   float* __restrict__ next0, int W, int H, int pitch, int next_pitch, Partition part, Taps taps, CandSink sink)
+march_level_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ src, float* __restrict__ dst,
+                   float* __restrict__ dog, float* __restrict__ next0, int W, int H, int pitch, int next_pitch, Partition part,
+                   Taps taps, CandSink sink)
 {
     using G = Geo<R>;
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];   // TMA destinations: 128-byte aligned (every staging buffer is)
+    __shared__ __align__(8) uint64_t full[G::NBUF];  // one mbarrier per staging buffer
+    __shared__ int s_cand_n;                         // candidates of this block so far
     int strip, ys, ye;
     if (!locate(part, blockIdx.x, H, Q, strip, ys, ye)) return;
     const int x0 = strip * TW;
     const bool edge = (x0 - G::RP < 0) || (x0 + TW + G::RP > W);
-    __shared__ int s_cand_n;                         // candidates of this block so far
-    if (CAND && threadIdx.x == 0) s_cand_n = 0;      // published by the first barrier of the chunk loop
-    if (!edge) march_body<R, false, NEXT, CAND>(smem, src, dst, dog, next0, W, H, pitch, next_pitch, x0, ys, ye, taps, sink, &s_cand_n);
-    else       march_body<R, true, NEXT, CAND>(smem, src, dst, dog, next0, W, H, pitch, next_pitch, x0, ys, ye, taps, sink, &s_cand_n);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int b = 0; b < G::NBUF; ++b) mbar_init(full + b, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (CAND) s_cand_n = 0;
+    }
+    // programmatic dependent launch: everything above overlaps the previous grid's tail; its planes are complete and
+    // visible after the wait.  The next grid may be scheduled as soon as every CTA of this one has passed this point
+    // (it waits for our completion in the same way).
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    __syncthreads();
+    if (!edge) march_body<R, false, NEXT, CAND>(smem, full, &tmap, src, dst, dog, next0, W, H, pitch, next_pitch, x0, ys, ye, taps, sink, &s_cand_n);
+    else       march_body<R, true, NEXT, CAND>(smem, full, &tmap, src, dst, dog, next0, W, H, pitch, next_pitch, x0, ys, ye, taps, sink, &s_cand_n);
 }
 
 // ---- octave 0, level 0 from the input image -----------------------------------------------------
@@ -426,9 +441,7 @@ __device__ __forceinline__ void level0_body(float* __restrict__ smem, AxisTap* _
             if (sizeof(PIX) == 1) {
                 const unsigned t00 = (unsigned)r0[tx.i0], t10 = (unsigned)r0[tx.i1];
                 const unsigned t01 = (unsigned)r1[tx.i0], t11 = (unsigned)r1[tx.i1];
-                const unsigned wx1 = tx.a, wx0 = 256u - wx1, wy1 = ty.a, wy0 = 256u - wy1;
-                const unsigned num = wx0 * wy0 * t00 + wx1 * wy0 * t10 + wx0 * wy1 * t01 + wx1 * wy1 * t11;
-                v = unorm16_to_float((num * 257u + 32768u) >> 16);
+                v = unorm16_to_float(tex_blend_u8(t00, t10, t01, t11, tx.a, ty.a));
             } else {
                 v = tex_blend_f32((float)r0[tx.i0], (float)r0[tx.i1], (float)r1[tx.i0], (float)r1[tx.i1], tx.a, ty.a);
             }
@@ -451,7 +464,7 @@ march_level0_kernel(const PIX* __restrict__ img, size_t img_pitch, int w, int h,
                     float* __restrict__ dst, int W, int H, int pitch, Partition part, Taps dd, Taps inc0)
 {
     using G = Geo<R>;
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     __shared__ AxisTap ax[G::SW];
     __shared__ AxisTap ay[Q];
     int strip, ys, ye;
@@ -490,7 +503,7 @@ march_level0x2_kernel(const uint8_t* __restrict__ img, size_t img_pitch, int w, 
 {
     using G = Geo<R>;
     using G0 = Geo0<R>;
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     int strip, ys, ye;
     if (!locate(part, blockIdx.x, H, Q, strip, ys, ye)) return;
     const int x0 = strip * TW;
@@ -599,13 +612,57 @@ int level0_slots()
     return v > 0 ? v : 6 * sm_count();
 }
 
+// Tensor map of one w x h float plane (row pitch in floats) with a box of box_w x box_h elements; elements outside
+// the plane read as zero.  cuTensorMapEncodeTiled is a host-side encoder: it is fetched through the runtime
+// (cudaGetDriverEntryPoint), so the library does not link against libcuda.
+bool make_plane_tmap(CUtensorMap* map, const float* plane, int w, int h, int pitch, int box_w, int box_h)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static const EncodeFn encode = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+        }
+        return reinterpret_cast<EncodeFn>(p);
+    }();
+    if (!encode) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)w, (cuuint64_t)h};
+    const cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+    const cuuint32_t estr[2] = {1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(plane), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// POPSIFT_B200_PDL=0 launches the level kernels without programmatic dependent launch (A/B switch)
+bool pdl_choice()
+{
+    static const bool v = [] { const char* e = getenv("POPSIFT_B200_PDL"); return !(e && e[0] == '0'); }();
+    return v;
+}
+
 template <int R, bool NEXT, bool CAND>
-void launch_march(const Partition& part, const float* src, float* dst, float* dog, float* next0, const OctaveView& o,
-                  int next_pitch, const Taps& t, const CandSink& sink, cudaStream_t st)
+int launch_march(const Partition& part, const float* src, float* dst, float* dog, float* next0, const OctaveView& o,
+                 int next_pitch, const Taps& t, const CandSink& sink, cudaStream_t st)
 {
     ensure_smem(march_level_kernel<R, NEXT, CAND>, Geo<R>::smem, true);
-    march_level_kernel<R, NEXT, CAND><<<part.B, NT, Geo<R>::smem, st>>>(src, dst, dog, next0, o.w, o.h, o.pitch, next_pitch,
-                                                                        part, t, sink);
+    CUtensorMap map;
+    if (!make_plane_tmap(&map, src, o.w, o.h, o.pitch, Geo<R>::SWP, Q)) return -2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(part.B); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = Geo<R>::smem; cfg.stream = st;
+    // programmatic dependent launch: the next level's CTAs are scheduled while this grid drains and run their
+    // prologue (partition lookup, mbarrier init); they touch the planes only after griddepcontrol.wait
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_choice() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, march_level_kernel<R, NEXT, CAND>, map, src, dst, dog, next0, o.w, o.h, o.pitch, next_pitch,
+                              part, t, sink) == cudaSuccess ? 1 : -2;
 }
 
 template <int R>
@@ -617,11 +674,10 @@ int run_march(const OctaveView& o, int level, const Taps& t, float* next0, int n
     float* dog = o.dog + o.plane * (level - 1);
     const bool cand = sink && sink->list && o.w <= 65535 && o.h <= 65535 && sink->region == cand_region_cap(part, TW, Q);
     const CandSink cs = cand ? *sink : CandSink();
-    if (next0) { if (cand) launch_march<R, true, true>(part, src, dst, dog, next0, o, next_pitch, t, cs, st);
-                 else      launch_march<R, true, false>(part, src, dst, dog, next0, o, next_pitch, t, cs, st); }
-    else       { if (cand) launch_march<R, false, true>(part, src, dst, dog, next0, o, next_pitch, t, cs, st);
-                 else      launch_march<R, false, false>(part, src, dst, dog, next0, o, next_pitch, t, cs, st); }
-    return 1;
+    if (next0) return cand ? launch_march<R, true, true>(part, src, dst, dog, next0, o, next_pitch, t, cs, st)
+                           : launch_march<R, true, false>(part, src, dst, dog, next0, o, next_pitch, t, cs, st);
+    return cand ? launch_march<R, false, true>(part, src, dst, dog, next0, o, next_pitch, t, cs, st)
+                : launch_march<R, false, false>(part, src, dst, dog, next0, o, next_pitch, t, cs, st);
 }
 
 template <int R, typename PIX>

@@ -24,7 +24,7 @@ using namespace psb;
 namespace {
 
 thread_local std::string g_create_error;
-constexpr bool kGridFilterBuilt = false;
+constexpr bool kGridFilterBuilt = true;
 
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -44,6 +44,9 @@ struct Slot {
     PyramidView view{};
     // detections
     InitialExtremum* d_iext = nullptr;
+    InitialExtremum* d_iext_f = nullptr;      // grid filter: survivors, keep flags, plan (allocated only when the filter is configured)
+    unsigned char*   d_keep = nullptr;
+    FilterPlan*      d_plan = nullptr;
     ps_extremum*     d_ext = nullptr;
     ps_feature*      d_feat = nullptr;
     ps_descriptor*   d_desc = nullptr;
@@ -262,7 +265,13 @@ static int submit_common(ps_ctx* ctx, Slot& s)
     if (tm) PS_CUDA(ctx, cudaEventRecord(s.ev[2], s.stream));
     int n = launch_find_extrema(s.view, ctx->k, s.d_iext, s.d_ct, s.stream);
     if (tm) PS_CUDA(ctx, cudaEventRecord(s.ev[3], s.stream));
-    n += launch_orientation(s.view, ctx->k, s.d_iext, s.d_ext, s.d_f2e, s.d_ori_slice, s.d_ct, s.stream);
+    {
+        // grid filter (off by default): between extrema and orientation, like the reference (s_orientation.cu:380-383)
+        const FilterCfg fc = {ctx->cfg.filter_max_extrema, ctx->cfg.filter_grid_size, ctx->cfg.filter_sort};
+        n += launch_grid_filter(s.view, ctx->k, fc, s.d_iext, s.d_iext_f, s.d_keep, (size_t)s.num_octaves * ctx->k.max_extrema,
+                                s.d_plan, s.d_ct, s.stream);
+    }
+    n += launch_orientation(s.view, ctx->k, s.d_iext, s.d_iext_f, s.d_ext, s.d_f2e, s.d_ori_slice, s.d_ct, s.stream);
     if (tm) PS_CUDA(ctx, cudaEventRecord(s.ev[4], s.stream));
     n += launch_descriptors(s.view, ctx->k, s.d_ext, s.d_f2e, s.d_desc, s.d_ct, s.stream);
     n += launch_prep_features(ctx->k, s.d_ext, s.d_feat, s.d_ct, s.stream);
@@ -294,7 +303,7 @@ extern "C" void ps_destroy(ps_ctx* ctx)
     cudaSetDevice(ctx->device);
     for (Slot& s : ctx->slots) {
         if (s.stream) cudaStreamSynchronize(s.stream);
-        cudaFree(s.d_img); cudaFreeHost(s.h_img); cudaFree(s.d_planes); cudaFree(s.d_iext); cudaFree(s.d_ext); cudaFree(s.d_ori_slice);
+        cudaFree(s.d_img); cudaFreeHost(s.h_img); cudaFree(s.d_planes); cudaFree(s.d_iext); cudaFree(s.d_iext_f); cudaFree(s.d_keep); cudaFree(s.d_plan); cudaFree(s.d_ext); cudaFree(s.d_ori_slice);
         cudaFree(s.d_feat); cudaFree(s.d_desc); cudaFree(s.d_f2e); cudaFree(s.d_ct); cudaFreeHost(s.h_ct);
         cudaFreeHost(s.h_feat); cudaFreeHost(s.h_desc);
         for (auto& e : s.ev) if (e) cudaEventDestroy(e);
@@ -386,6 +395,11 @@ extern "C" ps_ctx* ps_create(int device, const ps_config* cfg, int max_w, int ma
         PS_TRY(cudaMalloc(&s.d_planes, planes * sizeof(float)));
         s.planes_floats = planes;
         PS_TRY(cudaMalloc(&s.d_iext, sizeof(InitialExtremum) * (size_t)ctx->max_octaves * k.max_extrema));
+        if (ctx->cfg.filter_max_extrema > 0) {
+            PS_TRY(cudaMalloc(&s.d_iext_f, sizeof(InitialExtremum) * (size_t)ctx->max_octaves * k.max_extrema));
+            PS_TRY(cudaMalloc(&s.d_keep, (size_t)ctx->max_octaves * k.max_extrema));
+            PS_TRY(cudaMalloc(&s.d_plan, sizeof(FilterPlan)));
+        }
         PS_TRY(cudaMalloc(&s.d_ext, sizeof(ps_extremum) * (size_t)k.ext_capacity));
         PS_TRY(cudaMalloc(&s.d_feat, sizeof(ps_feature) * (size_t)k.ext_capacity));
         PS_TRY(cudaMalloc(&s.d_desc, sizeof(ps_descriptor) * (size_t)k.desc_capacity));

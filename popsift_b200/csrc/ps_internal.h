@@ -29,7 +29,16 @@ struct Counters {
     int overflow;              // bit 0: extrema capacity hit, bit 1: descriptor capacity hit
     int work_ori;              // work-stealing cursors
     int work_desc;
-    int pad_[3];
+    int filtered;              // the grid filter fired: the orientation stage reads ext_ct_f / the filtered array
+    int ext_ct_f[kMaxOctaves]; // extrema per octave that survived the grid filter
+    int pad_[2];
+};
+
+// grid filter (k_filter.cu; reference s_filtergrid.cu:112-325)
+struct FilterCfg { int max_extrema, grid, sort; };
+struct FilterPlan {
+    int active, limit, total, pad_;
+    int cell_count[PS_MAX_FILTER_GRID * PS_MAX_FILTER_GRID];
 };
 
 // One octave's planes in HBM: linear float32, row pitch a multiple of 32 floats (128 B).
@@ -123,9 +132,15 @@ int cand_region_for(int w, int h);
 long long cand_entry_bound_for(int w, int h);
 
 int launch_find_extrema(const PyramidView& pyr, const Consts& k, InitialExtremum* iext, Counters* ct, cudaStream_t st);
+// grid filter between the extrema and the orientation stage; no-op (returns 0) when fc.max_extrema <= 0.
+// keep: one byte per initial extremum (num_octaves * max_extrema); iext_f: a second InitialExtremum array
+int launch_grid_filter(const PyramidView& pyr, const Consts& k, const FilterCfg& fc, const InitialExtremum* iext,
+                       InitialExtremum* iext_f, unsigned char* keep, size_t keep_bytes, FilterPlan* plan, Counters* ct,
+                       cudaStream_t st);
 // slice_sum: ext_capacity / PS_ORI_SLICE + 1 ints, zeroed per image
 #define PS_ORI_SLICE 256
-int launch_orientation(const PyramidView& pyr, const Consts& k, const InitialExtremum* iext, ps_extremum* ext,
+// iext_f: the grid-filtered extrema (read instead of iext when ct->filtered); may be nullptr when the filter is off
+int launch_orientation(const PyramidView& pyr, const Consts& k, const InitialExtremum* iext, const InitialExtremum* iext_f, ps_extremum* ext,
                        int* feat_to_ext, int* slice_sum, Counters* ct, cudaStream_t st);
 int launch_descriptors(const PyramidView& pyr, const Consts& k, const ps_extremum* ext, const int* feat_to_ext,
                        ps_descriptor* desc, Counters* ct, cudaStream_t st);

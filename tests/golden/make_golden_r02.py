@@ -9,6 +9,7 @@ Fixtures:
   texture_float.npz            what the B200 texture unit returns for the reference's FLOAT input texture
                                (ImageFloat): a random 64x64 float image, 2x2 blends at a 16x16 grid of
                                fractions for 16x32 texels, and the fraction quantisation of one texel row
+  texture_u8_general.npz       the 8-bit input texture at a 16x16 grid of general fractions (`texprobe upairs`)
   planes_f256_float.npz        sha256 (+ data of two) of the planes the float-mode reference run dumped
   feat_*_opencv_*.npz          Config::OpenCV SiftMode
   feat_*_float_*.npz           PopSift::FloatImages (pixels = u8 / 256)
@@ -62,6 +63,14 @@ def main(src):
         grid = o[:n1].reshape(32, 32, 16, 16)[:16]              # texel rows j = 8..23, i = 8..39; [j, i, b, a]
         quant = o[n1:].reshape(4, 32, 1024)[0]                  # j = 8, i = 8..39, a/1024
         np.savez_compressed(os.path.join(HERE, "texture_float.npz"), img=img, grid=grid, quant=quant)
+    # ---- 8-bit texture at general fractions
+    fn = os.path.join(src, "tex_upairs.bin")
+    if os.path.exists(fn):
+        data = open(fn, "rb").read()
+        W, H, n1, _ = struct.unpack_from("4i", data, 0)
+        img = np.frombuffer(data, np.uint8, W * H, 16).reshape(H, W)
+        o = np.frombuffer(data, np.float32, n1, 16 + W * H).reshape(32, 32, 16, 16)[:16]
+        np.savez_compressed(os.path.join(HERE, "texture_u8_general.npz"), img=img, grid=o)
     # ---- float-mode planes
     meta, keep = {}, {}
     for fn in sorted(glob.glob(os.path.join(src, "logf256", "dir-octave-dump", "*.dump"))):

@@ -460,3 +460,41 @@ def test_matching_mode_device_results_equal_host_results():
     with pytest.raises(api.PopSiftError):
         fd.match(fd)
     ps.uninit(); pm.uninit()
+
+
+@pytest.mark.parametrize("fm,g,sort", [(100, 2, "up"), (100, 2, "down"), (100, 3, "up"), (200, 3, "down"), (200, 2, "up"),
+                                       (100, 3, "random"), (200, 2, "random"), (300, 2, "up")])
+def test_grid_filter_vs_reference_goldens(fm, g, sort):
+    """--filter-max-extrema / --filter-grid / --filter-sort (reference s_filtergrid.cu:112-325): the kept keypoints are
+    the reference's for the `up` / `down` orders; for `random` (arrival order, not reproducible even by the reference)
+    the number kept is.  300 does not trigger the filter on this frame (int(1.1 * 300) >= 317 extrema)."""
+    w, h = 640, 480
+    cfg = mk_cfg("vlfeat", "classic")
+    cfg.setFilterMaxExtrema(fm); cfg.setFilterGridSize(g); cfg.setFilterSorting(sort)
+    ps, feats = run_gpu(make_frame(w, h, 1), cfg)
+    name = "feat_f640_filter_%d_%d_%s.npz" % (fm, g, sort) if fm != 300 else "feat_f640_vlfeat_classic_a.npz"
+    z = np.load(os.path.join(G, name))
+    rf = z["feat"]
+    assert feats.getFeatureCount() == len(rf)
+    if sort != "random":
+        a = sorted((int(f["octave"]), float(f["x"]), float(f["y"]), float(f["sigma"])) for f in feats.feat)
+        b = sorted((int(f["octave"]), float(f["x"]), float(f["y"]), float(f["sigma"])) for f in rf)
+        assert a == b
+        assert feats.getDescriptorCount() == (int(z["n_desc"][0]) if "n_desc" in z.files else len(z["desc"]))
+    ps.uninit()
+
+
+def test_grid_filter_1280_and_unsupported_options_are_refused():
+    z = np.load(os.path.join(G, "feat_f1280_filter_1000_4_up.npz"))
+    cfg = mk_cfg()
+    cfg.setFilterMaxExtrema(1000); cfg.setFilterGridSize(4); cfg.setFilterSorting("up")
+    ps, feats = run_gpu(make_frame(1280, 960, 5), cfg)
+    assert feats.getFeatureCount() == len(z["feat"]) and feats.getDescriptorCount() == int(z["n_desc"][0])
+    ps.uninit()
+    # options whose numerics are not implemented are refused, never silently computed with the default path
+    for setter in (lambda c: c.setDescMode("grid"), lambda c: c.setDescMode("notile"), lambda c: c.setGaussMode("fixed9"),
+                   lambda c: c.setScalingMode(0)):
+        c = mk_cfg()
+        setter(c)
+        with pytest.raises(api.PopSiftError):
+            api.PopSift(c, max_width=64, max_height=64)
