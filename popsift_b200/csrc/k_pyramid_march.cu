@@ -78,11 +78,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
 {
-    unsigned ok;
-    do {
+    unsigned ok, spins = 0;
+    for (;;) {
         asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
                      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!ok);
+        if (ok) break;
+        if (++spins > (1u << 24)) __trap();      // a copy that never lands must abort the launch, not hang the device
+    }
 }
 // one box of the source plane -> shared; coordinates may lie outside the tensor (zero fill)
 __device__ __forceinline__ void tma_load_2d(float* dst, const CUtensorMap* map, int x, int y, uint64_t* bar)
