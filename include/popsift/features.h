@@ -4,6 +4,7 @@
 #pragma once
 
 #include <iostream>
+#include <vector>
 
 #define ORIENTATION_MAX_COUNT 4
 
@@ -79,8 +80,8 @@ std::ostream& operator<<(std::ostream& ostr, const FeaturesHost& feature);
 
 /// Device-resident results (Config::MatchingMode; reference features.h:104-122): Feature records,
 /// descriptors and the descriptor -> feature reverse map live in device memory owned by this object;
-/// Feature::desc[] are device pointers into getDescriptors().  The brute-force matcher
-/// (FeaturesDev::match) is not part of this library yet.
+/// Feature::desc[] are device pointers into getDescriptors().  match() is the reference's brute-force
+/// 2-nearest-neighbour matcher (features.cu:282-304), computed on the tensor cores (C ABI ps_match).
 class FeaturesDev : public FeaturesBase
 {
     Feature*    _ext;
@@ -94,7 +95,11 @@ public:
 
     void reset(int num_ext, int num_ori);
 
-    void match(FeaturesDev* other);     // throws: not implemented
+    /// reference behaviour: prints one "accept/reject feat ..." line per descriptor of *this to stdout
+    void match(FeaturesDev* other);
+    /// the same search without the printing: 3 ints (best index, second index, accept) per descriptor of *this
+    /// (an addition to the reference's interface; flags as for ps_match)
+    std::vector<int> matchIndices(FeaturesDev* other, int flags = 0);
 
     Feature*    getFeatures() { return _ext; }
     Descriptor* getDescriptors() { return _ori; }

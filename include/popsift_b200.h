@@ -164,6 +164,18 @@ int ps_download_dev(ps_ctx* ctx, int slot, ps_feature* d_feat, ps_descriptor* d_
 void* ps_dev_alloc(size_t bytes);
 void  ps_dev_free(void* p);
 int   ps_dev_to_host(void* dst_host, const void* src_dev, size_t bytes);
+int   ps_host_to_dev(void* dst_dev, const void* src_host, size_t bytes);
+/* ordinal of the CUDA device a device pointer belongs to, or -1 */
+int   ps_pointer_device(const void* dev_ptr);
+/* replaces FeaturesDev::match -> compute_distance (reference features.cu:165-227,282-304): brute-force 2-nearest-
+ * neighbour search of every LEFT descriptor among the RIGHT descriptors by squared L2 distance.  d_left / d_right are
+ * DEVICE arrays (e.g. the descriptor arrays filled by ps_download_dev); d_out receives n_left x {best index, second
+ * index, accept} with accept = (best / second < 0.8f), also in DEVICE memory.  The call returns when the result is
+ * complete.  flags: PS_MATCH_AUTO, or force one implementation (PS_MATCH_EXACT: CUDA cores in the reference's
+ * evaluation order; PS_MATCH_TENSOR: tcgen05 tf32x3 candidate pass + exact re-rank). */
+enum { PS_MATCH_AUTO = 0, PS_MATCH_EXACT = 1, PS_MATCH_TENSOR = 2 };
+int ps_match(int device, const ps_descriptor* d_left, int n_left, const ps_descriptor* d_right, int n_right,
+             int32_t* d_out, int flags);
 /* page-locked host memory for images and results (thin wrappers of cudaHostAlloc / cudaFreeHost).
  * ps_submit_* and ps_download detect page-locked buffers and copy straight from / into them; pageable
  * buffers are staged through the slot's own pinned buffers (one extra host memcpy). */

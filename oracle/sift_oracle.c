@@ -560,7 +560,8 @@ static void orientation_one(const orc_ctx* c, const iext_t* ie, ext_t* e)
             const int sq_dist = (int)(ddx * ddx + ddy * ddy);
             if (sq_dist <= sq_thres) {
                 const float weight = grad * expf((float)sq_dist * factor);
-                int bidx = (int)roundf((float)ORI_NBINS * (theta + F_PI) / F_PI2);
+                /* reference SASS: (theta + pi) * 36 * RN(1 / 2pi) (the constant division is folded) */
+                int bidx = (int)roundf(((theta + F_PI) * (float)ORI_NBINS) * 0.15915493667125701904f);
                 if (bidx == ORI_NBINS) bidx = 0;
                 if (bidx < 0 || bidx > ORI_NBINS) continue;
                 hist[bidx] += weight;

@@ -53,7 +53,7 @@ EXPORTS = ["ps_abi_version", "ps_config_default", "ps_gauss_tables_compute", "ps
            "ps_last_error", "ps_submit_u8", "ps_submit_f32", "ps_submit_dev_u8", "ps_counts", "ps_download",
            "ps_sync", "ps_debug_plane", "ps_debug_extrema", "ps_slot_geometry", "ps_set_timing", "ps_stage_ms",
            "ps_launch_count", "ps_slot_stream", "ps_run_pyramid_only", "ps_run_level_only", "ps_host_alloc", "ps_host_free",
-           "ps_download_dev", "ps_dev_alloc", "ps_dev_free", "ps_dev_to_host", "ps_wait_input"]
+           "ps_download_dev", "ps_dev_alloc", "ps_dev_free", "ps_dev_to_host", "ps_wait_input", "ps_match", "ps_pointer_device", "ps_host_to_dev"]
 
 _lib = None
 
@@ -83,6 +83,9 @@ def load_library():
     L.ps_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.ps_sync.argtypes = [C.c_void_p, C.c_int]
     L.ps_wait_input.argtypes = [C.c_void_p, C.c_int]
+    L.ps_match.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    L.ps_pointer_device.argtypes = [C.c_void_p]
+    L.ps_host_to_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.ps_debug_plane.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     L.ps_debug_extrema.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     L.ps_slot_geometry.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
@@ -354,8 +357,12 @@ class FeaturesDev:
     def getDescriptors(self): return self._pd
     def getReverseMap(self): return self._pr
 
-    def match(self, other):
-        raise PopSiftError("FeaturesDev.match (brute-force matcher) is not implemented")
+    MATCH_AUTO, MATCH_EXACT, MATCH_TENSOR = 0, 1, 2
+
+    def match(self, other: "FeaturesDev", flags: int = 0) -> np.ndarray:
+        """FeaturesDev::match (reference features.cu:282-304) without the printing: (n_desc, 3) int32 rows
+        (best index, second index, accept) of every descriptor of self among other's (C ABI ps_match)."""
+        return match_descriptors_dev(self._lib, self._pd, self._nd, other._pd, other._nd, flags)
 
     def to_host(self):
         """(features, descriptors, reverse map) copied to numpy arrays; desc_ptr still holds DEVICE addresses"""
@@ -374,6 +381,45 @@ class FeaturesDev:
                 if p:
                     lib.ps_dev_free(p)
             self._pf = self._pd = self._pr = None
+
+
+def match_descriptors_dev(lib, d_left, n_left, d_right, n_right, flags=0, device=None) -> np.ndarray:
+    out = np.zeros((max(n_left, 0), 3), np.int32)
+    if n_left <= 0:
+        return out
+    d_out = lib.ps_dev_alloc(out.nbytes)
+    if not d_out:
+        raise PopSiftError("ps_dev_alloc failed")
+    try:
+        dev = device if device is not None else max(0, lib.ps_pointer_device(d_left))
+        rc = lib.ps_match(dev, d_left, n_left, d_right, n_right, d_out, flags)
+        if rc != 0:
+            raise PopSiftError("ps_match error %d: %s" % (rc, lib.ps_last_error(None).decode()))
+        if lib.ps_dev_to_host(out.ctypes.data, d_out, out.nbytes) != 0:
+            raise PopSiftError("device -> host copy failed")
+    finally:
+        lib.ps_dev_free(d_out)
+    return out
+
+
+def match_descriptors(left: np.ndarray, right: np.ndarray, flags=0, device=0) -> np.ndarray:
+    """host arrays (n, 128) float32 -> (n_left, 3) int32 (best, second, accept); copies through device memory"""
+    lib = load_library()
+    left = np.ascontiguousarray(left, np.float32); right = np.ascontiguousarray(right, np.float32)
+    import ctypes as _C
+    bufs = []
+    try:
+        for a in (left, right):
+            p = lib.ps_dev_alloc(max(a.nbytes, 4))
+            if not p:
+                raise PopSiftError("ps_dev_alloc failed")
+            bufs.append(p)
+            if a.nbytes and lib.ps_host_to_dev(p, a.ctypes.data, a.nbytes) != 0:
+                raise PopSiftError("host -> device copy failed")
+        return match_descriptors_dev(lib, bufs[0], len(left), bufs[1], len(right), flags, device)
+    finally:
+        for p in bufs:
+            lib.ps_dev_free(p)
 
 
 class SiftJob:

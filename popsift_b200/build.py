@@ -26,9 +26,11 @@ NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC",
               "--fmad=false",   # no implicit contraction anywhere; every fma in the kernels is explicit
               "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 
-LIB_SOURCES = ["ps_tables.cpp", "ps_ctx.cu", "k_pyramid.cu", "k_pyramid_march.cu", "k_extrema.cu", "k_filter.cu", "k_orient.cu", "k_desc.cu",
-               "host/sift_conf.cpp", "host/features.cpp", "host/popsift.cpp", "host/device_prop.cpp"]
+LIB_SOURCES = ["ps_tables.cpp", "ps_ctx.cu", "k_pyramid.cu", "k_pyramid_march.cu", "tma_util.cu", "k_match.cu", "k_extrema.cu", "k_filter.cu", "k_orient.cu", "k_desc.cu",
+               "host/sift_conf.cpp", "host/features.cpp", "host/popsift.cpp", "host/device_prop.cpp", "host/log_dump.cpp"]
 DEMO_SOURCES = ["app/popsift_demo.cpp", "app/pgmread.cpp"]
+MATCH_SOURCES = ["app/popsift_match.cpp"]            # + app/pgmread.cpp
+MATCH = os.path.join(BIN_DIR, "popsift-match")
 API_CHECK = os.path.join(BIN_DIR, "api_check")
 API_CHECK_SRC = os.path.join(ROOT, "tests", "cpp", "api_check.cpp")
 API_BENCH = os.path.join(BIN_DIR, "api_bench")
@@ -60,7 +62,7 @@ def build(verbose: bool = False, force: bool = False) -> str:
     hdrs = _headers()
     objs = []
     procs = []
-    for src in LIB_SOURCES + DEMO_SOURCES:
+    for src in LIB_SOURCES + DEMO_SOURCES + MATCH_SOURCES:
         sp = os.path.join(CSRC, src)
         if not os.path.exists(sp):
             continue
@@ -84,6 +86,10 @@ def build(verbose: bool = False, force: bool = False) -> str:
         subprocess.check_call(["nvcc"] + ARCH + ["-shared", "-o", LIB] + lib_objs + ["-lpthread"])
     if demo_objs and (force or _newer(DEMO, demo_objs + [LIB])):
         subprocess.check_call(["nvcc"] + ARCH + ["-o", DEMO] + demo_objs +
+                              ["-L" + LIB_DIR, "-lpopsift_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../lib", "-lpthread"])
+    match_objs = [o for s, o in objs if s in MATCH_SOURCES or s == "app/pgmread.cpp"]
+    if len(match_objs) == 2 and (force or _newer(MATCH, match_objs + [LIB])):
+        subprocess.check_call(["nvcc"] + ARCH + ["-o", MATCH] + match_objs +
                               ["-L" + LIB_DIR, "-lpopsift_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../lib", "-lpthread"])
     if os.path.exists(API_CHECK_SRC) and (force or _newer(API_CHECK, [API_CHECK_SRC, LIB] + hdrs)):
         # a plain host compiler is enough for a caller of the C++ API: no CUDA in the translation unit

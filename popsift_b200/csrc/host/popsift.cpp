@@ -15,6 +15,7 @@
 #include "popsift/popsift.h"
 #include "popsift_b200.h"
 #include "pinned_pool.h"
+#include "log_dump.h"
 
 #include <algorithm>
 #include <condition_variable>
@@ -87,6 +88,9 @@ struct PopSift::Pipe
     std::vector<SiftJob*>     in_slot;
     int                       next_slot = 0;
     bool                      octaves_fixed = false;
+    bool                      log_all = false;      // Config::LogMode::All, fixed when the context is created
+    int                       log_levels = 3;
+    float                     log_upscale = 1.0f;
 };
 
 namespace {
@@ -129,6 +133,11 @@ PopSift::PopSift(ImageMode imode, int device) : _pipe(new Pipe), _image_mode(imo
                 rc = ps_download(p->ctx, s, reinterpret_cast<ps_feature*>(fh->getFeatures()),
                                  reinterpret_cast<ps_descriptor*>(fh->getDescriptors()));
                 if (rc != PS_OK) { delete fh; fail_job(job, ps_last_error(p->ctx)); return; }
+                if (p->log_all) {
+                    // --log (reference popsift.cpp:330-337): plane and descriptor dumps of this image
+                    popsift::detail::dump_slot_planes(p->ctx, s, p->log_levels, "pyramid");
+                    popsift::detail::dump_descriptors(*fh, p->log_upscale, "pyramid");
+                }
             } catch (const std::exception& e) { delete fh; fail_job(job, e.what()); return; }
             job->setFeatures(fh);
         };
@@ -170,6 +179,9 @@ PopSift::PopSift(ImageMode imode, int device) : _pipe(new Pipe), _image_mode(imo
                     }
                     _config.toC(c);
                     slots = p->slots;
+                    p->log_all = _config.getLogMode() == Config::All;
+                    p->log_levels = std::max(2, _config.levels);
+                    p->log_upscale = _config.getUpscaleFactor();
                 }
                 p->ctx_w = std::max(w, p->ctx_w); p->ctx_h = std::max(h, p->ctx_h);
                 p->ctx = ps_create(_device, &c, p->ctx_w, p->ctx_h, slots);

@@ -115,7 +115,9 @@ orientation_kernel(PyramidView pyr, Consts k, const InitialExtremum* __restrict_
                     const float grad = hypotf(gdx, gdy);
                     const float theta = atan2f(gdy, gdx);
                     weight = __fmul_rn(grad, expf(__fmul_rn((float)sq_dist, factor)));
-                    bidx = (int)roundf(__fdividef(__fmul_rn((float)kOriBins, __fadd_rn(theta, kPi)), kPi2));
+                    // reference SASS (ori_par): (theta + pi) * 36 * 0.15915494 -- the division by the constant 2 pi of
+                    // __fdividef(36 * (theta + pi), M_PI2) is folded into a multiplication by RN(1 / 2pi)
+                    bidx = (int)roundf(__fmul_rn(__fmul_rn(__fadd_rn(theta, kPi), (float)kOriBins), 0.15915493667125701904f));
                     if (bidx == kOriBins) bidx = 0;
                     if (bidx > kOriBins) bidx = -1;
                 }

@@ -73,7 +73,11 @@ inline Partition make_partition(int W, int H, int TW, int Q, int slots, bool uni
     int n = slots / S;
     if (n < 1) n = 1;
     int u = (C + n - 1) / n;
-    if (u < 4) u = 4;                              // keep the 2R-row warm-up a small fraction of the work
+    // Small planes (fewer chunk-rows than slots per strip) are latency-bound, not work-bound: a CTA that marches 4
+    // chunk-rows plus its 2R warm-up rows takes 6 serial chunks where one chunk-row per CTA takes 3, and the extra
+    // warm-up work runs on SMs that would otherwise idle.  (Round 1 kept u >= 4: octaves 2..4 of the 4K pyramid then
+    // ran 10-20 us per launch at 6-11 % of the warps.)
+    if (u < 1) u = 1;
     p.strips = S;
     p.uh = u;
     p.nh = (C + u - 1) / u;

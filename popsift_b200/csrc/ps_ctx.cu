@@ -621,6 +621,35 @@ extern "C" void ps_dev_free(void* p)
     if (p) cudaFree(p);
 }
 
+extern "C" int ps_host_to_dev(void* dst_dev, const void* src_host, size_t bytes)
+{
+    if (bytes == 0) return PS_OK;
+    if (!dst_dev || !src_host) return PS_ERR_ARG;
+    if (cudaMemcpy(dst_dev, src_host, bytes, cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); return PS_ERR_CUDA; }
+    return PS_OK;
+}
+
+extern "C" int ps_pointer_device(const void* dev_ptr)
+{
+    cudaPointerAttributes at{};
+    if (!dev_ptr || cudaPointerGetAttributes(&at, dev_ptr) != cudaSuccess || at.type != cudaMemoryTypeDevice) { cudaGetLastError(); return -1; }
+    return at.device;
+}
+
+extern "C" int ps_match(int device, const ps_descriptor* d_left, int n_left, const ps_descriptor* d_right, int n_right,
+                        int32_t* d_out, int flags)
+{
+    if (n_left < 0 || n_right < 0 || (n_left > 0 && (!d_left || !d_out)) || (n_right > 0 && !d_right)) return PS_ERR_ARG;
+    if (n_left == 0) return PS_OK;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return PS_ERR_CUDA; }
+    const char* err = nullptr;
+    const int n = run_match(d_left, n_left, d_right, n_right, d_out, flags, nullptr, &err);
+    if (n < 0) { g_create_error = err ? err : "ps_match failed"; return PS_ERR_CUDA; }
+    const cudaError_t e = cudaStreamSynchronize(nullptr);
+    if (e != cudaSuccess) { g_create_error = std::string("ps_match: ") + cudaGetErrorString(e); cudaGetLastError(); return PS_ERR_CUDA; }
+    return PS_OK;
+}
+
 extern "C" int ps_dev_to_host(void* dst_host, const void* src_dev, size_t bytes)
 {
     if (bytes == 0) return PS_OK;

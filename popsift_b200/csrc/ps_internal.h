@@ -148,4 +148,8 @@ int launch_prep_features(const Consts& k, const ps_extremum* ext, ps_feature* fe
 // device copy of the Feature records: desc[] become pointers into `desc` (first index is in pad_)
 int launch_fix_feature_pointers(ps_feature* feat, ps_descriptor* desc, int n, cudaStream_t st);
 
+// brute-force 2-NN matcher (k_match.cu; reference features.cu:165-304): out = n_left x (best, second, accept), device
+// memory; asynchronous on `st`; returns the number of kernels launched or -1 (*err set)
+int run_match(const ps_descriptor* l, int nl, const ps_descriptor* r, int nr, int32_t* out, int flags, cudaStream_t st, const char** err);
+
 } // namespace psb

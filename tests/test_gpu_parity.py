@@ -457,8 +457,8 @@ def test_matching_mode_device_results_equal_host_results():
     # reverse map: descriptor d belongs to feature rev[d], which lists it among its orientations
     for d in range(len(desc)):
         assert d in didx[rev[d]]
-    with pytest.raises(api.PopSiftError):
-        fd.match(fd)
+    m = fd.match(fd)                                   # every descriptor's nearest neighbour in its own set: itself
+    assert m.shape == (len(desc), 3) and (m[:, 0] == np.arange(len(desc))).mean() > 0.9
     ps.uninit(); pm.uninit()
 
 
@@ -498,3 +498,119 @@ def test_grid_filter_1280_and_unsupported_options_are_refused():
         setter(c)
         with pytest.raises(api.PopSiftError):
             api.PopSift(c, max_width=64, max_height=64)
+
+
+def _dev_rows(feat, desc):
+    out = []
+    for f in feat:
+        for k in range(int(f["num_ori"])):
+            out.append((int(f["octave"]), float(f["x"]), float(f["y"]), float(f["sigma"]), float(f["ori"][k])) + tuple(desc[int(f["desc_idx"][k])]))
+    return out
+
+
+@pytest.mark.parametrize("stem,mode,norm,imgs", [("match_640", "popsift", "rootsift", "f640"), ("match_aff12", "vlfeat", "classic", "aff")])
+def test_matching_mode_and_matcher_vs_reference(stem, mode, norm, imgs):
+    """Config::MatchingMode + FeaturesDev::match against the reference's own run (tests/golden/match_*.npz: the
+    device-resident features / descriptors / reverse maps ref_dump copied back, and its match() output):
+      * getDev results (clone_device_descriptors, sift_pyramid.cu:324-362) equal the reference's, reverse map included;
+      * ps_match on the REFERENCE's descriptors gives the reference's (best, second, accept) for every descriptor,
+        with the tensor-core pass and with the CUDA-core kernel;
+      * matching our own device results gives the same accepted pairs (in keypoint terms)."""
+    import match_oracle as mo
+    z = np.load(os.path.join(G, stem + ".npz"))
+    L = z["lines"]
+    want = np.stack([L["r1"], L["r2"], L["accept"].astype(np.int32)], 1)
+    for flags in (api.FeaturesDev.MATCH_EXACT, api.FeaturesDev.MATCH_TENSOR, api.FeaturesDev.MATCH_AUTO):
+        got = api.match_descriptors(z["desc0"], z["desc1"], flags)
+        assert np.array_equal(got, want), (flags, int((got != want).any(1).sum()))
+    # our own MatchingMode results
+    if imgs == "f640":
+        ims = [make_frame(640, 480, 1), make_frame(640, 480, 2)]
+    else:
+        from popsift_b200.synth import affine_set
+        ims = [im for im, _ in affine_set()[:2]]
+    h, w = ims[0].shape
+    pm = api.PopSift(mk_cfg(mode, norm), mode=api.Config.MatchingMode, max_width=w, max_height=h, slots=2)
+    fds = [pm.enqueue(w, h, im).getDev() for im in ims]
+    ours = []
+    for k, fd in enumerate(fds):
+        feat, desc, rev = fd.to_host()
+        rf, rd, rrev = z["feat%d" % k], z["desc%d" % k], z["rev%d" % k]
+        assert (len(feat), len(desc)) == (len(rf), len(rd))
+        base = fd.getDescriptors()
+        didx = np.full((len(feat), 4), -1, np.int64)
+        for q in range(4):
+            m = feat["num_ori"] > q
+            didx[m, q] = (feat["desc_ptr"][m, q].astype(np.int64) - base) // 512
+        mine = np.zeros(len(feat), dtype=ol.REF_FEATURE_DTYPE)
+        for name in ("octave", "x", "y", "sigma", "num_ori", "ori"):
+            mine[name] = feat[name]
+        mine["desc_idx"] = didx
+        a, b = sorted(_dev_rows(mine, desc)), sorted(_dev_rows(rf, rd))
+        assert len(a) == len(b)
+        ka = np.array([r[:5] for r in a]); kb = np.array([r[:5] for r in b])
+        assert np.array_equal(ka, kb)                                             # same keypoints, same orientations
+        assert np.abs(np.array([r[5:] for r in a]) - np.array([r[5:] for r in b])).max() < 1e-3
+        for d in range(len(desc)):                                                 # reverse map semantics
+            assert d in didx[rev[d]]
+        ours.append((mine, desc, rev))
+    m = fds[0].match(fds[1])
+    # accepted pairs as (left keypoint, right keypoint) sets
+    def pairs(feat0, rev0, feat1, rev1, mm):
+        out = set()
+        for i in np.nonzero(mm[:, 2])[0]:
+            a, b = feat0[rev0[i]], feat1[rev1[mm[i, 0]]]
+            out.add((float(a["x"]), float(a["y"]), float(b["x"]), float(b["y"])))
+        return out
+    po = pairs(ours[0][0], ours[0][2], ours[1][0], ours[1][2], m)
+    pr = pairs(z["feat0"], z["rev0"], z["feat1"], z["rev1"], want)
+    assert len(po ^ pr) <= max(1, len(pr) // 50), (len(po), len(pr), len(po ^ pr))
+    pm.uninit()
+
+
+def test_matcher_large_random_sets_tensor_equals_exact():
+    """n = 5000 x 7000 unit descriptors with planted near-duplicates: the tcgen05 pass (tf32 x 3 + exact re-rank of
+    four candidates) and the CUDA-core kernel (reference evaluation order) agree on every row."""
+    rng = np.random.default_rng(3)
+    def unit(n):
+        d = np.abs(rng.normal(size=(n, 128))).astype(np.float32)
+        return d / np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    left, right = unit(5000), unit(7000)
+    right[100:600] = left[:500] + rng.normal(scale=0.01, size=(500, 128)).astype(np.float32)      # true matches
+    a = api.match_descriptors(left, right, api.FeaturesDev.MATCH_EXACT)
+    b = api.match_descriptors(left, right, api.FeaturesDev.MATCH_TENSOR)
+    assert np.array_equal(a, b), int((a != b).any(1).sum())
+    assert a[:500, 2].mean() > 0.9 and (a[:500, 0] == np.arange(100, 600)).mean() > 0.99
+    # tails: sizes that are not multiples of the tile, tiny right sets
+    for nl, nr in ((1, 1), (3, 2), (129, 257), (300, 1000)):
+        l, r = unit(nl), unit(nr)
+        assert np.array_equal(api.match_descriptors(l, r, api.FeaturesDev.MATCH_EXACT), api.match_descriptors(l, r, api.FeaturesDev.MATCH_TENSOR)), (nl, nr)
+
+
+def test_popsift_match_cli_and_log_dumps(tmp_path):
+    """popsift-match -l a.pgm -r b.pgm prints the reference's lines (match.cpp:262-271, features.cu:229-277); popsift-demo
+    --log writes the reference's plane dumps (sift_octave.cu:111-188), which equal ps_debug_plane bit for bit."""
+    exe = os.path.join(BIN, "popsift-match")
+    assert os.path.exists(exe)
+    write_pgm(str(tmp_path / "a.pgm"), make_frame(640, 480, 1))
+    write_pgm(str(tmp_path / "b.pgm"), make_frame(640, 480, 2))
+    r = subprocess.run([exe, "-l", "a.pgm", "-r", "b.pgm"], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    z = np.load(os.path.join(G, "match_640.npz"))
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith(("accept", "reject"))]
+    assert len(lines) == len(z["lines"])
+    assert sum(ln.startswith("accept") for ln in lines) == int(z["lines"]["accept"].sum())
+    assert "Number of descriptors: %d" % len(z["desc0"]) in r.stdout
+    # --log
+    demo = os.path.join(BIN, "popsift-demo")
+    img = make_frame(256, 192, 3)
+    write_pgm(str(tmp_path / "c.pgm"), img)
+    r = subprocess.run([demo, "-i", "c.pgm", "--log", "--vlfeat-mode", "--norm-mode", "classic"], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    meta = json.loads(bytes(np.load(os.path.join(G, "planes_f256.npz"))["meta"]).decode())
+    for key, m in meta.items():
+        kind, oc, l = key.split("_")
+        fn = tmp_path / ("dir-octave-dump" if kind == "g" else "dir-dog-dump") / (("" if kind == "g" else "d-") + "pyramid-o-%s-l-%s.dump" % (oc, l))
+        p = ol.read_ref_dump(str(fn))
+        assert hashlib.sha256(p.tobytes()).hexdigest() == m["sha256"], key
+    assert (tmp_path / "dir-desc" / "desc-pyramid.txt").exists() and (tmp_path / "dir-fpt" / "desc-pyramid.txt").exists()
