@@ -285,6 +285,7 @@ ori_scatter_kernel(int num_octaves, Consts k, ps_extremum* __restrict__ ext, int
     if (b == last && threadIdx.x == 0) {
         ct->ext_total = total;
         ct->ori_total = min(base + block_total, k.desc_capacity);
+        ct->ori_needed = base + block_total;
         int raw = 0;
         const int* counts = ct->filtered ? ct->ext_ct_f : ct->ext_ct;
         for (int o = 0; o < num_octaves; ++o) raw += min(counts[o], k.max_extrema);

@@ -61,6 +61,7 @@ struct Slot {
     cudaEvent_t done = nullptr;
     cudaEvent_t in_done = nullptr;   // recorded after the host -> device copy of the slot's input image
     bool in_pending = false;         // in_done has been recorded at least once
+    int ext_cap = 0, desc_cap = 0;   // capacity of d_ext / d_feat and of d_desc / d_f2e; grown on demand (regrow_slot)
     bool submitted = false;
     bool is_float = false;
     int w = 0, h = 0;
@@ -253,13 +254,79 @@ int psb::sm_count()
     return cached[dev];
 }
 
+// the slot's view of the constants: its own (growable) capacities
+static Consts slot_consts(const ps_ctx* ctx, const Slot& s)
+{
+    Consts k = ctx->k;
+    k.ext_capacity = s.ext_cap;
+    k.desc_capacity = s.desc_cap;
+    return k;
+}
+
+// orientation -> descriptors -> Feature records -> counters to the host; everything after the (optional) grid filter
+static int run_tail(ps_ctx* ctx, Slot& s, bool tm)
+{
+    const Consts k = slot_consts(ctx, s);
+    PS_CUDA(ctx, cudaMemsetAsync(s.d_ori_slice, 0, sizeof(int) * ((size_t)s.ext_cap / PS_ORI_SLICE + 1), s.stream));
+    int n = launch_orientation(s.view, k, s.d_iext, s.d_iext_f, s.d_ext, s.d_f2e, s.d_ori_slice, s.d_ct, s.stream);
+    if (tm) PS_CUDA(ctx, cudaEventRecord(s.ev[4], s.stream));
+    n += launch_descriptors(s.view, k, s.d_ext, s.d_f2e, s.d_desc, s.d_ct, s.stream);
+    n += launch_prep_features(k, s.d_ext, s.d_feat, s.d_ct, s.stream);
+    if (tm) PS_CUDA(ctx, cudaEventRecord(s.ev[5], s.stream));
+    ctx->launches += n;
+    PS_CUDA(ctx, cudaGetLastError());
+    PS_CUDA(ctx, cudaMemcpyAsync(s.h_ct, s.d_ct, sizeof(Counters), cudaMemcpyDeviceToHost, s.stream));
+    PS_CUDA(ctx, cudaEventRecord(s.done, s.stream));
+    return PS_OK;
+}
+
+// More extrema or descriptors than the slot's buffers hold: grow them and run the tail of the pipeline again on the
+// planes and initial extrema that are still in the slot (reference: Pyramid::reallocExtrema, sift_pyramid.cu:179-209,
+// called from the orientation / descriptor stages).  Rare: the buffers start at 2 x max_extrema records.
+static int regrow_slot(ps_ctx* ctx, Slot& s)
+{
+    for (int round = 0; round < 3 && s.h_ct->overflow; ++round) {
+        const Counters& c = *s.h_ct;
+        const int* counts = c.filtered ? c.ext_ct_f : c.ext_ct;
+        long long need_ext = 0;
+        for (int o = 0; o < s.num_octaves; ++o) need_ext += std::min(counts[o], ctx->k.max_extrema);
+        const long long need_desc = c.ori_needed;
+        if (need_ext > s.ext_cap) {
+            const int cap = (int)std::min<long long>(need_ext + need_ext / 8 + 1024, 0x7ffffff0);
+            cudaFree(s.d_ext); cudaFree(s.d_feat); cudaFree(s.d_ori_slice);
+            s.d_ext = nullptr; s.d_feat = nullptr; s.d_ori_slice = nullptr; s.ext_cap = 0;
+            PS_CUDA(ctx, cudaMalloc(&s.d_ext, sizeof(ps_extremum) * (size_t)cap));
+            PS_CUDA(ctx, cudaMalloc(&s.d_feat, sizeof(ps_feature) * (size_t)cap));
+            PS_CUDA(ctx, cudaMalloc(&s.d_ori_slice, sizeof(int) * ((size_t)cap / PS_ORI_SLICE + 1)));
+            s.ext_cap = cap;
+        }
+        const long long want_desc = std::max<long long>(need_desc, (c.overflow & 1) ? need_ext * 5 / 4 : 0);
+        if (want_desc > s.desc_cap) {
+            const int cap = (int)std::min<long long>(want_desc + want_desc / 8 + 1024, 0x3ffffff0);
+            cudaFree(s.d_desc); cudaFree(s.d_f2e);
+            s.d_desc = nullptr; s.d_f2e = nullptr; s.desc_cap = 0;
+            PS_CUDA(ctx, cudaMalloc(&s.d_desc, sizeof(ps_descriptor) * (size_t)cap));
+            PS_CUDA(ctx, cudaMalloc(&s.d_f2e, sizeof(int) * (size_t)cap));
+            s.desc_cap = cap;
+        }
+        // reset what the tail writes (the per-octave extremum counts and the filter's verdict stay)
+        Counters reset = c;
+        reset.ext_total = reset.ori_total = reset.ori_needed = reset.overflow = reset.work_ori = reset.work_desc = 0;
+        PS_CUDA(ctx, cudaMemcpyAsync(s.d_ct, &reset, sizeof(Counters), cudaMemcpyHostToDevice, s.stream));
+        PS_CUDA(ctx, cudaStreamSynchronize(s.stream));          // `reset` lives on this stack frame
+        int rc = run_tail(ctx, s, false);
+        if (rc != PS_OK) return rc;
+        PS_CUDA(ctx, cudaEventSynchronize(s.done));
+    }
+    return PS_OK;
+}
+
 static int submit_common(ps_ctx* ctx, Slot& s)
 {
     const bool tm = ctx->timing;
     int rc;
     PS_CUDA(ctx, cudaMemsetAsync(s.d_ct, 0, sizeof(Counters), s.stream));
     PS_CUDA(ctx, cudaMemsetAsync(s.cand_cnt, 0, s.cand_cnt_bytes, s.stream));
-    PS_CUDA(ctx, cudaMemsetAsync(s.d_ori_slice, 0, sizeof(int) * ((size_t)ctx->k.ext_capacity / PS_ORI_SLICE + 1), s.stream));
     if (tm) PS_CUDA(ctx, cudaEventRecord(s.ev[1], s.stream));
     if ((rc = run_pyramid(ctx, s)) != PS_OK) return rc;
     if (tm) PS_CUDA(ctx, cudaEventRecord(s.ev[2], s.stream));
@@ -271,15 +338,8 @@ static int submit_common(ps_ctx* ctx, Slot& s)
         n += launch_grid_filter(s.view, ctx->k, fc, s.d_iext, s.d_iext_f, s.d_keep, (size_t)s.num_octaves * ctx->k.max_extrema,
                                 s.d_plan, s.d_ct, s.stream);
     }
-    n += launch_orientation(s.view, ctx->k, s.d_iext, s.d_iext_f, s.d_ext, s.d_f2e, s.d_ori_slice, s.d_ct, s.stream);
-    if (tm) PS_CUDA(ctx, cudaEventRecord(s.ev[4], s.stream));
-    n += launch_descriptors(s.view, ctx->k, s.d_ext, s.d_f2e, s.d_desc, s.d_ct, s.stream);
-    n += launch_prep_features(ctx->k, s.d_ext, s.d_feat, s.d_ct, s.stream);
-    if (tm) PS_CUDA(ctx, cudaEventRecord(s.ev[5], s.stream));
     ctx->launches += n;
-    PS_CUDA(ctx, cudaGetLastError());
-    PS_CUDA(ctx, cudaMemcpyAsync(s.h_ct, s.d_ct, sizeof(Counters), cudaMemcpyDeviceToHost, s.stream));
-    PS_CUDA(ctx, cudaEventRecord(s.done, s.stream));
+    if ((rc = run_tail(ctx, s, tm)) != PS_OK) return rc;
     s.submitted = true;
     return PS_OK;
 }
@@ -372,11 +432,12 @@ extern "C" ps_ctx* ps_create(int device, const ps_config* cfg, int max_w, int ma
     k.edge_limit = ctx->cfg.edge_limit;
     k.threshold = ctx->tab.peak_threshold;
     k.max_extrema = ctx->cfg.max_extrema;
-    // capacity of one slot: the reference starts with max_extrema Extremum records and
-    // max(2*max_extrema, 1.25*max_extrema) descriptors and grows on demand (sift_pyramid.cu:136-209);
-    // here the capacity is fixed at create time and an overflow is reported by ps_counts.
+    // initial capacity of one slot: like the reference (max_extrema Extremum records and max(2, 1.25) * max_extrema
+    // descriptors, sift_pyramid.cu:136-159) it grows on demand -- ps_counts re-runs orientation and descriptors
+    // with larger buffers when a frame overflows them (regrow_slot).  POPSIFT_B200_INIT_CAP overrides (tests).
     k.ext_capacity = 2 * k.max_extrema;
     k.desc_capacity = 2 * k.max_extrema;
+    if (const char* e = getenv("POPSIFT_B200_INIT_CAP")) { const int c = atoi(e); if (c > 0) k.ext_capacity = k.desc_capacity = c; }
     k.norm_multi = ctx->cfg.norm_multi;
     k.norm_mode = ctx->cfg.norm_mode;
     k.sift_mode = ctx->cfg.sift_mode;
@@ -400,6 +461,7 @@ extern "C" ps_ctx* ps_create(int device, const ps_config* cfg, int max_w, int ma
             PS_TRY(cudaMalloc(&s.d_keep, (size_t)ctx->max_octaves * k.max_extrema));
             PS_TRY(cudaMalloc(&s.d_plan, sizeof(FilterPlan)));
         }
+        s.ext_cap = k.ext_capacity; s.desc_cap = k.desc_capacity;
         PS_TRY(cudaMalloc(&s.d_ext, sizeof(ps_extremum) * (size_t)k.ext_capacity));
         PS_TRY(cudaMalloc(&s.d_feat, sizeof(ps_feature) * (size_t)k.ext_capacity));
         PS_TRY(cudaMalloc(&s.d_desc, sizeof(ps_descriptor) * (size_t)k.desc_capacity));
@@ -512,6 +574,11 @@ extern "C" int ps_counts(ps_ctx* ctx, int slot, int32_t* n_feat, int32_t* n_desc
     if (!s->submitted) return ctx->fail(PS_ERR_STATE, "ps_counts: nothing submitted to slot %d", slot);
     PS_CUDA(ctx, cudaSetDevice(ctx->device));
     PS_CUDA(ctx, cudaEventSynchronize(s->done));
+    if (s->h_ct->overflow) {
+        // more extrema / descriptors than the slot's buffers hold: grow them and redo orientation + descriptors
+        const int rc = regrow_slot(ctx, *s);
+        if (rc != PS_OK) return rc;
+    }
     if (n_feat) *n_feat = s->h_ct->ext_total;
     if (n_desc) *n_desc = s->h_ct->ori_total;
     if (s->h_ct->overflow)

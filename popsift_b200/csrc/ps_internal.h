@@ -31,7 +31,8 @@ struct Counters {
     int work_desc;
     int filtered;              // the grid filter fired: the orientation stage reads ext_ct_f / the filtered array
     int ext_ct_f[kMaxOctaves]; // extrema per octave that survived the grid filter
-    int pad_[2];
+    int ori_needed;            // descriptors the image has (may exceed desc_capacity: the host then grows the buffers)
+    int pad_[1];
 };
 
 // grid filter (k_filter.cu; reference s_filtergrid.cu:112-325)
