@@ -389,35 +389,156 @@ cand_prefix_kernel(const int* __restrict__ counts, int n, int* __restrict__ pref
     if (threadIdx.x == 0) prefix[n] = carry;
 }
 
+// Region-driven form (default).  A list region = the candidates one block of one level kernel reported; block b of this
+// kernel takes regions b, b + gridDim.x, ... (no prefix sum, no search: a region's octave, level and list follow from
+// its index), its 8 warps take the region's samples 32 at a time.  The three tests of a sample have very different
+// survival rates, so each is run on full warps of survivors:
+//   stage 1  (every sample)   threshold re-test + the 8 in-plane neighbours           ~10 % survive
+//   stage 2  (per-warp queue) the 18 neighbours of the planes below and above         ~0.6 % survive
+//   stage 3  (per-block queue) refine<MODE> + append
+// Survivors are compacted with a warp ballot into shared-memory queues; a queue is served when it holds a full warp
+// (stage 2) or when the block has run out of regions (stage 3 and the stage-2 remainders).
+constexpr int kQ2 = 64;            // stage-2 queue entries per warp (< 32 pending + <= 32 new)
+constexpr int kQ3 = 1024;          // stage-3 queue entries per block; overflowing survivors are refined at once
+
+struct Q2Entry { unsigned xy; unsigned ol; };      // x | y << 16 ;  octave | level << 8 | is_max << 16
+
+template <int MODE>
+__device__ __forceinline__ bool stage1(const DogOct& ov, int level, float thr, int x, int y, bool& is_max)
+{
+    const int W = ov.w, H = ov.h;
+    bool inside = x >= 1 && x <= W - 2 && y >= 1 && y <= H - 2;
+    if (MODE == PS_MODE_OPENCV) inside = inside && !(x < 5 || x >= W - 5) && !(y < 5 || y >= H - 5);
+    if (!inside) return false;
+    const float* pc = ov.dog + (size_t)level * ov.plane + (size_t)y * ov.pitch + x;
+    const float* ra = pc - ov.pitch;
+    const float* rb = pc + ov.pitch;
+    // all nine loads are issued together: the test is bound by memory latency, not by instructions
+    const float c = __ldg(pc);
+    const float n0 = __ldg(pc - 1), n1 = __ldg(pc + 1);
+    const float n2 = __ldg(ra - 1), n3 = __ldg(ra), n4 = __ldg(ra + 1);
+    const float n5 = __ldg(rb - 1), n6 = __ldg(rb), n7 = __ldg(rb + 1);
+    if (!(fabsf(c) >= thr)) return false;
+    const float mx = fmaxf(fmaxf(fmaxf(n0, n1), fmaxf(n2, n3)), fmaxf(fmaxf(n4, n5), fmaxf(n6, n7)));
+    const float mn = fminf(fminf(fminf(n0, n1), fminf(n2, n3)), fminf(fminf(n4, n5), fminf(n6, n7)));
+    is_max = c > mx;
+    return is_max || c < mn;
+}
+
+__device__ __forceinline__ bool stage2(const DogOct& ov, int level, int x, int y, bool is_max, float& cval)
+{
+    const float* pc = ov.dog + (size_t)level * ov.plane + (size_t)y * ov.pitch + x;
+    const float c = __ldg(pc);
+    cval = c;
+    float mx = -INFINITY, mn = INFINITY;
+#pragma unroll
+    for (int dz = -1; dz <= 1; dz += 2) {
+        const float* p = dz < 0 ? pc - ov.plane : pc + ov.plane;
+        const float* ra = p - ov.pitch;
+        const float* rb = p + ov.pitch;
+        const float n0 = __ldg(p - 1), n1 = __ldg(p), n2 = __ldg(p + 1);
+        const float n3 = __ldg(ra - 1), n4 = __ldg(ra), n5 = __ldg(ra + 1);
+        const float n6 = __ldg(rb - 1), n7 = __ldg(rb), n8 = __ldg(rb + 1);
+        mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(n0, n1), fmaxf(n2, n3)), fmaxf(fmaxf(n4, n5), fmaxf(fmaxf(n6, n7), n8))));
+        mn = fminf(mn, fminf(fminf(fminf(n0, n1), fminf(n2, n3)), fminf(fminf(n4, n5), fminf(fminf(n6, n7), n8))));
+    }
+    return is_max ? c > mx : c < mn;
+}
+
+template <int MODE>
+__device__ __forceinline__ void stage3(const PyramidView& pyr, const Consts& k, const Q2Entry q, float cval,
+                                       InitialExtremum* __restrict__ iext, Counters* ct)
+{
+    const int o = (int)(q.ol & 0xffu), level = (int)((q.ol >> 8) & 0xffu);
+    const OctaveView& ov = pyr.oct[o];
+    DogView dv;
+    dv.base = ov.dog; dv.w = ov.w; dv.h = ov.h; dv.pitch = ov.pitch; dv.plane = ov.plane;
+    dv.nplanes = pyr.levels + 2;
+    InitialExtremum e;
+    e.xpos = e.ypos = e.sigma = 0.f; e.lpos = 0;
+    if (refine<MODE>(dv, k, (int)(q.xy & 0xffffu), (int)(q.xy >> 16), level, dv.nplanes, cval, e)) {
+        const int idx = atomicAdd(&ct->ext_ct[o], 1);
+        if (idx < k.max_extrema) iext[(size_t)o * k.max_extrema + idx] = e;
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kScanThreads, 4)
 cand_extrema_kernel(PyramidView pyr, Consts k, InitialExtremum* __restrict__ iext, Counters* ct)
 {
+    __shared__ Q2Entry q2[kScanThreads / 32][kQ2];
+    __shared__ Q2Entry q3[kQ3];
+    __shared__ float q3c[kQ3];
+    __shared__ int q3n;
     const int L = pyr.levels;
     const float thr = extrema_threshold(k);
     const int nreg = pyr.cand_regions;
-    const int* __restrict__ prefix = pyr.cand_prefix;
-    const long long total = 2LL * __ldg(prefix + nreg);           // two samples per reported pair
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
-        const int e = (int)(t >> 1);
-        // region g with prefix[g] <= e < prefix[g + 1]  (consecutive threads mostly share it: the loads broadcast)
-        int lo = 0, hi = nreg;                                   // invariant: prefix[lo] <= e < prefix[hi]
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (__ldg(prefix + mid) <= e) lo = mid; else hi = mid;
-        }
-        int o = 0, local = lo;                                    // region -> octave, q * cand_blocks + block
-        while (local >= pyr.oct[o].cand_blocks * L) { local -= pyr.oct[o].cand_blocks * L; ++o; }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    if (threadIdx.x == 0) q3n = 0;
+    __syncthreads();
+    int q2n = 0;                                               // warp-uniform
+
+    auto octave_view = [&](int o) {
+        DogOct d;
         const OctaveView& ov = pyr.oct[o];
-        const int idx = e - __ldg(prefix + lo);
-        if (idx >= ov.cand_region) continue;                      // never: a region holds every pair of its block
-        const int level = local / ov.cand_blocks + 1;             // DoG plane of the region's samples
-        DogOct dogv;
-        dogv.dog = ov.dog; dogv.w = ov.w; dogv.h = ov.h; dogv.pitch = ov.pitch; dogv.plane = ov.plane; dogv.nplanes = L + 2;
-        const unsigned packed = __ldg(ov.cand + (size_t)local * ov.cand_region + idx);
-        test_candidate<MODE>(dogv, k, o, level, thr, (int)(packed & 0xffffu) + (int)(t & 1), (int)(packed >> 16), iext, ct);
+        d.dog = ov.dog; d.w = ov.w; d.h = ov.h; d.pitch = ov.pitch; d.plane = ov.plane; d.nplanes = L + 2;
+        return d;
+    };
+    // stage 2 on one warp-full (or the remainder) of this warp's queue, survivors -> the block's stage-3 queue
+    auto serve_q2 = [&](int first, int n) {
+        Q2Entry q; q.xy = 0u; q.ol = 0u;
+        bool ok = false;
+        float cval = 0.0f;
+        if (lane < n) {
+            q = q2[warp][first + lane];
+            const DogOct ov = octave_view((int)(q.ol & 0xffu));
+            ok = stage2(ov, (int)((q.ol >> 8) & 0xffu), (int)(q.xy & 0xffffu), (int)(q.xy >> 16), (q.ol >> 16) & 1u, cval);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (m == 0u) return;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&q3n, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (ok) {
+            const int pos = base + __popc(m & lt);
+            if (pos < kQ3) { q3[pos] = q; q3c[pos] = cval; }
+            else stage3<MODE>(pyr, k, q, cval, iext, ct);      // queue full (never on real images): refine at once
+        }
+    };
+
+    for (int g = blockIdx.x; g < nreg; g += gridDim.x) {
+        const int cnt = __ldg(pyr.cand_cnt_all + g);           // block-uniform
+        if (cnt <= 0) continue;
+        int o = 0, local = g;                                    // region -> octave, q * cand_blocks + block
+        while (local >= pyr.oct[o].cand_blocks * L) { local -= pyr.oct[o].cand_blocks * L; ++o; }
+        const OctaveView& ovv = pyr.oct[o];
+        const int level = local / ovv.cand_blocks + 1;           // DoG plane of the region's samples
+        const int n = min(cnt, ovv.cand_region) * 2;             // two samples per reported pair
+        const unsigned* __restrict__ list = ovv.cand + (size_t)local * ovv.cand_region;
+        const DogOct ov = octave_view(o);
+        for (int t0 = warp * 32; t0 < n; t0 += kScanThreads) {
+            const int t = t0 + lane;
+            bool ok = false, is_max = false;
+            unsigned packed = 0u;
+            if (t < n) {
+                packed = __ldg(list + (t >> 1)) + (unsigned)(t & 1);          // x + 1 for the pair's second sample
+                ok = stage1<MODE>(ov, level, thr, (int)(packed & 0xffffu), (int)(packed >> 16), is_max);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                Q2Entry q; q.xy = packed; q.ol = (unsigned)o | ((unsigned)level << 8) | ((is_max ? 1u : 0u) << 16);
+                q2[warp][q2n + __popc(m & lt)] = q;
+            }
+            q2n += __popc(m);
+            __syncwarp();
+            if (q2n >= 32) { q2n -= 32; serve_q2(q2n, 32); __syncwarp(); }
+        }
     }
+    if (q2n > 0) serve_q2(0, q2n);
+    __syncthreads();
+    const int n3 = min(q3n, kQ3);
+    for (int i = threadIdx.x; i < n3; i += kScanThreads) stage3<MODE>(pyr, k, q3[i], q3c[i], iext, ct);
 }
 
 // POPSIFT_B200_DENSE_SCAN=1 forces the dense scan kernels (A/B timing and cross-check)
@@ -431,9 +552,8 @@ template <int MODE>
 int launch_scan(const PyramidView& pyr, const Consts& k, InitialExtremum* iext, Counters* ct, cudaStream_t st)
 {
     if (pyr.cands_filled && !dense_choice()) {
-        cand_prefix_kernel<<<1, 1024, 0, st>>>(pyr.cand_cnt_all, pyr.cand_regions, pyr.cand_prefix);
         cand_extrema_kernel<MODE><<<sm_count() * 4, kScanThreads, 0, st>>>(pyr, k, iext, ct);
-        return 2;
+        return 1;
     }
     int launches = 0;
     // levels are evaluated in groups of up to 3 (all of them at once for the default levels = 3)
