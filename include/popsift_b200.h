@@ -61,8 +61,8 @@ typedef struct ps_config {
     float   initial_blur;      /* 0.5                                                      */
     int32_t has_initial_blur;  /* 1                                                        */
     int32_t sift_mode;         /* PS_MODE_*                                                */
-    int32_t gauss_mode;        /* PS_GAUSS_*  (only VLFEAT_COMPUTE is implemented; others are REJECTED by ps_create) */
-    int32_t desc_mode;         /* PS_DESC_*   (only LOOP is implemented; others are REJECTED by ps_create)           */
+    int32_t gauss_mode;        /* PS_GAUSS_*  (VLFEAT_COMPUTE and OPENCV_COMPUTE are implemented; the others are REJECTED by ps_create) */
+    int32_t desc_mode;         /* PS_DESC_*   (loop is the fast path; iloop / grid / igrid / notile follow the reference's schemes) */
     int32_t norm_mode;         /* PS_NORM_*                                                */
     int32_t norm_multi;        /* descriptor scaled by 2^norm_multi                        */
     int32_t max_extrema;       /* 100000 per octave                                        */

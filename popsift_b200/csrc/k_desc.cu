@@ -20,6 +20,7 @@
 // reference: per-lane round-up float sums and a shuffle tree) -- run-to-run deterministic descriptors.  Only
 // __sincosf of the keypoint angle and the normalisation (fused below) keep the reference's intrinsics.
 #include "ps_internal.h"
+#include "k_desc_norm.h"
 
 namespace psb {
 
@@ -33,16 +34,6 @@ __device__ __forceinline__ float plane_at(const float* pl, int w, int h, int pit
     x = min(max(x, 0), w - 1);
     y = min(max(y, 0), h - 1);
     return __ldg(pl + (size_t)y * pitch + x);
-}
-
-__device__ __forceinline__ float tree_down(float v)
-{   // lane 0 ends with the reference's shuffle-down tree sum
-    v += __shfl_down_sync(0xffffffffu, v, 16);
-    v += __shfl_down_sync(0xffffffffu, v, 8);
-    v += __shfl_down_sync(0xffffffffu, v, 4);
-    v += __shfl_down_sync(0xffffffffu, v, 2);
-    v += __shfl_down_sync(0xffffffffu, v, 1);
-    return v;
 }
 
 constexpr int DWARPS = 4;     // warps that share one descriptor (one CTA per descriptor in flight); == histogram copies
@@ -101,11 +92,13 @@ descriptor_kernel(PyramidView pyr, Consts k, const ps_extremum* __restrict__ ext
     // lanes that add to the same (cell, bin) -- the common case along a row of samples -- hit different
     // banks instead of serialising on one word; the copies are summed before normalisation
     // kCopies = 8: the 8 lanes of a band (consecutive pixels of one row: usually the same cell and often the same bin)
-    // each add to their own copy, and the copies start 4 banks apart, so adds to the same (cell, bin) from one band are
-    // conflict-free; lanes 8 apart share a copy but work in different bands = distant rows = other cells.  (With 4
-    // copies skewed by 8 banks ncu counted 4.2e7 conflict wavefronts for 1.0e7 ATOMS instructions at 4K: the LSU, not the
-    // issue slots, set the kernel time.)
-    constexpr int kCopies = 8, kHStride = 128 + 4;
+    // each add to their own copy, and the copies start 4 banks apart; lanes 8 apart share a copy but work in different
+    // bands = distant rows = other cells.
+    // Every copy is a 6 x 6 grid of cells: the 4 x 4 descriptor cells plus a guard ring, so that the 2 x 2 cells a sample
+    // spreads over always exist and its eight adds need no range checks, no predicates and no branches (the four
+    // conditional blocks of the 4 x 4 form diverged in almost every warp, so all four bodies ran anyway); the ring is
+    // simply not read back.
+    constexpr int kCopies = 8, kRing = 6, kHStride = kRing * kRing * 8 + 4;
     __shared__ __align__(16) unsigned H[kCopies * kHStride];
     __shared__ int next_d;
     // per row of the support: x = candidates before the row (exclusive prefix), y = first column - x
@@ -131,9 +124,8 @@ descriptor_kernel(PyramidView pyr, Consts k, const ps_extremum* __restrict__ ext
         const int lvl = min(max(e.lpos, 0), pyr.levels + 2);
         const float* pl = ov.gauss + (size_t)lvl * ov.plane;
 
-#pragma unroll
-        for (int c = warp; c < kCopies; c += DWARPS)
-            *reinterpret_cast<uint4*>(H + c * kHStride + 4 * lane) = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = threadIdx.x; i < kCopies * kHStride / 4; i += DTHREADS)
+            reinterpret_cast<uint4*>(H)[i] = make_uint4(0u, 0u, 0u, 0u);
 
         const float x = e.xpos, y = e.ypos;
         const float SBP = fabsf(__fmul_rn(3.0f, e.sigma));
@@ -238,69 +230,40 @@ descriptor_kernel(PyramidView pyr, Consts k, const ps_extremum* __restrict__ ext
                     const float w1 = __fmul_rn(do0, wm), w0 = __fsub_rn(wm, w1);
                     // the (at most) 2x2 cells whose bilinear window covers this pixel
                     // cell coordinates biased by one so that the floor trick sees a non-negative number
-                    const float fx = __fadd_rn(rx, 2.5f), fy = __fadd_rn(ry, 2.5f);     // in (0, 5)
+                    // (rx + 2.5 can round to exactly 5.0: clamped to the last float below, which keeps the guard column index at 5)
+                    const float fx = fminf(__fadd_rn(rx, 2.5f), 4.99999952f), fy = fminf(__fadd_rn(ry, 2.5f), 4.99999952f);   // in [0, 5)
                     const unsigned bx = floor_bits(fx), by = floor_bits(fy);
-                    const int cx0 = (int)(bx & 7u) - 1, cy0 = (int)(by & 7u) - 1;       // -1 .. 3
+                    const unsigned gx = bx & 7u, gy = by & 7u;                          // ring cell of the lower-left window: 0 .. 4
                     const float ax1 = __fsub_rn(fx, floor_val(bx));                     // in [0,1)
                     const float ay1 = __fsub_rn(fy, floor_val(by));
                     const float ax0 = __fsub_rn(1.0f, ax1), ay0 = __fsub_rn(1.0f, ay1);
-                    // rx + 2.5 can round up to exactly 5.0 (cell 4): every cell index is range-checked on both sides
-                    const bool x0ok = (unsigned)cx0 < 4u, x1ok = (unsigned)(cx0 + 1) < 4u;
-                    const bool y0ok = (unsigned)cy0 < 4u, y1ok = (unsigned)(cy0 + 1) < 4u;
-                    unsigned* hb = H + (lane & (kCopies - 1)) * kHStride + ((cy0 << 2) + cx0) * 8;   // cell (cx0, cy0); may be out of range
-                    if (x0ok && y0ok) {
-                        const float wc = __fmul_rn(ax0, ay0);
-                        atomicAdd(hb + b0, fix_bits(w0, wc));
-                        atomicAdd(hb + b1, fix_bits(w1, wc));
-                    }
-                    if (x1ok && y0ok) {
-                        const float wc = __fmul_rn(ax1, ay0);
-                        atomicAdd(hb + 8 + b0, fix_bits(w0, wc));
-                        atomicAdd(hb + 8 + b1, fix_bits(w1, wc));
-                    }
-                    if (x0ok && y1ok) {
-                        const float wc = __fmul_rn(ax0, ay1);
-                        atomicAdd(hb + 32 + b0, fix_bits(w0, wc));
-                        atomicAdd(hb + 32 + b1, fix_bits(w1, wc));
-                    }
-                    if (x1ok && y1ok) {
-                        const float wc = __fmul_rn(ax1, ay1);
-                        atomicAdd(hb + 40 + b0, fix_bits(w0, wc));
-                        atomicAdd(hb + 40 + b1, fix_bits(w1, wc));
-                    }
+                    unsigned* hb = H + (lane & (kCopies - 1)) * kHStride + (gy * kRing + gx) * 8;
+                    const float c00 = __fmul_rn(ax0, ay0), c10 = __fmul_rn(ax1, ay0), c01 = __fmul_rn(ax0, ay1), c11 = __fmul_rn(ax1, ay1);
+                    atomicAdd(hb + b0, fix_bits(w0, c00));
+                    atomicAdd(hb + b1, fix_bits(w1, c00));
+                    atomicAdd(hb + 8 + b0, fix_bits(w0, c10));
+                    atomicAdd(hb + 8 + b1, fix_bits(w1, c10));
+                    atomicAdd(hb + kRing * 8 + b0, fix_bits(w0, c01));
+                    atomicAdd(hb + kRing * 8 + b1, fix_bits(w1, c01));
+                    atomicAdd(hb + kRing * 8 + 8 + b0, fix_bits(w0, c11));
+                    atomicAdd(hb + kRing * 8 + 8 + b1, fix_bits(w1, c11));
                 }
                 // the next pass (or the next descriptor) rewrites row_tab only after its own barrier
             }
         }
         __syncthreads();
         if (warp == 0) {
-            uint4 hv = *reinterpret_cast<const uint4*>(H + 4 * lane);
+            // lane = (cell, half of its 8 bins); descriptor cell (cx, cy) is ring cell (cx + 1, cy + 1)
+            const int cell = lane >> 1;
+            const int hoff = (((cell >> 2) + 1) * kRing + (cell & 3) + 1) * 8 + (lane & 1) * 4;
+            uint4 hv = *reinterpret_cast<const uint4*>(H + hoff);
 #pragma unroll
             for (int c = 1; c < kCopies; ++c) {
-                const uint4 t = *reinterpret_cast<const uint4*>(H + c * kHStride + 4 * lane);
+                const uint4 t = *reinterpret_cast<const uint4*>(H + c * kHStride + hoff);
                 hv.x += t.x; hv.y += t.y; hv.z += t.z; hv.w += t.w;
             }
             float4 v = make_float4((float)hv.x * kUnfix, (float)hv.y * kUnfix, (float)hv.z * kUnfix, (float)hv.w * kUnfix);
-            if (k.norm_mode == PS_NORM_ROOTSIFT) {
-                float sum = __fadd_rn(__fadd_rn(__fadd_rn(v.x, v.y), v.z), v.w);
-                sum = __shfl_sync(0xffffffffu, tree_down(sum), 0);
-                v.x = scalbnf(__fsqrt_rn(__fdividef(v.x, sum)), k.norm_multi);
-                v.y = scalbnf(__fsqrt_rn(__fdividef(v.y, sum)), k.norm_multi);
-                v.z = scalbnf(__fsqrt_rn(__fdividef(v.z, sum)), k.norm_multi);
-                v.w = scalbnf(__fsqrt_rn(__fdividef(v.w, sum)), k.norm_multi);
-            } else {
-                float n = __fmaf_rn(v.w, v.w, __fmaf_rn(v.z, v.z, __fmaf_rn(v.y, v.y, __fmul_rn(v.x, v.x))));
-                n = tree_down(n);
-                if (lane == 0) n = __fsqrt_rn(n);
-                n = __shfl_sync(0xffffffffu, n, 0);
-                const float lim = __fmul_rn(0.2f, n);
-                v.x = fminf(v.x, lim); v.y = fminf(v.y, lim); v.z = fminf(v.z, lim); v.w = fminf(v.w, lim);
-                n = __fmaf_rn(v.w, v.w, __fmaf_rn(v.z, v.z, __fmaf_rn(v.y, v.y, __fmul_rn(v.x, v.x))));
-                n = tree_down(n);
-                if (lane == 0) n = scalbnf(__frsqrt_rn(n), k.norm_multi);
-                n = __shfl_sync(0xffffffffu, n, 0);
-                v.x = __fmul_rn(v.x, n); v.y = __fmul_rn(v.y, n); v.z = __fmul_rn(v.z, n); v.w = __fmul_rn(v.w, n);
-            }
+            v = normalize_descriptor(v, lane, k.norm_mode, k.norm_multi);
             reinterpret_cast<float4*>(desc[d].features)[lane] = v;
         }
         // the next iteration's first __syncthreads orders this read of H before the next reset

@@ -270,7 +270,8 @@ static int run_tail(ps_ctx* ctx, Slot& s, bool tm)
     PS_CUDA(ctx, cudaMemsetAsync(s.d_ori_slice, 0, sizeof(int) * ((size_t)s.ext_cap / PS_ORI_SLICE + 1), s.stream));
     int n = launch_orientation(s.view, k, s.d_iext, s.d_iext_f, s.d_ext, s.d_f2e, s.d_ori_slice, s.d_ct, s.stream);
     if (tm) PS_CUDA(ctx, cudaEventRecord(s.ev[4], s.stream));
-    n += launch_descriptors(s.view, k, s.d_ext, s.d_f2e, s.d_desc, s.d_ct, s.stream);
+    if (ctx->cfg.desc_mode == PS_DESC_LOOP) n += launch_descriptors(s.view, k, s.d_ext, s.d_f2e, s.d_desc, s.d_ct, s.stream);
+    else n += launch_descriptors_mode(ctx->cfg.desc_mode, s.view, k, s.d_ext, s.d_f2e, s.d_desc, s.d_ct, s.stream);
     n += launch_prep_features(k, s.d_ext, s.d_feat, s.d_ct, s.stream);
     if (tm) PS_CUDA(ctx, cudaEventRecord(s.ev[5], s.stream));
     ctx->launches += n;
@@ -399,8 +400,8 @@ extern "C" ps_ctx* ps_create(int device, const ps_config* cfg, int max_w, int ma
     // Options whose numerics are not implemented are refused, never silently replaced by the default path.
     {
         const char* why = nullptr;
-        if (ctx->cfg.desc_mode != PS_DESC_LOOP)
-            why = "ps_create: unsupported configuration: descriptor mode other than 'loop' (iloop/grid/igrid/notile are not implemented)";
+        if (ctx->cfg.desc_mode < PS_DESC_LOOP || ctx->cfg.desc_mode > PS_DESC_NOTILE)
+            why = "ps_create: bad descriptor mode";
         else if (ctx->cfg.scaling_mode != PS_SCALE_DEFAULT)
             why = "ps_create: unsupported configuration: direct scaling (Config::ScaleDirect) is not implemented";
         else if (ctx->cfg.sift_mode != PS_MODE_POPSIFT && ctx->cfg.sift_mode != PS_MODE_OPENCV && ctx->cfg.sift_mode != PS_MODE_VLFEAT)
@@ -413,7 +414,7 @@ extern "C" ps_ctx* ps_create(int device, const ps_config* cfg, int max_w, int ma
     }
     if (ps_gauss_tables_compute(&ctx->cfg, &ctx->tab) != PS_OK) {
         delete ctx;
-        return bail("ps_create: unsupported configuration (sigma > 2.0, levels > 12 or gauss mode other than vlfeat)", cudaSuccess);
+        return bail("ps_create: unsupported configuration (sigma > 2.0, levels > 12, or a gauss mode other than vlfeat / opencv)", cudaSuccess);
     }
     for (int l = 0; l < PS_GAUSS_LEVELS; ++l) {
         std::memcpy(ctx->rows[l].tap, &ctx->tab.inc_filter[l * PS_GAUSS_ALIGN], sizeof(float) * PS_GAUSS_ALIGN);

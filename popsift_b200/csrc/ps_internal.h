@@ -145,6 +145,10 @@ int launch_orientation(const PyramidView& pyr, const Consts& k, const InitialExt
                        int* feat_to_ext, int* slice_sum, Counters* ct, cudaStream_t st);
 int launch_descriptors(const PyramidView& pyr, const Consts& k, const ps_extremum* ext, const int* feat_to_ext,
                        ps_descriptor* desc, Counters* ct, cudaStream_t st);
+// --desc-mode grid / igrid / iloop / notile (k_desc_modes.cu; reference s_desc_grid.cu, s_desc_igrid.cu, s_desc_iloop.cu,
+// s_desc_notile.cu); PS_DESC_LOOP goes through launch_descriptors
+int launch_descriptors_mode(int mode, const PyramidView& pyr, const Consts& k, const ps_extremum* ext, const int* feat_to_ext,
+                            ps_descriptor* desc, Counters* ct, cudaStream_t st);
 int launch_prep_features(const Consts& k, const ps_extremum* ext, ps_feature* feat, const Counters* ct, cudaStream_t st);
 // device copy of the Feature records: desc[] become pointers into `desc` (first index is in pad_)
 int launch_fix_feature_pointers(ps_feature* feat, ps_descriptor* desc, int n, cudaStream_t st);

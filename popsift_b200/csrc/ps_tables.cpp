@@ -14,18 +14,25 @@
 
 namespace {
 
-// Half-width (including the centre tap) of the VLFeat-style kernel for one sigma.
-int kernel_span(float sigma)
+// Half-width (including the centre tap) of the kernel for one sigma: VLFeat's rule (reference gauss_filter.cu:301-307)
+// or OpenCV's (--gauss-mode opencv, gauss_filter.cu:320-327).  Everything else about the two modes is identical.
+int kernel_span(float sigma, bool opencv)
 {
+    if (opencv) {
+        int span = static_cast<int>(std::roundf(2.0f * 4.0f * sigma + 1.0f)) | 1;
+        span >>= 1;
+        span += 1;
+        return std::min(span, PS_GAUSS_ALIGN - 1);
+    }
     const int s = static_cast<int>(std::ceil(4.0f * sigma) + 1.0f);
     return std::min(s, PS_GAUSS_ALIGN - 1);
 }
 
 // One normalised half-kernel.  The taps are evaluated in double, stored as float; the
 // normaliser is a double that accumulates twice the *stored float* tap.
-void fill_kernel(float sigma, float* taps, int32_t* span_out)
+void fill_kernel(float sigma, float* taps, int32_t* span_out, bool opencv)
 {
-    const int span = kernel_span(sigma);
+    const int span = kernel_span(sigma, opencv);
     std::fill(taps, taps + PS_GAUSS_ALIGN, 0.0f);
     taps[0] = 1.0f;
     double norm = 1.0;
@@ -74,7 +81,8 @@ extern "C" int ps_gauss_tables_compute(const ps_config* cfg, ps_gauss_tables* ou
     const float s0 = cfg->sigma;
     if (s0 > 2.0f) return PS_ERR_ARG;                 // reference gauss_filter.cu:131-137
     if (levels > PS_GAUSS_LEVELS) return PS_ERR_ARG;  // reference gauss_filter.cu:138-144
-    if (cfg->gauss_mode != PS_GAUSS_VLFEAT_COMPUTE) return PS_ERR_ARG;
+    if (cfg->gauss_mode != PS_GAUSS_VLFEAT_COMPUTE && cfg->gauss_mode != PS_GAUSS_OPENCV_COMPUTE) return PS_ERR_ARG;
+    const bool ocv = cfg->gauss_mode == PS_GAUSS_OPENCV_COMPUTE;
     const int planes = levels + 3;
     const float blur_in = cfg->has_initial_blur ? cfg->initial_blur * std::pow(2.0f, cfg->upscale) : 0.0f;
 
@@ -87,14 +95,14 @@ extern "C" int ps_gauss_tables_compute(const ps_config* cfg, ps_gauss_tables* ou
         out->inc_sigma[l] = std::sqrt(hi * hi - lo * lo);
     }
     for (int l = 0; l < PS_GAUSS_LEVELS; ++l)
-        fill_kernel(out->inc_sigma[l], &out->inc_filter[l * PS_GAUSS_ALIGN], &out->inc_span[l]);
+        fill_kernel(out->inc_sigma[l], &out->inc_filter[l * PS_GAUSS_ALIGN], &out->inc_span[l], ocv);
 
     // first horizontal pass over the input image (octave 0): sqrt(|sigma0^2 - blur_in^2|)
     {
         const float so = std::scalbn(s0, 0);
         const float gap = std::sqrt(std::fabs(so * so - blur_in * blur_in));
         out->dd_sigma0 = std::scalbn(gap, 0);
-        fill_kernel(out->dd_sigma0, out->dd_filter0, &out->dd_span0);
+        fill_kernel(out->dd_sigma0, out->dd_filter0, &out->dd_span0, ocv);
     }
     out->peak_threshold = cfg->threshold * 0.5f * 255.0f / static_cast<float>(levels);
     out->sigma_k = std::pow(2.0f, 1.0f / static_cast<float>(levels));

@@ -134,6 +134,9 @@ def test_1080p_counts_vs_golden():
     (1920, 1080, 102, "popsift", "rootsift", []),
     (800, 600, 21, "vlfeat", "classic", ["--downsampling", "0"]),
     (3840, 2160, 7, "vlfeat", "classic", ["--octaves", "5"]),
+    (800, 600, 22, "vlfeat", "classic", ["--gauss-mode", "opencv"]),       # OpenCV filter widths (gauss_filter.cu:320-327)
+    (640, 480, 23, "popsift", "rootsift", ["--gauss-mode", "opencv", "--sigma", "1.2", "--levels", "4"]),
+    (700, 500, 24, "vlfeat", "classic", ["--downsampling", "-0.5"]),       # non-integer up-scale: general texture fractions
 ])
 def test_live_against_reference_library(tmp_path, w, h, seed, mode, norm, extra):
     """same bytes -> reference libpopsift (compiled from /root/reference for sm_100) and this library,
@@ -148,7 +151,16 @@ def test_live_against_reference_library(tmp_path, w, h, seed, mode, norm, extra)
         kw["downsampling"] = 0
     if "--octaves" in extra:
         kw["octaves"] = 5
-    ps, feats = run_gpu(img, mk_cfg(mode, norm, **kw))
+    if "--downsampling" in extra:
+        kw["downsampling"] = float(extra[extra.index("--downsampling") + 1])
+    if "--sigma" in extra:
+        kw["sigma"] = float(extra[extra.index("--sigma") + 1])
+    if "--levels" in extra:
+        kw["levels"] = int(extra[extra.index("--levels") + 1])
+    cfg = mk_cfg(mode, norm, **kw)
+    if "--gauss-mode" in extra:
+        cfg.setGaussMode(extra[extra.index("--gauss-mode") + 1])
+    ps, feats = run_gpu(img, cfg)
     assert feats.getFeatureCount() == len(rf), (feats.getFeatureCount(), len(rf))
     assert feats.getDescriptorCount() == len(rd), (feats.getDescriptorCount(), len(rd))
     r = compare.report(*feats.keypoints(), *ol.flatten(rf, rd))
@@ -508,8 +520,7 @@ def test_grid_filter_1280_and_unsupported_options_are_refused():
     assert feats.getFeatureCount() == len(z["feat"]) and feats.getDescriptorCount() == int(z["n_desc"][0])
     ps.uninit()
     # options whose numerics are not implemented are refused, never silently computed with the default path
-    for setter in (lambda c: c.setDescMode("grid"), lambda c: c.setDescMode("notile"), lambda c: c.setGaussMode("fixed9"),
-                   lambda c: c.setScalingMode(0)):
+    for setter in (lambda c: c.setGaussMode("fixed9"), lambda c: c.setGaussMode("relative"), lambda c: c.setScalingMode(0)):
         c = mk_cfg()
         setter(c)
         with pytest.raises(api.PopSiftError):
@@ -630,3 +641,57 @@ def test_popsift_match_cli_and_log_dumps(tmp_path):
         p = ol.read_ref_dump(str(fn))
         assert hashlib.sha256(p.tobytes()).hexdigest() == m["sha256"], key
     assert (tmp_path / "dir-desc" / "desc-pyramid.txt").exists() and (tmp_path / "dir-fpt" / "desc-pyramid.txt").exists()
+
+
+@pytest.mark.parametrize("dm", ["iloop", "grid", "igrid", "notile"])
+def test_descriptor_modes_vs_reference(tmp_path, dm):
+    """--desc-mode iloop | grid | igrid | notile (reference s_desc_iloop.cu, s_desc_grid.cu, s_desc_igrid.cu, s_desc_notile.cu):
+    same keypoints and orientations as the default mode, descriptors within 1e-3 of the reference's for that mode --
+    against the committed 256x192 fixture and, live, on a 640x480 frame."""
+    z = np.load(os.path.join(G, "feat_f256_desc_%s.npz" % dm))
+    cfg = mk_cfg("vlfeat", "classic")
+    cfg.setDescMode(dm)
+    ps, feats = run_gpu(make_frame(256, 192, 3), cfg)
+    assert (feats.getFeatureCount(), feats.getDescriptorCount()) == (len(z["feat"]), len(z["desc"]))
+    r = compare.report(*feats.keypoints(), *ol.flatten(z["feat"], z["desc"]))
+    assert r["f1"] == 1.0 and r["desc_l2_max"] < L2_MAX, r
+    ps.uninit()
+    # the modes really are different sampling schemes: the default mode's descriptors are NOT within the tolerance
+    base = np.load(os.path.join(G, "feat_f256_vlfeat_classic.npz"))
+    r0 = compare.report(*ol.flatten(base["feat"], base["desc"]), *ol.flatten(z["feat"], z["desc"]))
+    assert r0["desc_l2_max"] > L2_MAX
+    if os.path.exists(REF):
+        img = make_frame(640, 480, 1)
+        pgm, out = str(tmp_path / "f.pgm"), str(tmp_path / "f.bin")
+        write_pgm(pgm, img)
+        subprocess.run([REF, "-i", pgm, "-o", out, "--desc-mode", dm], check=True, capture_output=True)
+        rf, rd = ol.read_ref_features(out)
+        cfg = mk_cfg()
+        cfg.setDescMode(dm)
+        ps, feats = run_gpu(img, cfg)
+        assert (feats.getFeatureCount(), feats.getDescriptorCount()) == (len(rf), len(rd))
+        r = compare.report(*feats.keypoints(), *ol.flatten(rf, rd))
+        assert r["f1"] >= F1_MIN and r["desc_l2_max"] < L2_MAX, r
+        print("desc mode %s: max L2 %.3g, median %.3g" % (dm, r["desc_l2_max"], r["desc_l2_median"]))
+        ps.uninit()
+
+
+def test_planes_bit_exact_vs_oracle_1080p():
+    """Every Gaussian and DoG plane of a 1920x1080 frame (octave 0 = 3840x2160: interior strips, all segment kinds, TMA
+    tiles and the clamped border rows) against the CPU oracle, bit for bit; the two largest octaves of the benchmark's
+    4K frame are covered by the sha256 of the oracle's planes as well."""
+    for (w, h, seed, octaves) in ((1920, 1080, 100, 6), (3840, 2160, 7, 3)):
+        img = make_frame(w, h, seed)
+        ps, _ = run_gpu(img, mk_cfg(octaves=octaves))
+        o = ol.Oracle(ol.make_config(octaves=octaves), w, h)
+        o.run(img, 1)
+        bad = []
+        for oc in range(o.num_octaves):
+            for l in range(6):
+                if not np.array_equal(ps.plane(0, oc, l), o.gauss(oc, l)):
+                    bad.append(("g", oc, l))
+            for l in range(5):
+                if not np.array_equal(ps.plane(0, oc, l, dog=True), o.dog(oc, l)):
+                    bad.append(("d", oc, l))
+        assert not bad, bad
+        ps.uninit(); o.close()
