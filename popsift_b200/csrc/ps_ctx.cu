@@ -62,6 +62,10 @@ struct Slot {
     cudaEvent_t in_done = nullptr;   // recorded after the host -> device copy of the slot's input image
     bool in_pending = false;         // in_done has been recorded at least once
     int ext_cap = 0, desc_cap = 0;   // capacity of d_ext / d_feat and of d_desc / d_f2e; grown on demand (regrow_slot)
+    // the slot's per-frame work as a CUDA graph (submit_common)
+    cudaGraphExec_t graph_exec = nullptr;
+    bool graph_ok = false, graph_float = false, warm_float = false;
+    int graph_w = 0, graph_h = 0, warm_w = 0, warm_h = 0, graph_launches = 0;
     bool submitted = false;
     bool is_float = false;
     int w = 0, h = 0;
@@ -82,6 +86,7 @@ struct ps_ctx {
     int max_octaves = 0;
     int levels = 3;
     bool timing = false;
+    bool graph_broken = false;       // a stream capture failed once: direct launches from then on
     std::vector<Slot> slots;
     std::atomic<int64_t> launches{0};
     mutable std::mutex err_mu;
@@ -277,7 +282,6 @@ static int run_tail(ps_ctx* ctx, Slot& s, bool tm)
     ctx->launches += n;
     PS_CUDA(ctx, cudaGetLastError());
     PS_CUDA(ctx, cudaMemcpyAsync(s.h_ct, s.d_ct, sizeof(Counters), cudaMemcpyDeviceToHost, s.stream));
-    PS_CUDA(ctx, cudaEventRecord(s.done, s.stream));
     return PS_OK;
 }
 
@@ -317,15 +321,19 @@ static int regrow_slot(ps_ctx* ctx, Slot& s)
         PS_CUDA(ctx, cudaStreamSynchronize(s.stream));          // `reset` lives on this stack frame
         int rc = run_tail(ctx, s, false);
         if (rc != PS_OK) return rc;
+        PS_CUDA(ctx, cudaEventRecord(s.done, s.stream));
         PS_CUDA(ctx, cudaEventSynchronize(s.done));
+        s.graph_ok = false;                  // the captured graph holds the old buffer addresses
     }
     return PS_OK;
 }
 
-static int submit_common(ps_ctx* ctx, Slot& s)
+// everything between the input copy and the `done` event: memsets, pyramid, extrema, (grid filter), orientation,
+// descriptors, Feature records, counters to the host.  Issued directly, or once under stream capture (below).
+static int enqueue_pipeline(ps_ctx* ctx, Slot& s, bool tm, int* launched)
 {
-    const bool tm = ctx->timing;
     int rc;
+    const long long before = ctx->launches.load();
     PS_CUDA(ctx, cudaMemsetAsync(s.d_ct, 0, sizeof(Counters), s.stream));
     PS_CUDA(ctx, cudaMemsetAsync(s.cand_cnt, 0, s.cand_cnt_bytes, s.stream));
     if (tm) PS_CUDA(ctx, cudaEventRecord(s.ev[1], s.stream));
@@ -341,6 +349,60 @@ static int submit_common(ps_ctx* ctx, Slot& s)
     }
     ctx->launches += n;
     if ((rc = run_tail(ctx, s, tm)) != PS_OK) return rc;
+    if (launched) *launched = (int)(ctx->launches.load() - before);
+    return PS_OK;
+}
+
+// POPSIFT_B200_GRAPH=0 issues every launch of every frame individually (A/B switch)
+static bool graph_choice()
+{
+    static const bool v = [] { const char* e = getenv("POPSIFT_B200_GRAPH"); return !(e && e[0] == '0'); }();
+    return v;
+}
+
+// The per-frame work of a slot is the same ~35 launches, memsets and stream forks for every image of one geometry, on
+// buffers that do not move: from the second image of a geometry on it is replayed as ONE CUDA graph launch (captured
+// from the slot's own stream, side stream included).  The submitting thread then makes 3 driver calls per frame
+// instead of ~45 -- on a busy host (this path is driven from one thread per GPU) that is the difference between a
+// GPU-bound and a launch-bound pipeline.  The first image of a geometry runs un-captured so that every lazy
+// initialisation (shared-memory opt-ins, tensor-map encoder lookup, constant tables) happens outside a capture.
+static int submit_common(ps_ctx* ctx, Slot& s)
+{
+    const bool tm = ctx->timing;
+    int rc;
+    const bool want_graph = graph_choice() && !tm && !ctx->graph_broken;
+    if (want_graph && s.graph_ok && s.graph_w == s.w && s.graph_h == s.h && s.graph_float == s.is_float) {
+        PS_CUDA(ctx, cudaGraphLaunch(s.graph_exec, s.stream));
+        ctx->launches += s.graph_launches;
+    } else if (want_graph && s.warm_w == s.w && s.warm_h == s.h && s.warm_float == s.is_float) {
+        // second image of this geometry: capture while issuing
+        if (s.graph_exec) { cudaGraphExecDestroy(s.graph_exec); s.graph_exec = nullptr; }
+        s.graph_ok = false;
+        cudaGraph_t g = nullptr;
+        int launched = 0;
+        cudaError_t e = cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeRelaxed);
+        if (e == cudaSuccess) {
+            rc = enqueue_pipeline(ctx, s, false, &launched);
+            e = cudaStreamEndCapture(s.stream, &g);
+            if (rc == PS_OK && e == cudaSuccess && g) e = cudaGraphInstantiate(&s.graph_exec, g, 0);
+            else if (e == cudaSuccess) e = cudaErrorUnknown;
+            if (g) cudaGraphDestroy(g);
+        }
+        if (e != cudaSuccess || !s.graph_exec) {
+            // capture is an optimisation: fall back to direct launches for this context and say so once
+            cudaGetLastError();
+            ctx->graph_broken = true;
+            fprintf(stderr, "popsift_b200: CUDA graph capture failed (%s); launching directly\n", cudaGetErrorString(e));
+            if ((rc = enqueue_pipeline(ctx, s, tm, nullptr)) != PS_OK) return rc;
+        } else {
+            s.graph_ok = true; s.graph_w = s.w; s.graph_h = s.h; s.graph_float = s.is_float; s.graph_launches = launched;
+            PS_CUDA(ctx, cudaGraphLaunch(s.graph_exec, s.stream));       // the capture recorded the work, it did not run it
+        }
+    } else {
+        if ((rc = enqueue_pipeline(ctx, s, tm, nullptr)) != PS_OK) return rc;
+        s.warm_w = s.w; s.warm_h = s.h; s.warm_float = s.is_float;
+    }
+    PS_CUDA(ctx, cudaEventRecord(s.done, s.stream));
     s.submitted = true;
     return PS_OK;
 }
@@ -369,6 +431,7 @@ extern "C" void ps_destroy(ps_ctx* ctx)
         cudaFreeHost(s.h_feat); cudaFreeHost(s.h_desc);
         for (auto& e : s.ev) if (e) cudaEventDestroy(e);
         if (s.done) cudaEventDestroy(s.done);
+        if (s.graph_exec) cudaGraphExecDestroy(s.graph_exec);
         if (s.in_done) cudaEventDestroy(s.in_done);
         for (auto& e : s.ev_fork) if (e) cudaEventDestroy(e);
         for (auto& e : s.ev_join) if (e) cudaEventDestroy(e);
