@@ -192,6 +192,10 @@ int ps_sync(ps_ctx* ctx, int slot);
 int ps_debug_plane(ps_ctx* ctx, int slot, int octave, int level, int which, float* out);
 /* extrema of the last image of the slot (after orientation); returns count, fills up to cap */
 int ps_debug_extrema(ps_ctx* ctx, int slot, ps_extremum* out, int cap);
+/* which evaluation of octave 0 / level 0 is bit-exact for a w x h input scaled to W x H with the reference's `shift`
+ * and a row filter of radius R (host arithmetic only, no device needed): 0 = ideal 2x pattern, 1 = neighbouring outputs
+ * share their texture fetches, 2 = every tap fetched at its own coordinate (input texture). */
+int ps_debug_level0_plan(int w, int h, int W, int H, float shift, int R);
 /* geometry of the last image submitted to the slot */
 int ps_slot_geometry(ps_ctx* ctx, int slot, int32_t* n_octaves, int32_t* W, int32_t* H);
 /* CUDA-event time of each stage of the slot's last image (ms); enable with ps_set_timing(ctx,1) */

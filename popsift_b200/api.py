@@ -53,7 +53,8 @@ EXPORTS = ["ps_abi_version", "ps_config_default", "ps_gauss_tables_compute", "ps
            "ps_last_error", "ps_submit_u8", "ps_submit_f32", "ps_submit_dev_u8", "ps_counts", "ps_download",
            "ps_sync", "ps_debug_plane", "ps_debug_extrema", "ps_slot_geometry", "ps_set_timing", "ps_stage_ms",
            "ps_launch_count", "ps_slot_stream", "ps_run_pyramid_only", "ps_run_level_only", "ps_host_alloc", "ps_host_free",
-           "ps_download_dev", "ps_dev_alloc", "ps_dev_free", "ps_dev_to_host", "ps_wait_input", "ps_match", "ps_pointer_device", "ps_host_to_dev"]
+           "ps_download_dev", "ps_dev_alloc", "ps_dev_free", "ps_dev_to_host", "ps_wait_input", "ps_match", "ps_pointer_device", "ps_host_to_dev",
+           "ps_debug_level0_plan"]
 
 _lib = None
 
@@ -88,6 +89,7 @@ def load_library():
     L.ps_host_to_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.ps_debug_plane.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     L.ps_debug_extrema.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    L.ps_debug_level0_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int]
     L.ps_slot_geometry.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.ps_set_timing.argtypes = [C.c_void_p, C.c_int]
     L.ps_stage_ms.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]

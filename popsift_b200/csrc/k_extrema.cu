@@ -281,113 +281,13 @@ find_extrema_kernel(PyramidView pyr, Consts k, ScanParams sp, InitialExtremum* _
 // The pyramid kernels report every DoG pixel pair in which a sample has |value| >= threshold into the
 // list region of the block that produced it (CandSink) while they write the plane.  On real and
 // synthetic images that is a few samples per thousand, so testing only those against their 26
-// neighbours replaces the dense scan's read of every DoG plane.  One block per list region, one thread
-// per sample, grid-stride over the regions of all octaves and levels: no host round trip, no shared
-// memory; the only atomics are the final appends.  Accepted set and refinement are those of the dense
+// neighbours replaces the dense scan's read of every DoG plane.  Accepted set and refinement are those of the dense
 // kernel: same comparisons, same refine<MODE>.
 constexpr int kScanThreads = 256;
 
 // one octave's DoG planes, by value (a reference to the kernel's PyramidView parameter would make every
 // thread copy the whole structure to local memory)
 struct DogOct { const float* dog; int w, h, pitch, nplanes; size_t plane; };
-
-template <int MODE>
-__device__ __noinline__ void test_candidate(const DogOct ov, const Consts& k, int o, int level, float thr, int x, int y,
-                                            InitialExtremum* __restrict__ iext, Counters* ct)
-{
-    const int W = ov.w, H = ov.h;
-    bool inside = x >= 1 && x <= W - 2 && y >= 1 && y <= H - 2;
-    if (MODE == PS_MODE_OPENCV) inside = inside && !(x < 5 || x >= W - 5) && !(y < 5 || y >= H - 5);
-    if (!inside) return;
-    const float* pc = ov.dog + (size_t)level * ov.plane + (size_t)y * ov.pitch + x;
-    const float c = __ldg(pc);
-    if (!(fabsf(c) >= thr)) return;
-    // strict maximum or strict minimum of the 3x3x3 neighbourhood.  The loads of a plane are issued
-    // together (the test is bound by memory latency, not by instructions); most samples are beaten by an
-    // in-plane neighbour and stop after the first batch.
-    bool ismax = true, ismin = true;
-    auto beat = [&](float n) { ismax = ismax && c > n; ismin = ismin && c < n; };
-    {
-        const float* ra = pc - ov.pitch;
-        const float* rb = pc + ov.pitch;
-        const float n0 = __ldg(pc - 1), n1 = __ldg(pc + 1);
-        const float n2 = __ldg(ra - 1), n3 = __ldg(ra), n4 = __ldg(ra + 1);
-        const float n5 = __ldg(rb - 1), n6 = __ldg(rb), n7 = __ldg(rb + 1);
-        beat(n0); beat(n1); beat(n2); beat(n3); beat(n4); beat(n5); beat(n6); beat(n7);
-    }
-    if (!(ismax || ismin)) return;
-#pragma unroll
-    for (int dz = -1; dz <= 1; dz += 2) {
-        const float* p = dz < 0 ? pc - ov.plane : pc + ov.plane;
-        const float* ra = p - ov.pitch;
-        const float* rb = p + ov.pitch;
-        const float n0 = __ldg(p - 1), n1 = __ldg(p), n2 = __ldg(p + 1);
-        const float n3 = __ldg(ra - 1), n4 = __ldg(ra), n5 = __ldg(ra + 1);
-        const float n6 = __ldg(rb - 1), n7 = __ldg(rb), n8 = __ldg(rb + 1);
-        beat(n0); beat(n1); beat(n2); beat(n3); beat(n4); beat(n5); beat(n6); beat(n7); beat(n8);
-    }
-    if (!(ismax || ismin)) return;
-
-    DogView dv;
-    dv.base = ov.dog; dv.w = W; dv.h = H; dv.pitch = ov.pitch; dv.plane = ov.plane;
-    dv.nplanes = ov.nplanes;
-    InitialExtremum e;
-    e.xpos = e.ypos = e.sigma = 0.f; e.lpos = 0;
-    if (refine<MODE>(dv, k, x, y, level, ov.nplanes, c, e)) {
-        const int idx = atomicAdd(&ct->ext_ct[o], 1);
-        if (idx < k.max_extrema) iext[(size_t)o * k.max_extrema + idx] = e;
-    }
-}
-
-// Exclusive prefix sum of the list regions' counts (single block; every thread's loads are in flight at
-// once): sample t of the image then belongs to the region g with prefix[g] <= t/2 < prefix[g+1].
-__global__ void __launch_bounds__(1024)
-cand_prefix_kernel(const int* __restrict__ counts, int n, int* __restrict__ prefix)
-{
-    __shared__ int warp_sums[32];
-    __shared__ int carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int PER = 16;
-    for (int base = 0; base < n; base += 1024 * PER) {
-        const int first = base + threadIdx.x * PER;
-        int c[PER];
-#pragma unroll
-        for (int j = 0; j < PER; ++j) c[j] = first + j < n ? max(counts[first + j], 0) : 0;
-        int sum = 0;
-#pragma unroll
-        for (int j = 0; j < PER; ++j) sum += c[j];
-        int v = sum;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, v, d);
-            if (lane >= d) v += t;
-        }
-        if (lane == 31) warp_sums[warp] = v;
-        __syncthreads();
-        if (warp == 0) {
-            int s = warp_sums[lane];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, s, d);
-                if (lane >= d) s += t;
-            }
-            warp_sums[lane] = s;
-        }
-        __syncthreads();
-        int excl = carry + (warp ? warp_sums[warp - 1] : 0) + v - sum;
-#pragma unroll
-        for (int j = 0; j < PER; ++j) {
-            if (first + j < n) prefix[first + j] = excl;
-            excl += c[j];
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) carry += warp_sums[31];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) prefix[n] = carry;
-}
 
 // Region-driven form (default).  A list region = the candidates one block of one level kernel reported; block b of this
 // kernel takes regions b, b + gridDim.x, ... (no prefix sum, no search: a region's octave, level and list follow from

@@ -36,9 +36,14 @@ bool march_supports(int R);
 int march_cand_blocks(int w, int h);
 int march_cand_region(int w, int h);
 long long march_cand_entry_bound(int w, int h);
+// How level 0 of octave 0 may be evaluated for one geometry (level0_plan, k_pyramid.cu): whether neighbouring outputs can
+// share their texture fetches is decided by evaluating the texture unit's coordinate arithmetic for every (column, tap).
+enum { LEVEL0_IDEAL_X2 = 0,   // exactly 2x: every fetch has fraction 0 or 1/2 at texels X>>1, (X+1)>>1 (the byte-tile kernel)
+       LEVEL0_SHARED   = 1,   // tap `off` of output X fetches what output X+off fetches at its centre: separable staging
+       LEVEL0_PER_TAP  = 2 }; // neither: every tap is fetched at its own coordinate
 int march_level0_u8(const uint8_t* img, size_t img_pitch, int w, int h, float shift, const OctaveView& o0,
-                    const Taps& dd, const Taps& inc0, int R, cudaStream_t st);
+                    const Taps& dd, const Taps& inc0, int R, int plan, cudaStream_t st);
 int march_level0_f32(const float* img, size_t img_pitch, int w, int h, float shift, const OctaveView& o0,
-                     const Taps& dd, const Taps& inc0, int R, cudaStream_t st);
+                     const Taps& dd, const Taps& inc0, int R, int plan, cudaStream_t st);
 
 } // namespace psb

@@ -379,21 +379,12 @@ march_level_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
 
 // ---- octave 0, level 0 from the input image -----------------------------------------------------
 
-struct AxisTap { int i0, i1, a; };
+using AxisTap = TexAxis;
 
+// the coordinate the reference hands to tex2D for virtual sample X (s_pyramid_build.cu:108-131): (X + shift) / N0
 __device__ __forceinline__ AxisTap virt_axis(int X, float shift, int N0, int n)
-{   // see k_pyramid.cu: the measured behaviour of the reference's input texture
-    float f = __fmul_rn(__fdiv_rn(__fadd_rn((float)X, shift), (float)N0), (float)n) - 0.5f;
-    f = fminf(fmaxf(f, -0.5f), (float)n - 0.5f);
-    const float fl = floorf(f);
-    int i = (int)fl;
-    int a = (int)floorf(__fmaf_rn(f - fl, 256.0f, 0.5f));
-    if (a == 256) { a = 0; i += 1; }
-    AxisTap t;
-    t.i0 = clampi(i, 0, n - 1);
-    t.i1 = clampi(i + 1, 0, n - 1);
-    t.a = a;
-    return t;
+{
+    return tex_axis(__fdiv_rn(__fadd_rn((float)X, shift), (float)N0), n);
 }
 
 // unorm16 -> float exactly as the texture unit: (float)r16 / 65535.0f, correctly rounded.
@@ -410,7 +401,7 @@ __device__ __forceinline__ float unorm16_to_float(unsigned r16)
 
 // General path (any scale factor, 8-bit or float input): every staged sample is one emulated
 // bilinear texture fetch.
-template <int R, typename PIX>
+template <int R, typename PIX, bool EXACT>
 __device__ __forceinline__ void level0_body(float* __restrict__ smem, AxisTap* __restrict__ ax, AxisTap* __restrict__ ay,
                                             const PIX* __restrict__ img, size_t img_pitch, int w, int h, float shift,
                                             float* __restrict__ dst, int W, int H, int pitch, int x0, int ys, int ye,
@@ -422,8 +413,10 @@ __device__ __forceinline__ void level0_body(float* __restrict__ smem, AxisTap* _
     float* HB = smem + G::NBUF * Q * G::SWP;
     const int nchunks = (ye - ys + 2 * R + Q - 1) / Q;
 
-    for (int i = threadIdx.x; i < G::SW; i += NT) ax[i] = virt_axis(x0 - G::RP + i, shift, W, w);
-    __syncthreads();
+    if (!EXACT) {
+        for (int i = threadIdx.x; i < G::SW; i += NT) ax[i] = virt_axis(x0 - G::RP + i, shift, W, w);
+        __syncthreads();
+    }
 
     int slot_in = 0;
     for (int k = 0; k < nchunks; ++k) {
@@ -432,26 +425,26 @@ __device__ __forceinline__ void level0_body(float* __restrict__ smem, AxisTap* _
         // rows outside the octave clamp to the border row of the row-filtered plane
         if (threadIdx.x < Q) ay[threadIdx.x] = virt_axis(clampi(iy + threadIdx.x, 0, H - 1), shift, H, h);
         __syncthreads();
-        for (int e = threadIdx.x; e < Q * G::SW; e += NT) {
-            const int j = e / G::SW;
-            const int i = e - j * G::SW;
-            const AxisTap ty = ay[j];
-            const AxisTap tx = ax[i];
-            const PIX* r0 = img + (size_t)ty.i0 * img_pitch;
-            const PIX* r1 = img + (size_t)ty.i1 * img_pitch;
-            float v;
-            if (sizeof(PIX) == 1) {
-                const unsigned t00 = (unsigned)r0[tx.i0], t10 = (unsigned)r0[tx.i1];
-                const unsigned t01 = (unsigned)r1[tx.i0], t11 = (unsigned)r1[tx.i1];
-                v = unorm16_to_float(tex_blend_u8(t00, t10, t01, t11, tx.a, ty.a));
-            } else {
-                v = tex_blend_f32((float)r0[tx.i0], (float)r0[tx.i1], (float)r1[tx.i0], (float)r1[tx.i1], tx.a, ty.a);
+        if (EXACT) {
+            // every tap at the reference's own coordinate: thread = column, one chunk row after the other
+            static_assert(NT == TW, "one thread per output column");
+            const int X = min(x0 + (int)threadIdx.x, W - 1);
+            for (int j = 0; j < Q; ++j) {
+                int slot = slot_in + j;
+                if (slot >= G::RING) slot -= G::RING;
+                HB[slot * HBW + threadIdx.x] = level0_row_sample<R, PIX>(img, img_pitch, w, ay[j], X, shift, W, dd);
             }
-            Scur[j * G::SWP + i] = v;
+            __syncthreads();
+        } else {
+            for (int e = threadIdx.x; e < Q * G::SW; e += NT) {
+                const int j = e / G::SW;
+                const int i = e - j * G::SW;
+                Scur[j * G::SWP + i] = tex_fetch(img, img_pitch, ax[i], ay[j]);
+            }
+            __syncthreads();
+            row_pass<R, true>(Scur, HB, slot_in, dd);
+            __syncthreads();
         }
-        __syncthreads();
-        row_pass<R, true>(Scur, HB, slot_in, dd);
-        __syncthreads();
         int slot_old = slot_in + Q;
         if (slot_old >= G::RING) slot_old -= G::RING;
         col_pass<R, false, false>(HB, Scur, Scur, slot_old, ys - 2 * R + k * Q, ys, ye, x0, W, dst, nullptr, nullptr, pitch, 0, inc0);
@@ -460,7 +453,7 @@ __device__ __forceinline__ void level0_body(float* __restrict__ smem, AxisTap* _
     }
 }
 
-template <int R, typename PIX>
+template <int R, typename PIX, bool EXACT>
 __global__ void __launch_bounds__(NT)
 march_level0_kernel(const PIX* __restrict__ img, size_t img_pitch, int w, int h, float shift,
                     float* __restrict__ dst, int W, int H, int pitch, Partition part, Taps dd, Taps inc0)
@@ -471,7 +464,7 @@ march_level0_kernel(const PIX* __restrict__ img, size_t img_pitch, int w, int h,
     __shared__ AxisTap ay[Q];
     int strip, ys, ye;
     if (!locate(part, blockIdx.x, H, Q, strip, ys, ye)) return;
-    level0_body<R, PIX>(smem, ax, ay, img, img_pitch, w, h, shift, dst, W, H, pitch, strip * TW, ys, ye, dd, inc0);
+    level0_body<R, PIX, EXACT>(smem, ax, ay, img, img_pitch, w, h, shift, dst, W, H, pitch, strip * TW, ys, ye, dd, inc0);
 }
 
 // ---- octave 0, level 0, the default case: 8-bit input, exactly 2x up-scaled -------------------------
@@ -659,10 +652,10 @@ int run_march(const OctaveView& o, int level, const Taps& t, float* next0, int n
 
 template <int R, typename PIX>
 int run_march0(const PIX* img, size_t img_pitch, int w, int h, float shift, const OctaveView& o0, const Taps& dd,
-               const Taps& inc0, cudaStream_t st)
+               const Taps& inc0, int plan, cudaStream_t st)
 {
     if constexpr (sizeof(PIX) == 1) {
-        const bool x2 = shift == 1.0f && o0.w == 2 * w && o0.h == 2 * h && (img_pitch & 3) == 0 &&
+        const bool x2 = plan == LEVEL0_IDEAL_X2 && shift == 1.0f && o0.w == 2 * w && o0.h == 2 * h && (img_pitch & 3) == 0 &&
                         (reinterpret_cast<uintptr_t>(img) & 3) == 0;
         if (x2) {
             const Partition part = make_partition(o0.w, o0.h, level0_slots());
@@ -673,9 +666,15 @@ int run_march0(const PIX* img, size_t img_pitch, int w, int h, float shift, cons
         }
     }
     const Partition part = make_partition(o0.w, o0.h);
-    ensure_smem(march_level0_kernel<R, PIX>, Geo<R>::smem, true);
-    march_level0_kernel<R, PIX><<<part.B, NT, Geo<R>::smem, st>>>(img, img_pitch, w, h, shift, o0.gauss, o0.w, o0.h,
-                                                                  o0.pitch, part, dd, inc0);
+    if (plan == LEVEL0_PER_TAP) {
+        ensure_smem(march_level0_kernel<R, PIX, true>, Geo<R>::smem, true);
+        march_level0_kernel<R, PIX, true><<<part.B, NT, Geo<R>::smem, st>>>(img, img_pitch, w, h, shift, o0.gauss, o0.w, o0.h,
+                                                                            o0.pitch, part, dd, inc0);
+    } else {
+        ensure_smem(march_level0_kernel<R, PIX, false>, Geo<R>::smem, true);
+        march_level0_kernel<R, PIX, false><<<part.B, NT, Geo<R>::smem, st>>>(img, img_pitch, w, h, shift, o0.gauss, o0.w, o0.h,
+                                                                             o0.pitch, part, dd, inc0);
+    }
     return 1;
 }
 
@@ -699,10 +698,10 @@ int march_blur_level(const OctaveView& o, int level, const Taps& t, int R, float
 }
 
 int march_level0_u8(const uint8_t* img, size_t img_pitch, int w, int h, float shift, const OctaveView& o0,
-                    const Taps& dd, const Taps& inc0, int R, cudaStream_t st)
+                    const Taps& dd, const Taps& inc0, int R, int plan, cudaStream_t st)
 {
     switch (R) {
-#define PSB_CASE(N) case N: return run_march0<N, uint8_t>(img, img_pitch, w, h, shift, o0, dd, inc0, st);
+#define PSB_CASE(N) case N: return run_march0<N, uint8_t>(img, img_pitch, w, h, shift, o0, dd, inc0, plan, st);
         PSB_CASE(3) PSB_CASE(4) PSB_CASE(5) PSB_CASE(6) PSB_CASE(7) PSB_CASE(8) PSB_CASE(9)
 #undef PSB_CASE
         default: return -1;
@@ -710,10 +709,10 @@ int march_level0_u8(const uint8_t* img, size_t img_pitch, int w, int h, float sh
 }
 
 int march_level0_f32(const float* img, size_t img_pitch, int w, int h, float shift, const OctaveView& o0,
-                     const Taps& dd, const Taps& inc0, int R, cudaStream_t st)
+                     const Taps& dd, const Taps& inc0, int R, int plan, cudaStream_t st)
 {
     switch (R) {
-#define PSB_CASE(N) case N: return run_march0<N, float>(img, img_pitch, w, h, shift, o0, dd, inc0, st);
+#define PSB_CASE(N) case N: return run_march0<N, float>(img, img_pitch, w, h, shift, o0, dd, inc0, plan, st);
         PSB_CASE(3) PSB_CASE(4) PSB_CASE(5) PSB_CASE(6) PSB_CASE(7) PSB_CASE(8) PSB_CASE(9)
 #undef PSB_CASE
         default: return -1;

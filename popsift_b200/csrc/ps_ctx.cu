@@ -807,6 +807,12 @@ extern "C" int ps_debug_plane(ps_ctx* ctx, int slot, int octave, int level, int 
     return PS_OK;
 }
 
+extern "C" int ps_debug_level0_plan(int w, int h, int W, int H, float shift, int R)
+{
+    if (w < 1 || h < 1 || W < 1 || H < 1 || R < 0 || R >= PS_GAUSS_ALIGN) return PS_ERR_ARG;
+    return psb::level0_plan_for(w, h, W, H, shift, R);
+}
+
 extern "C" int ps_debug_extrema(ps_ctx* ctx, int slot, ps_extremum* out, int cap)
 {
     Slot* s = get_slot(ctx, slot);

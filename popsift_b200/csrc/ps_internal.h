@@ -114,6 +114,7 @@ int sm_count();
 
 struct GaussRow { float tap[PS_GAUSS_ALIGN]; int span; };
 
+int level0_plan_for(int w, int h, int W, int H, float shift, int R);   // k_pyramid.cu: LEVEL0_* choice for one geometry
 // octave 0, level 0 from the 8-bit or float input image
 int launch_level0_u8(const uint8_t* img, size_t img_pitch, int w, int h, float upscale, int sift_mode,
                      const OctaveView& o0, const GaussRow& dd, const GaussRow& inc0, cudaStream_t st);

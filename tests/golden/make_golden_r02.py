@@ -124,6 +124,25 @@ def main(src):
                              "ours_vs_ref_a": {k: (len(v) if k == "ori_diffs" else v) for k, v in f["ours_vs_ref_a"].items()}}
                             for f in r["frames"]]}
         json.dump(small, open(os.path.join(HERE, "bench32_parity.json"), "w"), indent=1)
+    # ---- texture coordinates at non-integer scale factors (`texprobe coords 700 500 0.5`, `coords 640 480 1.5`)
+    probes = (("a", "tex_c700_up05.bin", 0.5), ("b", "tex_c640_up15.bin", 1.5))
+    if all(os.path.exists(os.path.join(src, fn)) for _, fn, _ in probes):
+        import struct
+        out = {}
+        for tag, fn, up in probes:
+            data = open(os.path.join(src, fn), "rb").read()
+            w, h, W0, H0, nrows, maxoff = struct.unpack_from("6i", data, 0)
+            rows = np.frombuffer(data, np.int32, nrows, 24)
+            off = 24 + 4 * nrows
+            img = np.frombuffer(data, np.uint8, w * h, off).reshape(h, w).copy()
+            o = np.frombuffer(data, np.float32, nrows * W0 * (2 * maxoff + 1), off + w * h).reshape(nrows, W0, 2 * maxoff + 1)
+            r16 = np.rint(o.astype(np.float64) * 65535).astype(np.int64)          # the unit returns r16 / 65535
+            assert ((r16.astype(np.float32) / np.float32(65535)) == o).all()
+            sel, xs = [0, 3, 7, 8, 12, 15, 16, 17], np.arange(0, W0, 7)
+            out[tag + "_img"], out[tag + "_rows"], out[tag + "_xs"] = img, rows[sel], xs.astype(np.int32)
+            out[tag + "_r16"] = r16[sel][:, xs, :].astype(np.uint16)
+            out[tag + "_meta"], out[tag + "_up"] = np.array([w, h, W0, H0, maxoff], np.int32), np.float32(up)
+        np.savez_compressed(os.path.join(HERE, "texture_coords.npz"), **out)
 
 
 if __name__ == "__main__":

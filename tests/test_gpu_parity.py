@@ -137,6 +137,8 @@ def test_1080p_counts_vs_golden():
     (800, 600, 22, "vlfeat", "classic", ["--gauss-mode", "opencv"]),       # OpenCV filter widths (gauss_filter.cu:320-327)
     (640, 480, 23, "popsift", "rootsift", ["--gauss-mode", "opencv", "--sigma", "1.2", "--levels", "4"]),
     (700, 500, 24, "vlfeat", "classic", ["--downsampling", "-0.5"]),       # non-integer up-scale: general texture fractions
+    (640, 480, 25, "popsift", "rootsift", ["--downsampling", "0.5"]),      # non-integer down-scale
+    (641, 479, 26, "vlfeat", "classic", ["--downsampling", "1"]),          # odd extent halved: not a power-of-two ratio
 ])
 def test_live_against_reference_library(tmp_path, w, h, seed, mode, norm, extra):
     """same bytes -> reference libpopsift (compiled from /root/reference for sm_100) and this library,
@@ -164,12 +166,9 @@ def test_live_against_reference_library(tmp_path, w, h, seed, mode, norm, extra)
     assert feats.getFeatureCount() == len(rf), (feats.getFeatureCount(), len(rf))
     assert feats.getDescriptorCount() == len(rd), (feats.getDescriptorCount(), len(rd))
     r = compare.report(*feats.keypoints(), *ol.flatten(rf, rd))
-    # Non-integer up-scale factors put the input texture's sample points at general fractions of a texel; the blend
-    # arithmetic there is pinned (texture_u8_general.npz) but the texture unit's float -> fixed-point conversion of
-    # the COORDINATE is only pinned for power-of-two ratios, so a few samples land one 1/256 step apart: same
-    # keypoints, same counts, descriptors within 1e-2 instead of 1e-3 (accepted-but-different).
-    l2_bound = 1e-2 if ("--downsampling" in extra and float(extra[extra.index("--downsampling") + 1]) % 1.0 != 0.0) else L2_MAX
-    assert r["f1"] >= F1_MIN and r["desc_l2_max"] < l2_bound, r
+    # non-integer up-scale factors included: the texture unit's coordinate arithmetic is pinned (texture_coords.npz) and
+    # every tap is then fetched at the reference's own coordinate (LEVEL0_PER_TAP)
+    assert r["f1"] >= F1_MIN and r["desc_l2_max"] < L2_MAX, r
     ps.uninit()
 
 
@@ -700,3 +699,37 @@ def test_planes_bit_exact_vs_oracle_1080p():
                     bad.append(("d", oc, l))
         assert not bad, bad
         ps.uninit(); o.close()
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/ref_dump not built")
+@pytest.mark.parametrize("w,h,seed,extra", [
+    (700, 500, 24, ["--downsampling", "-0.5"]),      # 2^0.5: every tap at its own coordinate
+    (640, 480, 27, ["--downsampling", "-1.5"]),      # 2^1.5
+    (641, 479, 26, ["--downsampling", "1"]),         # 321 x 240 from 641 x 479
+    (5000, 96, 28, []),                              # 2x of a frame wider than 4096 that is not a power of two: the
+                                                     # 21-bit coordinate truncation shows even at the default scale
+    (4096, 64, 29, []),                              # power-of-two width: coordinates exact, ideal 2x pattern
+    (1000, 700, 30, ["--downsampling", "0"]),        # 1:1
+])
+def test_level0_planes_bit_exact_vs_live_reference(tmp_path, w, h, seed, extra):
+    """Octave 0 of the reference's own --log dumps (Gaussian levels and DoG) against this library's planes, bit for bit,
+    for scale factors and extents where the input texture's coordinate arithmetic matters."""
+    img = make_frame(w, h, seed)
+    write_pgm(str(tmp_path / "f.pgm"), img)
+    subprocess.run([REF, "-i", "f.pgm", "-o", "f.bin", "--log", "--octaves", "2"] + extra, cwd=str(tmp_path), check=True, capture_output=True)
+    kw = {"octaves": 2}
+    if "--downsampling" in extra:
+        kw["downsampling"] = float(extra[extra.index("--downsampling") + 1])
+    ps, feats = run_gpu(img, mk_cfg(**kw))
+    bad = []
+    for oc in range(2):
+        for l in range(6):
+            ref = ol.read_ref_dump(str(tmp_path / "dir-octave-dump" / ("pyramid-o-%d-l-%d.dump" % (oc, l))))
+            mine = ps.plane(0, oc, l)
+            assert ref.shape == mine.shape, (ref.shape, mine.shape)
+            if not np.array_equal(ref, mine):
+                bad.append(("g", oc, l, int((ref != mine).sum())))
+    assert not bad, bad
+    rf, rd = ol.read_ref_features(str(tmp_path / "f.bin"))
+    assert (feats.getFeatureCount(), feats.getDescriptorCount()) == (len(rf), len(rd))
+    ps.uninit()

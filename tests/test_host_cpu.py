@@ -309,3 +309,44 @@ def test_result_arrays_keep_their_page_locked_block_alive():
     del f, d
     gc.collect()
     assert not L.live                                      # freed when the last view died
+
+
+def test_level0_plan_follows_the_texture_coordinate_model():
+    """ps_debug_level0_plan (host arithmetic, the same tex_axis the kernels run) against a numpy restatement of the
+    measured coordinate model: the benchmark's 2x geometries keep the byte-tile kernel, other power-of-two ratios share
+    fetches, everything else -- non-integer scale factors, odd extents halved, non-power-of-two widths beyond 4096
+    at 2x -- fetches per tap."""
+    f32 = np.float32
+
+    def tex_axis(c, n):
+        c = np.clip(c, f32(-1), f32(2)).astype(np.float32)
+        q = np.floor(c * f32(2097152.0)).astype(np.int64)
+        I = np.clip(((q * n + 4096) >> 13) - 128, -128, n * 256 - 128)
+        i, a = I >> 8, I & 255
+        i0, i1 = np.clip(i, 0, n - 1), np.clip(i + 1, 0, n - 1)
+        a = np.where(i0 == i1, 0, a)
+        return i0, np.where(a == 0, i0, i1), a
+
+    def centre(X, shift, N0):
+        return ((X.astype(np.float32) + f32(shift)) / f32(N0)).astype(np.float32)
+
+    def shared(w, W, shift, R):
+        X = np.arange(W)
+        cx = centre(X, shift, W)
+        for off in range(-R, R + 1):
+            rel = f32(abs(off)) / f32(W)
+            A = tex_axis((cx - rel if off < 0 else cx + rel).astype(np.float32), w)
+            B = tex_axis(centre(X + off, shift, W), w)
+            if any((a != b).any() for a, b in zip(A, B)):
+                return False
+        return True
+
+    L = api.load_library()
+    expect_fixed = {(3840, 2160, 1.0): 0, (1920, 1080, 1.0): 0, (4096, 2160, 1.0): 0, (640, 480, 0.0): 1, (640, 480, -1.0): 1,
+                    (640, 480, 2.0): 1, (640, 480, 0.5): 2, (641, 479, -1.0): 2, (5000, 96, 1.0): 2}
+    for (w, h, up), want in expect_fixed.items():
+        W, H = int(np.ceil(f32(w) * f32(2.0 ** up))), int(np.ceil(f32(h) * f32(2.0 ** up)))
+        shift = float(f32(0.5) * f32(2.0 ** up))
+        got = L.ps_debug_level0_plan(w, h, W, H, shift, 4)
+        assert got == want, (w, h, up, got, want)
+        assert (got != 2) == shared(w, W, shift, 4), (w, h, up)
