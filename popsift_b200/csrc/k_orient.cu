@@ -27,7 +27,7 @@ namespace psb {
 
 namespace {
 
-constexpr int WARPS = 4;
+constexpr int kWarps = 4;        // keypoints (warps) per CTA
 constexpr int kSlice = PS_ORI_SLICE;   // extrema per slice of the descriptor-index scan (ori_scatter_kernel)
 __device__ const float kPi  = 3.14159265358979323846f;
 __device__ const float kPi2 = 2.0f * 3.14159265358979323846f;
@@ -49,7 +49,7 @@ __device__ __forceinline__ int octave_prefix(const Counters* ct, const Consts& k
 
 // ATOMIC = true: histogram by shared float atomics like the reference (default); false: lane-private bins summed in
 // lane order (POPSIFT_B200_ORI_LANESUM=1; run-to-run deterministic by construction, ~20 % faster, not the reference's sums)
-template <bool ATOMIC>
+template <bool ATOMIC, int WARPS, int BATCH>
 __global__ void __launch_bounds__(WARPS * 32)
 orientation_kernel(PyramidView pyr, Consts k, const InitialExtremum* __restrict__ iext_all, const InitialExtremum* __restrict__ iext_f,
                    ps_extremum* __restrict__ ext, int* __restrict__ slice_sum, Counters* ct)
@@ -102,33 +102,51 @@ orientation_kernel(PyramidView pyr, Consts k, const InitialExtremum* __restrict_
         // All lanes of an iteration reconverge before the atomic, like the reference's warp does.
         int xx = xmin + lane, yy = ymin;
         while (xx > xmax && wx > 0) { xx -= wx; ++yy; }
-        for (int i0 = 0; i0 < loops; i0 += 32) {
-            int bidx = -1;
-            float weight = 0.0f;
-            if (i0 + lane < loops) {
-                const float ddx = __fsub_rn((float)xx, x), ddy = __fsub_rn((float)yy, y);
-                const int sq_dist = (int)__fmaf_rn(ddx, ddx, __fmul_rn(ddy, ddy));
-                if (sq_dist <= sq_thres) {
-                    const float* p = pl + (yy * ov.pitch + xx);         // a plane holds < 2^31 floats
-                    const float gdx = __fsub_rn(__ldg(p + 1), __ldg(p - 1));
-                    const float gdy = __fsub_rn(__ldg(p + ov.pitch), __ldg(p - ov.pitch));
-                    const float grad = hypotf(gdx, gdy);
-                    const float theta = atan2f(gdy, gdx);
-                    weight = __fmul_rn(grad, expf(__fmul_rn((float)sq_dist, factor)));
-                    // reference SASS (ori_par): (theta + pi) * 36 * 0.15915494 -- the division by the constant 2 pi of
-                    // __fdividef(36 * (theta + pi), M_PI2) is folded into a multiplication by RN(1 / 2pi)
-                    bidx = (int)roundf(__fmul_rn(__fmul_rn(__fadd_rn(theta, kPi), (float)kOriBins), 0.15915493667125701904f));
-                    if (bidx == kOriBins) bidx = 0;
-                    if (bidx > kOriBins) bidx = -1;
+        // BATCH iterations are evaluated together -- positions first, then all gradient loads (samples outside the window
+        // or the circle read the window's first pixel and are dropped afterwards), then the hypotf / atan2f / expf chains side
+        // by side -- and their atomics issued in iteration order: per bin, the adds still arrive iteration by iteration, the
+        // lanes of one iteration together.
+        const float* safe = pl + (max(ymin, 1) * ov.pitch + max(xmin, 1));
+        for (int i0 = 0; i0 < loops; i0 += 32 * BATCH) {
+            int bidx[BATCH], sq[BATCH];
+            float weight[BATCH];
+            const float* p[BATCH];
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) {
+                sq[u] = -1; p[u] = safe;
+                if (i0 + 32 * u + lane < loops) {
+                    const float ddx = __fsub_rn((float)xx, x), ddy = __fsub_rn((float)yy, y);
+                    const int sq_dist = (int)__fmaf_rn(ddx, ddx, __fmul_rn(ddy, ddy));
+                    if (sq_dist <= sq_thres) { sq[u] = sq_dist; p[u] = pl + (yy * ov.pitch + xx); }   // a plane holds < 2^31 floats
+                    xx += 32;
+                    while (xx > xmax) { xx -= wx; ++yy; }
                 }
-                xx += 32;
-                while (xx > xmax) { xx -= wx; ++yy; }
             }
-            if (ATOMIC) {
-                __syncwarp();
-                if (bidx >= 0) atomicAdd(&A[bidx], weight);
-            } else if (bidx >= 0) {
-                Hp[bidx * 33 + lane] += weight;
+            float gdx[BATCH], gdy[BATCH];
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) {
+                gdx[u] = __fsub_rn(__ldg(p[u] + 1), __ldg(p[u] - 1));
+                gdy[u] = __fsub_rn(__ldg(p[u] + ov.pitch), __ldg(p[u] - ov.pitch));
+            }
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) {
+                const float grad = hypotf(gdx[u], gdy[u]);
+                const float theta = atan2f(gdy[u], gdx[u]);
+                weight[u] = __fmul_rn(grad, expf(__fmul_rn((float)sq[u], factor)));
+                // reference SASS (ori_par): (theta + pi) * 36 * 0.15915494 -- the division by the constant 2 pi of
+                // __fdividef(36 * (theta + pi), M_PI2) is folded into a multiplication by RN(1 / 2pi)
+                int b = (int)roundf(__fmul_rn(__fmul_rn(__fadd_rn(theta, kPi), (float)kOriBins), 0.15915493667125701904f));
+                if (b == kOriBins) b = 0;
+                bidx[u] = (sq[u] < 0 || b > kOriBins) ? -1 : b;
+            }
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) {
+                if (ATOMIC) {
+                    __syncwarp();
+                    if (bidx[u] >= 0) atomicAdd(&A[bidx[u]], weight[u]);
+                } else if (bidx[u] >= 0) {
+                    Hp[bidx[u] * 33 + lane] += weight[u];
+                }
             }
         }
         __syncwarp();
@@ -300,8 +318,16 @@ int launch_orientation(const PyramidView& pyr, const Consts& k, const InitialExt
 {
     // fixed grid: SMs x 8 resident CTAs of 4 warps; warps stride over the device-side count
     static const bool lanesum = [] { const char* e = getenv("POPSIFT_B200_ORI_LANESUM"); return e && e[0] == '1'; }();
-    if (lanesum) orientation_kernel<false><<<sm_count() * 8, WARPS * 32, 0, st>>>(pyr, k, iext, iext_f, ext, slice_sum, ct);
-    else         orientation_kernel<true><<<sm_count() * 8, WARPS * 32, 0, st>>>(pyr, k, iext, iext_f, ext, slice_sum, ct);
+    // experiments: POPSIFT_B200_ORI_WARPS=1 -> one warp per CTA like the reference's ori_par; POPSIFT_B200_ORI_GRID=n -> n CTAs
+    static const int one_warp = [] { const char* e = getenv("POPSIFT_B200_ORI_WARPS"); return e && e[0] == '1'; }();
+    static const int grid_env = [] { const char* e = getenv("POPSIFT_B200_ORI_GRID"); return e ? atoi(e) : 0; }();
+    const int grid = grid_env > 0 ? grid_env : sm_count() * 8;
+    static const int batch = [] { const char* e = getenv("POPSIFT_B200_ORI_BATCH"); return e ? atoi(e) : 1; }();
+    if (lanesum)         orientation_kernel<false, kWarps, 1><<<grid, kWarps * 32, 0, st>>>(pyr, k, iext, iext_f, ext, slice_sum, ct);
+    else if (one_warp)   orientation_kernel<true, 1, 1><<<grid_env > 0 ? grid_env : sm_count() * 32, 32, 0, st>>>(pyr, k, iext, iext_f, ext, slice_sum, ct);
+    else if (batch == 2) orientation_kernel<true, kWarps, 2><<<grid, kWarps * 32, 0, st>>>(pyr, k, iext, iext_f, ext, slice_sum, ct);
+    else if (batch == 4) orientation_kernel<true, kWarps, 4><<<grid, kWarps * 32, 0, st>>>(pyr, k, iext, iext_f, ext, slice_sum, ct);
+    else                 orientation_kernel<true, kWarps, 1><<<grid, kWarps * 32, 0, st>>>(pyr, k, iext, iext_f, ext, slice_sum, ct);
     ori_scatter_kernel<<<k.ext_capacity / kSlice + 1, kSlice, 0, st>>>(pyr.num_octaves, k, ext, feat_to_ext, slice_sum, ct);
     return 2;
 }

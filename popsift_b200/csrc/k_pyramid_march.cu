@@ -55,7 +55,9 @@ struct Geo {
     // ahead where four buffers still leave room for 4 CTAs per SM (R <= 8).
     static constexpr int NBUF = (R <= 8) ? 4 : 3;
     static constexpr int AHEAD = NBUF - 2;
-    static constexpr int RING = Q + 2 * R;              // lines in the ring buffer
+    // lines in the ring buffer: Q + 2R rounded up to a multiple of 8, so that every window of the column pass starts on
+    // a multiple of 8 and wraps between two blocks of 8 lines (col_pass)
+    static constexpr int RING = (Q + 2 * R + 7) / 8 * 8;
     static constexpr size_t smem = sizeof(float) * (NBUF * Q * SWP + RING * HBW);   // staging buffers + ring
     static_assert(R <= Q, "centre rows must still be in the two staging buffers");
     static_assert((Q * SWP * sizeof(float)) % 128 == 0, "staging buffers stay 128-byte aligned (TMA destination)");
@@ -276,16 +278,20 @@ __device__ __forceinline__ void col_pass(const float* __restrict__ HB, const flo
     const int c2 = 2 * (threadIdx.x & 63);
     const int jbase = (threadIdx.x >> 6) * QH;          // 0 or Q/2 (warp-uniform)
     f32x2 win[QH + 2 * R];
-    int first = slot_oldest + jbase;                    // ring slot of the first window line (warp-uniform)
+    int first = slot_oldest + jbase;                    // ring slot of the first window line (warp-uniform, a multiple of 8)
     if (first >= G::RING) first -= G::RING;
-    // the window wraps around the ring at most once: lines before the wrap use base a0, the others a1,
-    // both with compile-time offsets
-    const int nw = G::RING - first;
+    // The window wraps around the ring at most once, and only between two blocks of 8 lines (RING, the chunk height and the
+    // half-chunk offset are multiples of 8): one base-pointer select per block, every line at a compile-time offset from it.
+    const int nb = (G::RING - first) >> 3;              // blocks before the wrap
     const float* a0 = HB + first * HBW + c2;
     const float* a1 = a0 - G::RING * HBW;
 #pragma unroll
-    for (int i = 0; i < QH + 2 * R; ++i)
-        win[i] = *reinterpret_cast<const f32x2*>((i < nw ? a0 : a1) + i * HBW);
+    for (int b = 0; b < (QH + 2 * R + 7) / 8; ++b) {
+        const float* base = (b < nb) ? a0 : a1;
+#pragma unroll
+        for (int i = 8 * b; i < 8 * b + 8 && i < QH + 2 * R; ++i)
+            win[i] = *reinterpret_cast<const f32x2*>(base + i * HBW);
+    }
     const int x = x0 + c2;
     const int yb = y_first + jbase;
     if (yb + QH <= ys || yb >= ye) return;                     // nothing of this half-block is inside the segment (warp-uniform)
