@@ -554,7 +554,7 @@ static void orientation_one(const orc_ctx* c, const iext_t* ie, ext_t* e)
             float grad, theta;
             get_gradiant(&grad, &theta, xx, yy, pl, W, H);
             const float ddx = (float)xx - x, ddy = (float)yy - y;
-            const int sq_dist = (int)(ddx * ddx + ddy * ddy);
+            const int sq_dist = (int)fmaf(ddy, ddy, ddx * ddx);   /* reference SASS: FMUL dx*dx ; FFMA dy*dy + . ; F2I.TRUNC */
             if (sq_dist <= sq_thres) {
                 const float weight = grad * expf((float)sq_dist * factor);
                 /* reference SASS: (theta + pi) * 36 * RN(1 / 2pi) (the constant division is folded) */

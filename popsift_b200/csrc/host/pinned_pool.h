@@ -2,9 +2,14 @@
 #pragma once
 #include "popsift_b200.h"
 
+#include <algorithm>
+#include <condition_variable>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <mutex>
+#include <thread>
+#include <vector>
 
 namespace popsift { namespace detail {
 
@@ -60,5 +65,78 @@ inline PinnedPool& pinned_pool()
     return *p;
 }
 
+// The caller's image is pageable; enqueue() copies it into a page-locked block (like the reference, popsift.cpp:392-395).
+// One core moves 8 MB in about a millisecond -- as long as a 4K frame takes on the GPU -- and much longer on a busy host, so
+// large images are copied by a few helper threads in parallel (POPSIFT_B200_COPY_THREADS, default 4, 1 = plain memcpy).
+class ParallelCopy {
+public:
+    void copy(void* dst, const void* src, size_t n)
+    {
+        const int parts = threads_;
+        if (parts <= 1 || n < (size_t)(2u << 20)) { std::memcpy(dst, src, n); return; }
+        std::lock_guard<std::mutex> one_at_a_time(call_mu_);
+        start_helpers();
+        const size_t chunk = ((n + parts - 1) / parts + 4095) & ~(size_t)4095;
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            dst_ = static_cast<unsigned char*>(dst); src_ = static_cast<const unsigned char*>(src); n_ = n; chunk_ = chunk;
+            pending_ = parts - 1;
+            ++generation_;
+        }
+        cv_.notify_all();
+        std::memcpy(dst, src, std::min(chunk, n));                       // part 0 on the calling thread
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [&] { return pending_ == 0; });
+    }
+    static ParallelCopy& instance()
+    {
+        static ParallelCopy* p = new ParallelCopy;   // leaked like the pool: helpers are detached and sleep on the condition variable
+        return *p;
+    }
+private:
+    ParallelCopy()
+    {
+        const char* e = std::getenv("POPSIFT_B200_COPY_THREADS");
+        int t = e ? std::atoi(e) : 4;
+        const int hw = (int)std::thread::hardware_concurrency();
+        if (hw > 0 && t > hw) t = hw;
+        threads_ = std::max(1, std::min(t, 16));
+    }
+    void start_helpers()
+    {
+        if (started_) return;
+        started_ = true;
+        for (int k = 1; k < threads_; ++k)
+            std::thread([this, k] {
+                unsigned long long seen = 0;
+                for (;;) {
+                    unsigned char* d; const unsigned char* s; size_t n, chunk;
+                    {
+                        std::unique_lock<std::mutex> lk(mu_);
+                        cv_.wait(lk, [&] { return generation_ != seen; });
+                        seen = generation_;
+                        d = dst_; s = src_; n = n_; chunk = chunk_;
+                    }
+                    const size_t off = chunk * (size_t)k;
+                    if (off < n) std::memcpy(d + off, s + off, std::min(chunk, n - off));
+                    {
+                        std::lock_guard<std::mutex> g(mu_);
+                        --pending_;
+                    }
+                    done_cv_.notify_one();
+                }
+            }).detach();
+    }
+    std::mutex call_mu_, mu_;
+    std::condition_variable cv_, done_cv_;
+    unsigned char* dst_ = nullptr;
+    const unsigned char* src_ = nullptr;
+    size_t n_ = 0, chunk_ = 0;
+    int pending_ = 0, threads_ = 1;
+    unsigned long long generation_ = 0;
+    bool started_ = false;
+};
+
+inline void parallel_copy(void* dst, const void* src, size_t n) { ParallelCopy::instance().copy(dst, src, n); }
 
 }} // namespace popsift::detail

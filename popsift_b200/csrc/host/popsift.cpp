@@ -40,7 +40,7 @@ SiftJob::SiftJob(int w, int h, const unsigned char* imageData) : _w(w), _h(h), _
     // reference's two, popsift.cpp:392-395 + s_image.cu:75)
     _imageData = static_cast<unsigned char*>(popsift::detail::pinned_pool().get(n ? n : 1));
     if (!_imageData) throw std::runtime_error("Memory limitation\nE    Failed to allocate memory for SiftJob");
-    std::memcpy(_imageData, imageData, n);
+    popsift::detail::parallel_copy(_imageData, imageData, n);
 }
 
 SiftJob::SiftJob(int w, int h, const float* imageData) : _w(w), _h(h), _isFloat(true)
@@ -51,7 +51,7 @@ SiftJob::SiftJob(int w, int h, const float* imageData) : _w(w), _h(h), _isFloat(
     // reference's two, popsift.cpp:392-395 + s_image.cu:75)
     _imageData = static_cast<unsigned char*>(popsift::detail::pinned_pool().get(n ? n : 1));
     if (!_imageData) throw std::runtime_error("Memory limitation\nE    Failed to allocate memory for SiftJob");
-    std::memcpy(_imageData, imageData, n);
+    popsift::detail::parallel_copy(_imageData, imageData, n);
 }
 
 SiftJob::~SiftJob() { popsift::detail::pinned_pool().put(_imageData); }

@@ -68,7 +68,15 @@ orientation_kernel(PyramidView pyr, Consts k, const InitialExtremum* __restrict_
     float* A = sm_a[warp];
     float* B = sm_b[warp];
 
-    for (int item = blockIdx.x * WARPS + warp; item < total; item += gridDim.x * WARPS) {
+    // Keypoints cost between ~150 and ~1100 samples and a resident warp only gets about three of them, so a static
+    // assignment leaves the SMs 72 % busy on average; every warp instead draws its next keypoint from a device-side
+    // cursor (zeroed with the frame's counters), one draw ahead so that the atomic's latency hides behind the current one.
+    int pend = 0;
+    if (lane == 0) pend = atomicAdd(&ct->work_ori, 1);
+    for (;;) {
+        const int item = __shfl_sync(0xffffffffu, pend, 0);
+        if (item >= total) break;
+        if (lane == 0) pend = atomicAdd(&ct->work_ori, 1);
         int o = 0;
         while (o + 1 < pyr.num_octaves && item >= ps[o + 1]) ++o;
         const InitialExtremum ie = iext[(size_t)o * k.max_extrema + (item - ps[o])];
@@ -116,7 +124,10 @@ orientation_kernel(PyramidView pyr, Consts k, const InitialExtremum* __restrict_
                 sq[u] = -1; p[u] = safe;
                 if (i0 + 32 * u + lane < loops) {
                     const float ddx = __fsub_rn((float)xx, x), ddy = __fsub_rn((float)yy, y);
-                    const int sq_dist = (int)__fmaf_rn(ddx, ddx, __fmul_rn(ddy, ddy));
+                    // reference SASS (ori_par): FMUL dx*dx, then FFMA dy*dy + that, F2I.TRUNC -- the contraction nvcc chose;
+                    // the other operand order differs in the last bit often enough to move int(sq_dist) for about one
+                    // keypoint in a thousand (a 1 % change of one sample's weight, angles off by ~1e-5 rad)
+                    const int sq_dist = (int)__fmaf_rn(ddy, ddy, __fmul_rn(ddx, ddx));
                     if (sq_dist <= sq_thres) { sq[u] = sq_dist; p[u] = pl + (yy * ov.pitch + xx); }   // a plane holds < 2^31 floats
                     xx += 32;
                     while (xx > xmax) { xx -= wx; ++yy; }
@@ -322,7 +333,7 @@ int launch_orientation(const PyramidView& pyr, const Consts& k, const InitialExt
     static const int one_warp = [] { const char* e = getenv("POPSIFT_B200_ORI_WARPS"); return e && e[0] == '1'; }();
     static const int grid_env = [] { const char* e = getenv("POPSIFT_B200_ORI_GRID"); return e ? atoi(e) : 0; }();
     const int grid = grid_env > 0 ? grid_env : sm_count() * 8;
-    static const int batch = [] { const char* e = getenv("POPSIFT_B200_ORI_BATCH"); return e ? atoi(e) : 1; }();
+    static const int batch = [] { const char* e = getenv("POPSIFT_B200_ORI_BATCH"); return e ? atoi(e) : 4; }();
     if (lanesum)         orientation_kernel<false, kWarps, 1><<<grid, kWarps * 32, 0, st>>>(pyr, k, iext, iext_f, ext, slice_sum, ct);
     else if (one_warp)   orientation_kernel<true, 1, 1><<<grid_env > 0 ? grid_env : sm_count() * 32, 32, 0, st>>>(pyr, k, iext, iext_f, ext, slice_sum, ct);
     else if (batch == 2) orientation_kernel<true, kWarps, 2><<<grid, kWarps * 32, 0, st>>>(pyr, k, iext, iext_f, ext, slice_sum, ct);

@@ -280,17 +280,20 @@ __device__ __forceinline__ void col_pass(const float* __restrict__ HB, const flo
     f32x2 win[QH + 2 * R];
     int first = slot_oldest + jbase;                    // ring slot of the first window line (warp-uniform, a multiple of 8)
     if (first >= G::RING) first -= G::RING;
-    // The window wraps around the ring at most once, and only between two blocks of 8 lines (RING, the chunk height and the
-    // half-chunk offset are multiples of 8): one base-pointer select per block, every line at a compile-time offset from it.
+    // `first` is the line Q + 2R' lines before the newest (R' = R rounded so that the ring is a multiple of 8); the window
+    // proper starts PAD lines later.  It wraps around the ring at most once, and only between two blocks of 8 lines (RING,
+    // the chunk height and the half-chunk offset are multiples of 8): one base-pointer select per block, every line at a
+    // compile-time offset from it.
+    constexpr int PAD = G::RING - Q - 2 * R;
     const int nb = (G::RING - first) >> 3;              // blocks before the wrap
     const float* a0 = HB + first * HBW + c2;
     const float* a1 = a0 - G::RING * HBW;
 #pragma unroll
-    for (int b = 0; b < (QH + 2 * R + 7) / 8; ++b) {
+    for (int b = 0; b < (PAD + QH + 2 * R + 7) / 8; ++b) {
         const float* base = (b < nb) ? a0 : a1;
 #pragma unroll
-        for (int i = 8 * b; i < 8 * b + 8 && i < QH + 2 * R; ++i)
-            win[i] = *reinterpret_cast<const f32x2*>(base + i * HBW);
+        for (int p = (8 * b > PAD ? 8 * b : PAD); p < 8 * b + 8 && p < PAD + QH + 2 * R; ++p)
+            win[p - PAD] = *reinterpret_cast<const f32x2*>(base + p * HBW);
     }
     const int x = x0 + c2;
     const int yb = y_first + jbase;

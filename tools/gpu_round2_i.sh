@@ -4,7 +4,7 @@ set -uo pipefail
 cd "$(dirname "$0")/.."
 O=gpurun_out/r02i; mkdir -p $O
 ( cat /proc/loadavg; nproc ) > $O/host.txt 2>&1; cat $O/host.txt
-timeout 1200 python -m pytest tests -q -m gpu -x -k "planes or benchmark_workload or full_size or features_vs_golden or fallback" > $O/pytest_sel.txt 2>&1; tail -5 $O/pytest_sel.txt
+timeout 1500 python -m pytest tests -q -m gpu -x > $O/pytest_sel.txt 2>&1; tail -5 $O/pytest_sel.txt
 timeout 600 python bench.py --steps 5 --warmup 3 > $O/bench.json 2> $O/bench.err; tail -2 $O/bench.err
 python - "$O/bench.json" <<'PY'
 import json,sys
@@ -19,5 +19,6 @@ python tools/summarize_launches.py $O/launches_b1.csv > $O/launches.txt 2>&1; he
 for B in 2 4; do
   POPSIFT_B200_ORI_BATCH=$B timeout 900 python -m pytest tests -q -m gpu -x -k "benchmark_workload or features_vs_golden" > $O/pytest_batch$B.txt 2>&1; tail -2 $O/pytest_batch$B.txt
 done
+timeout 600 python tools/match_bench.py $O/match_bench.json 2> $O/match_bench.err | tail -1
 timeout 900 python tools/ori_experiment.py $O/ori_experiment.json > $O/ori_experiment.txt 2>&1; cat $O/ori_experiment.txt | tail -12
 du -sh gpurun_out
