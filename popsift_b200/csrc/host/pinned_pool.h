@@ -3,6 +3,8 @@
 #include "popsift_b200.h"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
@@ -66,8 +68,10 @@ inline PinnedPool& pinned_pool()
 }
 
 // The caller's image is pageable; enqueue() copies it into a page-locked block (like the reference, popsift.cpp:392-395).
-// One core moves 8 MB in about a millisecond -- as long as a 4K frame takes on the GPU -- and much longer on a busy host, so
-// large images are copied by a few helper threads in parallel (POPSIFT_B200_COPY_THREADS, default 4, 1 = plain memcpy).
+// One core moves 8 MB in about a millisecond -- as long as a 4K frame takes on the GPU -- so large images are copied by a few
+// helper threads in parallel (POPSIFT_B200_COPY_THREADS, default 4; 1 = plain memcpy).  A caller enqueues its images back to
+// back, so a helper spins for a short while after a copy before it goes to sleep on the condition variable: waking a
+// sleeping thread costs more than the copy it is woken for.
 class ParallelCopy {
 public:
     void copy(void* dst, const void* src, size_t n)
@@ -77,20 +81,20 @@ public:
         std::lock_guard<std::mutex> one_at_a_time(call_mu_);
         start_helpers();
         const size_t chunk = ((n + parts - 1) / parts + 4095) & ~(size_t)4095;
-        {
+        dst_ = static_cast<unsigned char*>(dst); src_ = static_cast<const unsigned char*>(src); n_ = n; chunk_ = chunk;
+        pending_.store(parts - 1, std::memory_order_relaxed);
+        generation_.fetch_add(1);                                       // seq_cst: ordered against the sleepers_ load below
+        if (sleepers_.load() > 0) {
             std::lock_guard<std::mutex> g(mu_);
-            dst_ = static_cast<unsigned char*>(dst); src_ = static_cast<const unsigned char*>(src); n_ = n; chunk_ = chunk;
-            pending_ = parts - 1;
-            ++generation_;
+            cv_.notify_all();
         }
-        cv_.notify_all();
         std::memcpy(dst, src, std::min(chunk, n));                       // part 0 on the calling thread
-        std::unique_lock<std::mutex> lk(mu_);
-        done_cv_.wait(lk, [&] { return pending_ == 0; });
+        for (unsigned spins = 0; pending_.load(std::memory_order_acquire) != 0; ++spins)
+            if (spins > 2000) std::this_thread::yield();
     }
     static ParallelCopy& instance()
     {
-        static ParallelCopy* p = new ParallelCopy;   // leaked like the pool: helpers are detached and sleep on the condition variable
+        static ParallelCopy* p = new ParallelCopy;   // leaked like the pool: the helpers are detached
         return *p;
     }
 private:
@@ -110,30 +114,33 @@ private:
             std::thread([this, k] {
                 unsigned long long seen = 0;
                 for (;;) {
-                    unsigned char* d; const unsigned char* s; size_t n, chunk;
-                    {
-                        std::unique_lock<std::mutex> lk(mu_);
-                        cv_.wait(lk, [&] { return generation_ != seen; });
-                        seen = generation_;
-                        d = dst_; s = src_; n = n_; chunk = chunk_;
+                    // spin ~100 us for the next copy of a burst, then sleep
+                    const auto t0 = std::chrono::steady_clock::now();
+                    unsigned polls = 0;
+                    while (generation_.load(std::memory_order_acquire) == seen) {
+                        if ((++polls & 255u) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(100)) {
+                            std::unique_lock<std::mutex> lk(mu_);
+                            sleepers_.fetch_add(1);
+                            cv_.wait(lk, [&] { return generation_.load() != seen; });
+                            sleepers_.fetch_sub(1);
+                            break;
+                        }
                     }
-                    const size_t off = chunk * (size_t)k;
-                    if (off < n) std::memcpy(d + off, s + off, std::min(chunk, n - off));
-                    {
-                        std::lock_guard<std::mutex> g(mu_);
-                        --pending_;
-                    }
-                    done_cv_.notify_one();
+                    seen = generation_.load(std::memory_order_acquire);
+                    const size_t off = chunk_ * (size_t)k;
+                    if (off < n_) std::memcpy(dst_ + off, src_ + off, std::min(chunk_, n_ - off));
+                    pending_.fetch_sub(1, std::memory_order_release);
                 }
             }).detach();
     }
     std::mutex call_mu_, mu_;
-    std::condition_variable cv_, done_cv_;
+    std::condition_variable cv_;
     unsigned char* dst_ = nullptr;
     const unsigned char* src_ = nullptr;
     size_t n_ = 0, chunk_ = 0;
-    int pending_ = 0, threads_ = 1;
-    unsigned long long generation_ = 0;
+    std::atomic<int> pending_{0}, sleepers_{0};
+    std::atomic<unsigned long long> generation_{0};
+    int threads_ = 1;
     bool started_ = false;
 };
 

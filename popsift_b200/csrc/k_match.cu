@@ -168,10 +168,9 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar)
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// 32 consecutive fp32 columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32])
+// 32 consecutive fp32 columns of this thread's TMEM lane: issue (the registers are valid after tmem_ld_wait)
+__device__ __forceinline__ void tmem_ld32_issue(unsigned taddr, unsigned (&r)[32])
 {
-    unsigned r[32];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                  "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
                  "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -180,9 +179,55 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32])
                    "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
                    "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                  : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Candidate bookkeeping of one left descriptor (one epilogue thread): the four smallest keys seen so far and where they
+// came from.  A key is the approximate distance |b|^2 - 2 a.b with its 5 low mantissa bits replaced by the column's index
+// inside its group of 32 (relative 2^-18: far below what separates candidates that matter, the exact re-rank follows), so
+// that the group's minimum -- a branch-free FMNMX tree -- carries its own position.
+struct Top4 {
+    float t0 = INFINITY, t1 = INFINITY, t2 = INFINITY, t3 = INFINITY;
+    int i0 = -1, i1 = -1, i2 = -1, i3 = -1;
+    __device__ __forceinline__ void insert(float key, int idx)           // key < t3
+    {
+        t3 = key; i3 = idx;
+        if (t3 < t2) { float tf = t2; t2 = t3; t3 = tf; int ti = i2; i2 = i3; i3 = ti;
+            if (t2 < t1) { tf = t1; t1 = t2; t2 = tf; ti = i1; i1 = i2; i2 = ti;
+                if (t1 < t0) { tf = t0; t0 = t1; t1 = tf; ti = i0; i0 = i1; i1 = ti; } } }
+    }
+};
+
+// one group of 32 columns: r = raw accumulator bits (a.b), rn = |b|^2 of the 32 columns, nb = index of the group's first column
+__device__ __forceinline__ void top4_group(Top4& T, const unsigned (&r)[32], const float4 (&rn)[8], int nb)
+{
+    float k[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    for (int i4 = 0; i4 < 8; ++i4) {
+        const float rr[4] = {rn[i4].x, rn[i4].y, rn[i4].z, rn[i4].w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i4 * 4 + u;
+            const float val = fmaf(-2.0f, __uint_as_float(r[i]), rr[u]);          // |b|^2 - 2 a.b  (+inf for padding)
+            k[i] = __uint_as_float((__float_as_uint(val) & 0xffffffe0u) | (unsigned)i);   // padding: inf -> inf (i = 0) or NaN
+        }
+    }
+    float m[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) m[i] = fminf(k[i], k[i + 16]);                  // fminf drops NaNs
+#pragma unroll
+    for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+        for (int i = 0; i < w; ++i) m[i] = fminf(m[i], m[i + w]);
+    float best = m[0];
+    // rare after the first tiles: the k-th best of n random items improves about 4 / n of the time
+    while (best < T.t3) {
+        T.insert(best, nb + (int)(__float_as_uint(best) & 31u));
+        float nxt = INFINITY;                                                  // the group's next key above `best`
+#pragma unroll
+        for (int i = 0; i < 32; ++i) nxt = (k[i] > best) ? fminf(nxt, k[i]) : nxt;
+        best = nxt;
+    }
 }
 
 // Every CTA walks the right set from a different tile, so that the CTAs do not all pull the same lines out of the same L2
@@ -286,39 +331,44 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tm_lhi, const __grid_constan
         // ===== epilogue: thread = one left descriptor = one TMEM lane =====
         const int q = warp & 3;                                  // TMEM lanes 32q .. 32q+31 belong to warps with warp % 4 == q
         const int row = m0 + q * 32 + lane;
-        float t0 = INFINITY, t1 = INFINITY, t2 = INFINITY, t3 = INFINITY;
-        int i0 = -1, i1 = -1, i2 = -1, i3 = -1;
+        Top4 T;
+        const unsigned lane_base = tmem_base + ((unsigned)(q * 32) << 16);
         for (int j = 0; j < n_tiles; ++j) {
             const int buf = j & 1;
+            const int nb0 = tile_of<ROT>(j, n_tiles) * BN;
+            const float4* rn4 = reinterpret_cast<const float4*>(rnorm + nb0);
+            // |b|^2 of the first group is on its way while the accumulator is still being written
+            float4 rnA[8], rnB[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rnA[i] = __ldg(rn4 + i);
             mb_wait(&acc_full[buf], (unsigned)(j >> 1) & 1u);
             tc_fence_after();
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                float v[32];
-                tmem_ld32(tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(buf * BN + c0), v);
-                const int nb = tile_of<ROT>(j, n_tiles) * BN + c0;
-                const float4* rn4 = reinterpret_cast<const float4*>(rnorm + nb);
+            // four groups of 32 columns, two register sets: group g+1 is loaded from TMEM while group g is processed
+            unsigned ra[32], rb[32];
+            tmem_ld32_issue(lane_base + (unsigned)(buf * BN), ra);
+            tmem_ld_wait();
+            tmem_ld32_issue(lane_base + (unsigned)(buf * BN + 32), rb);
 #pragma unroll
-                for (int i4 = 0; i4 < 8; ++i4) {
-                    const float4 rn = __ldg(rn4 + i4);
-                    const float rr[4] = {rn.x, rn.y, rn.z, rn.w};
+            for (int i = 0; i < 8; ++i) rnB[i] = __ldg(rn4 + 8 + i);
+            top4_group(T, ra, rnA, nb0);
+            tmem_ld_wait();
+            tmem_ld32_issue(lane_base + (unsigned)(buf * BN + 64), ra);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float val = fmaf(-2.0f, v[i4 * 4 + u], rr[u]);       // |b|^2 - 2 a.b  (+inf for padding)
-                        if (val < t3) {
-                            t3 = val; i3 = nb + i4 * 4 + u;
-                            if (t3 < t2) { float tf = t2; t2 = t3; t3 = tf; int ti = i2; i2 = i3; i3 = ti;
-                                if (t2 < t1) { tf = t1; t1 = t2; t2 = tf; ti = i1; i1 = i2; i2 = ti;
-                                    if (t1 < t0) { tf = t0; t0 = t1; t1 = tf; ti = i0; i0 = i1; i1 = ti; } } }
-                        }
-                    }
-                }
-            }
+            for (int i = 0; i < 8; ++i) rnA[i] = __ldg(rn4 + 16 + i);
+            top4_group(T, rb, rnB, nb0 + 32);
+            tmem_ld_wait();
+            tmem_ld32_issue(lane_base + (unsigned)(buf * BN + 96), rb);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rnB[i] = __ldg(rn4 + 24 + i);
+            top4_group(T, ra, rnA, nb0 + 64);
+            tmem_ld_wait();
+            // the accumulator has been read completely: hand it back before the last group is processed
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mb_arrive(&acc_empty[buf]);
+            top4_group(T, rb, rnB, nb0 + 96);
         }
-        if (row < nl) *reinterpret_cast<int4*>(cand + (size_t)row * kCand) = make_int4(i0, i1, i2, i3);
+        if (row < nl) *reinterpret_cast<int4*>(cand + (size_t)row * kCand) = make_int4(T.i0, T.i1, T.i2, T.i3);
     }
     tc_fence_before();
     __syncthreads();
