@@ -387,8 +387,8 @@ __device__ __forceinline__ void stage3(const PyramidView& pyr, const Consts& k, 
     }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kScanThreads, 4)
+template <int MODE, int CTAS>
+__global__ void __launch_bounds__(kScanThreads, CTAS)
 cand_extrema_kernel(PyramidView pyr, Consts k, InitialExtremum* __restrict__ iext, Counters* ct)
 {
     __shared__ Q2Entry q2[kScanThreads / 32][kQ2];
@@ -436,24 +436,48 @@ cand_extrema_kernel(PyramidView pyr, Consts k, InitialExtremum* __restrict__ iex
     // level (the level kernels have as many CTAs as this grid has blocks), so a block that draws a textured area would
     // draw it fifteen times; rotating the assignment by a stride coprime to the grid from one pass to the next spreads
     // the areas over the blocks (cycles active: average / maximum 0.78 -> see profiles).
+    // The count and the first candidates of the NEXT region are requested before the current region is processed (the list
+    // address does not depend on the count, entries beyond it are simply ignored), so a region costs one memory round trip
+    // -- its plane samples -- instead of three in a row.
     const int G = (int)gridDim.x;
-    for (int pass = 0, g0 = 0; g0 < nreg; ++pass, g0 += G) {
+    struct Region { const unsigned* list; int o, level, cap; bool valid; };
+    auto prepare = [&](int pass, Region& r, int& cnt, unsigned& first) -> bool {
+        const int g0 = pass * G;
+        if (g0 >= nreg) return false;
         const int g = g0 + (int)(((unsigned)blockIdx.x + (unsigned)pass * 197u) % (unsigned)G);
-        if (g >= nreg) continue;
-        const int cnt = __ldg(pyr.cand_cnt_all + g);           // block-uniform
-        if (cnt <= 0) continue;
-        int o = 0, local = g;                                    // region -> octave, q * cand_blocks + block
-        while (local >= pyr.oct[o].cand_blocks * L) { local -= pyr.oct[o].cand_blocks * L; ++o; }
-        const OctaveView& ovv = pyr.oct[o];
-        const int level = local / ovv.cand_blocks + 1;           // DoG plane of the region's samples
-        const int n = min(cnt, ovv.cand_region);                 // reported pairs
-        const unsigned* __restrict__ list = ovv.cand + (size_t)local * ovv.cand_region;
+        r.valid = g < nreg;
+        cnt = 0; first = 0u;
+        if (r.valid) {
+            int o = 0, local = g;                                // region -> octave, (level - 1) * cand_blocks + block
+            while (local >= pyr.oct[o].cand_blocks * L) { local -= pyr.oct[o].cand_blocks * L; ++o; }
+            const OctaveView& ovv = pyr.oct[o];
+            r.o = o;
+            r.level = local / ovv.cand_blocks + 1;               // DoG plane of the region's samples
+            r.cap = ovv.cand_region;
+            r.list = ovv.cand + (size_t)local * ovv.cand_region;
+            cnt = __ldg(pyr.cand_cnt_all + g);                   // block-uniform
+            if ((int)threadIdx.x < r.cap) first = __ldg(r.list + threadIdx.x);
+        }
+        return true;
+    };
+    Region nx; int cnt_nx = 0; unsigned first_nx = 0u;
+    int pass = 0;
+    bool more = prepare(pass, nx, cnt_nx, first_nx);
+    while (more) {
+        const Region cur = nx;
+        const int cnt = cnt_nx;
+        const unsigned first = first_nx;
+        more = prepare(++pass, nx, cnt_nx, first_nx);
+        if (!cur.valid || cnt <= 0) continue;
+        const int o = cur.o, level = cur.level;
+        const int n = min(cnt, cur.cap);                         // reported pairs
+        const unsigned* __restrict__ list = cur.list;
         const DogOct ov = octave_view(o);
         for (int t0 = warp * 32; t0 < n; t0 += kScanThreads) {
             const int t = t0 + lane;
             unsigned packed = 0u, res = 0u;
             if (t < n) {
-                packed = __ldg(list + t);
+                packed = t0 == warp * 32 ? first : __ldg(list + t);
                 res = stage1_pair<MODE>(ov, level, thr, (int)(packed & 0xffffu), (int)(packed >> 16));
             }
 #pragma unroll
@@ -490,7 +514,10 @@ template <int MODE>
 int launch_scan(const PyramidView& pyr, const Consts& k, InitialExtremum* iext, Counters* ct, cudaStream_t st)
 {
     if (pyr.cands_filled && !dense_choice()) {
-        cand_extrema_kernel<MODE><<<sm_count() * 4, kScanThreads, 0, st>>>(pyr, k, iext, ct);
+        // resident CTAs per SM: 4 (64 registers, some spills) or 3 (80 registers); POPSIFT_B200_EXTREMA_CTAS, A/B timing
+        static const int ctas = [] { const char* e = getenv("POPSIFT_B200_EXTREMA_CTAS"); return e && atoi(e) == 3 ? 3 : 4; }();
+        if (ctas == 3) cand_extrema_kernel<MODE, 3><<<sm_count() * 3, kScanThreads, 0, st>>>(pyr, k, iext, ct);
+        else           cand_extrema_kernel<MODE, 4><<<sm_count() * 4, kScanThreads, 0, st>>>(pyr, k, iext, ct);
         return 1;
     }
     int launches = 0;

@@ -23,7 +23,7 @@
 //                             candidates in the reference's own evaluation order (per lane x*x, fma, fma, fma over its
 //                             float4, shuffle-down tree 16, 8, 4, 2, 1) and applies the reference's scan rule
 //                             (strict <, ties keep the lower index) and ratio test.
-// The result equals the reference's except when three or more right descriptors lie within ~1e-6 of the second
+// The result equals the reference's except when three or more right descriptors lie within ~4e-6 (relative) of the second
 // best (the candidate pass could then miss the reference's pick among exact near-ties).
 // match_exact_kernel is the same computation on CUDA cores (one warp per left descriptor over all right ones): used
 // for small problems and as the in-library cross-check (PS_MATCH_EXACT).
@@ -33,6 +33,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 namespace psb {
 
@@ -433,16 +434,35 @@ int run_match(const ps_descriptor* l, int nl, const ps_descriptor* r, int nr, in
     float *lhi = nullptr, *llo = nullptr, *rhi = nullptr, *rlo = nullptr, *rnorm = nullptr;
     int32_t* cand = nullptr;
     const size_t lb = (size_t)nl_pad * 512, rb = (size_t)nr_pad * 512;
-    // one workspace allocation per call (stream-ordered, so nothing blocks)
+    // one workspace allocation per call, stream-ordered so nothing blocks, from the library's own pool per device: a pool
+    // gives freed memory back to the OS at the next synchronisation unless told to keep it, and mapping 50 MB again on
+    // every call costs more than the matching itself (the application's default pool is left alone)
+    cudaMemPool_t pool = nullptr;
+    {
+        static std::mutex mu;
+        static cudaMemPool_t pools[64] = {};
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); *err = "cudaGetDevice failed (matcher)"; return -1; }
+        std::lock_guard<std::mutex> g(mu);
+        if (!pools[dev]) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            if (cudaMemPoolCreate(&pools[dev], &props) != cudaSuccess) { cudaGetLastError(); pools[dev] = nullptr; *err = "cudaMemPoolCreate failed (matcher)"; return -1; }
+            unsigned long long keep = 1ull << 30;                          // up to 1 GB of freed workspace stays mapped
+            cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        pool = pools[dev];
+    }
     uint8_t* ws = nullptr;
     const size_t total = 2 * lb + 2 * rb + (size_t)nr_pad * 4 + (size_t)nl_pad * kCand * 4;
-    if (cudaMallocAsync(&ws, total, st) != cudaSuccess) { *err = "cudaMallocAsync failed (matcher workspace)"; cudaGetLastError(); return -1; }
+    if (cudaMallocFromPoolAsync(&ws, total, pool, st) != cudaSuccess) { *err = "cudaMallocFromPoolAsync failed (matcher workspace)"; cudaGetLastError(); return -1; }
     lhi = reinterpret_cast<float*>(ws); llo = reinterpret_cast<float*>(ws + lb);
     rhi = reinterpret_cast<float*>(ws + 2 * lb); rlo = reinterpret_cast<float*>(ws + 2 * lb + rb);
     rnorm = reinterpret_cast<float*>(ws + 2 * lb + 2 * rb);
     cand = reinterpret_cast<int32_t*>(ws + 2 * lb + 2 * rb + (size_t)nr_pad * 4);
-    match_split_kernel<<<(nl_pad + 3) / 4, 128, 0, st>>>(l, nl, nl_pad, lhi, llo, nullptr);
-    match_split_kernel<<<(nr_pad + 3) / 4, 128, 0, st>>>(r, nr, nr_pad, rhi, rlo, rnorm);
     // POPSIFT_B200_MATCH_RING = 128 | 64 | 128r | 64r: rows per B stage, r = every CTA starts at a different tile (A/B timing)
     static const int ring_cfg = [] {
         const char* e = getenv("POPSIFT_B200_MATCH_RING");
@@ -455,6 +475,8 @@ int run_match(const ps_descriptor* l, int nl, const ps_descriptor* r, int nr, in
                     make_tmap_2d(&m_rhi, rhi, 128, nr_pad, 512, KB, bns, true) && make_tmap_2d(&m_rlo, rlo, 128, nr_pad, 512, KB, bns, true);
     if (!ok) { cudaFreeAsync(ws, st); *err = "cuTensorMapEncodeTiled failed (matcher)"; return -1; }
     static_assert(TC_SMEM + 2048 <= 227 * 1024, "matcher shared memory");
+    match_split_kernel<<<(nl_pad + 3) / 4, 128, 0, st>>>(l, nl, nl_pad, lhi, llo, nullptr);
+    match_split_kernel<<<(nr_pad + 3) / 4, 128, 0, st>>>(r, nr, nr_pad, rhi, rlo, rnorm);
     auto launch = [&](auto kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
         kern<<<nl_pad / BM, TC_THREADS, TC_SMEM, st>>>(m_lhi, m_llo, m_rhi, m_rlo, rnorm, nl, n_tiles, cand);

@@ -402,11 +402,9 @@ def test_benchmark_workload_matches_reference_exactly(tmp_path):
         json.dump(diff_rows, open(os.path.join(out_dir, "bench32_angle_diffs.json"), "w"))
     assert tot == golden["totals"]["ref_a"] == [453753, 522542]
     assert worst_l2 < L2_MAX, worst_l2
-    # The orientation SETS are identical (same number of orientations for every one of the 453 753 keypoints).  The angles
-    # are bit-equal for all but a few hundredths of a percent of the keypoints, whose histograms differ in the last bit
-    # somewhere (the remaining suspects: libdevice's hypotf / atan2f / expf are compiled without FMA contraction here,
-    # with it in the reference); a nearly flat peak parabola amplifies that to at most ~2e-4 rad.
-    assert angle_diffs <= tot[0] // 1000 and worst_angle < 1e-3, (worst_angle, angle_diffs)
+    # orientation sets AND angles are bit-identical for every one of the 453 753 keypoints (the histogram is accumulated
+    # like the reference's and the three compiler-chosen contractions of ori_par are restated)
+    assert angle_diffs == 0 and worst_angle == 0.0, (worst_angle, angle_diffs)
     print("bench32 parity: %d features / %d descriptors identical; keypoints whose angles differ in the last bits: %d, "
           "max angle diff %.3g rad, max descriptor L2 %.3g" % (tot[0], tot[1], angle_diffs, worst_angle, worst_l2))
 
