@@ -514,8 +514,9 @@ template <int MODE>
 int launch_scan(const PyramidView& pyr, const Consts& k, InitialExtremum* iext, Counters* ct, cudaStream_t st)
 {
     if (pyr.cands_filled && !dense_choice()) {
-        // resident CTAs per SM: 4 (64 registers, some spills) or 3 (80 registers); POPSIFT_B200_EXTREMA_CTAS, A/B timing
-        static const int ctas = [] { const char* e = getenv("POPSIFT_B200_EXTREMA_CTAS"); return e && atoi(e) == 3 ? 3 : 4; }();
+        // resident CTAs per SM: 3 (80 registers: 77.7 us per 4K frame) or 4 (64 registers, spills in the candidate loop:
+        // 84.4 us); POPSIFT_B200_EXTREMA_CTAS=4 for A/B timing
+        static const int ctas = [] { const char* e = getenv("POPSIFT_B200_EXTREMA_CTAS"); return e && atoi(e) == 4 ? 4 : 3; }();
         if (ctas == 3) cand_extrema_kernel<MODE, 3><<<sm_count() * 3, kScanThreads, 0, st>>>(pyr, k, iext, ct);
         else           cand_extrema_kernel<MODE, 4><<<sm_count() * 4, kScanThreads, 0, st>>>(pyr, k, iext, ct);
         return 1;
