@@ -78,10 +78,6 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
 {
     unsigned ok, spins = 0;
@@ -210,12 +206,6 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm(
 
 constexpr int QH = Q / 2;   // output rows per thread in the column pass
 
-// Column-pass thread mapping: warp w owns output columns [32w, 32w + 32) -- exactly the columns whose row-filtered lines its
-// own lanes wrote in the row pass -- lanes 0..15 take the upper 8 rows of the chunk, lanes 16..31 the lower 8, each lane
-// one pair of adjacent columns.  (An LDS.64 / STG.64 is served per half-warp: 16 lanes x 8 bytes = one 128-byte line.)
-__device__ __forceinline__ int col_pair_x() { return 32 * (int)(threadIdx.x >> 5) + 2 * (int)(threadIdx.x & 15); }
-__device__ __forceinline__ int col_half_row() { return (int)((threadIdx.x >> 4) & 1) * QH; }
-
 // Candidates (CandSink): a lane notes the rows in which one of its two DoG samples passes the peak
 // threshold -- one compare pair and one predicated OR per row in the hot loop -- and afterwards, if it
 // has any, reserves entries of the block's list region with ONE shared-memory atomic and stores them.
@@ -226,7 +216,7 @@ __device__ __forceinline__ void col_emit(const f32x2 (&win)[QH + 2 * R], const f
                                          int pitch, int next_pitch, const Taps& t, const CandSink& sink, int* cand_n, int x, int W)
 {
     using G = Geo<R>;
-    const int c2 = col_pair_x();
+    const int c2 = 2 * (threadIdx.x & 63);
     const int par = y_first & 1;
     const bool col_in = !GUARD || x < W;            // GUARD: the pair may start right of the image
     unsigned pm = 0;
@@ -285,10 +275,10 @@ __device__ __forceinline__ void col_pass(const float* __restrict__ HB, const flo
                                          const CandSink& sink = CandSink(), int* cand_n = nullptr)
 {
     using G = Geo<R>;
-    const int c2 = col_pair_x();
-    const int jbase = col_half_row();                   // 0 or Q/2
+    const int c2 = 2 * (threadIdx.x & 63);
+    const int jbase = (threadIdx.x >> 6) * QH;          // 0 or Q/2 (warp-uniform)
     f32x2 win[QH + 2 * R];
-    int first = slot_oldest + jbase;                    // ring slot of the first window line (a multiple of 8)
+    int first = slot_oldest + jbase;                    // ring slot of the first window line (warp-uniform, a multiple of 8)
     if (first >= G::RING) first -= G::RING;
     // `first` is the line Q + 2R' lines before the newest (R' = R rounded so that the ring is a multiple of 8); the window
     // proper starts PAD lines later.  It wraps around the ring at most once, and only between two blocks of 8 lines (RING,
@@ -307,7 +297,7 @@ __device__ __forceinline__ void col_pass(const float* __restrict__ HB, const flo
     }
     const int x = x0 + c2;
     const int yb = y_first + jbase;
-    if (yb + QH <= ys || yb >= ye) return;                     // nothing of this half-block is inside the segment
+    if (yb + QH <= ys || yb >= ye) return;                     // nothing of this half-block is inside the segment (warp-uniform)
     const long long o = (long long)yb * pitch + x;             // may point outside for guarded samples (never dereferenced)
     float* pd = dst + o;
     float* pg = WRITE_DOG ? dog + o : nullptr;
@@ -319,7 +309,7 @@ __device__ __forceinline__ void col_pass(const float* __restrict__ HB, const flo
 }
 
 template <int R, bool EDGE, bool NEXT, bool CAND>
-__device__ __forceinline__ void march_body(float* __restrict__ smem, uint64_t* __restrict__ full, uint64_t* __restrict__ empty, bool own, const CUtensorMap* map,
+__device__ __forceinline__ void march_body(float* __restrict__ smem, uint64_t* __restrict__ full, const CUtensorMap* map,
                                            const float* __restrict__ src, float* __restrict__ dst,
                                            float* __restrict__ dog, float* __restrict__ next0, int W, int H, int pitch,
                                            int next_pitch, int x0, int ys, int ye, const Taps& taps, const CandSink& sink,
@@ -347,31 +337,18 @@ __device__ __forceinline__ void march_body(float* __restrict__ smem, uint64_t* _
         float* Scur = smem + cur * SB;
         float* Sprev = smem + (cur == 0 ? G::NBUF - 1 : cur - 1) * SB;
         mbar_wait(full + cur, parity);    // chunk k has landed
-        // A warp's column pass reads only ring lines that its own row pass wrote (col_pair_x), so between the two passes
-        // and from one chunk to the next the warp only has to agree with itself; whole-CTA barriers remain in border
-        // strips (their halo patch crosses warps) and when POPSIFT_B200_OWNED=0 asks for them (A/B timing).
-        const bool cta_sync = EDGE || !own;
-        if (cta_sync) __syncthreads(); else __syncwarp();
-        if (threadIdx.x == 0 && k + AHEAD < nchunks) {
-            // the buffer to refill held chunk k-2, last read (DoG centre rows) by column pass k-1: every warp has arrived
-            // on its `empty` barrier after that pass
-            if (k >= 2) mbar_wait(empty + ((k + AHEAD) % G::NBUF), (unsigned)((k + AHEAD) / G::NBUF - 1) & 1u);
-            issue(k + AHEAD);
-        }
+        __syncthreads();                  // column pass k-1 finished (ring + buffer of chunk k-2 are free)
+        if (threadIdx.x == 0 && k + AHEAD < nchunks) issue(k + AHEAD);
         if (EDGE) {
             patch_halo<R>(Scur, x0, W);
             __syncthreads();
         }
         row_pass<R, false>(Scur, HB, slot_in, taps);
-        if (cta_sync) __syncthreads(); else __syncwarp();
+        __syncthreads();
         int slot_old = slot_in + Q;       // oldest line = the one after the newest
         if (slot_old >= G::RING) slot_old -= G::RING;
         col_pass<R, true, NEXT, CAND>(HB, Scur, Sprev, slot_old, ys - 2 * R + k * Q, ys, ye, x0, W, dst, dog, next0, pitch,
                                       next_pitch, taps, sink, cand_n);
-        if (k >= 1) {                     // chunk k-1's staging buffer is dead for this warp
-            __syncwarp();
-            if ((threadIdx.x & 31) == 0) mbar_arrive(empty + (cur == 0 ? G::NBUF - 1 : cur - 1));
-        }
         slot_in = slot_old;
         if (cur == G::NBUF - 1) { cur = 0; parity ^= 1u; } else ++cur;
     }
@@ -383,12 +360,11 @@ template <int R, bool NEXT, bool CAND>
 __global__ void __launch_bounds__(NT, 4)
 march_level_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ src, float* __restrict__ dst,
                    float* __restrict__ dog, float* __restrict__ next0, int W, int H, int pitch, int next_pitch, Partition part,
-                   Taps taps, CandSink sink, int own)
+                   Taps taps, CandSink sink)
 {
     using G = Geo<R>;
     extern __shared__ __align__(128) float smem[];   // TMA destinations: 128-byte aligned (every staging buffer is)
-    __shared__ __align__(8) uint64_t full[G::NBUF];  // one mbarrier per staging buffer: its chunk has landed
-    __shared__ __align__(8) uint64_t empty[G::NBUF]; // ... and: every warp is done with the chunk it held
+    __shared__ __align__(8) uint64_t full[G::NBUF];  // one mbarrier per staging buffer
     __shared__ int s_cand_n;                         // candidates of this block so far
     int strip, ys, ye;
     if (!locate(part, blockIdx.x, H, Q, strip, ys, ye)) return;
@@ -396,7 +372,7 @@ march_level_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
     const bool edge = (x0 - G::RP < 0) || (x0 + TW + G::RP > W);
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int b = 0; b < G::NBUF; ++b) { mbar_init(full + b, 1); mbar_init(empty + b, NT / 32); }
+        for (int b = 0; b < G::NBUF; ++b) mbar_init(full + b, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (CAND) s_cand_n = 0;
     }
@@ -406,8 +382,8 @@ march_level_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     __syncthreads();
-    if (!edge) march_body<R, false, NEXT, CAND>(smem, full, empty, own != 0, &tmap, src, dst, dog, next0, W, H, pitch, next_pitch, x0, ys, ye, taps, sink, &s_cand_n);
-    else       march_body<R, true, NEXT, CAND>(smem, full, empty, own != 0, &tmap, src, dst, dog, next0, W, H, pitch, next_pitch, x0, ys, ye, taps, sink, &s_cand_n);
+    if (!edge) march_body<R, false, NEXT, CAND>(smem, full, &tmap, src, dst, dog, next0, W, H, pitch, next_pitch, x0, ys, ye, taps, sink, &s_cand_n);
+    else       march_body<R, true, NEXT, CAND>(smem, full, &tmap, src, dst, dog, next0, W, H, pitch, next_pitch, x0, ys, ye, taps, sink, &s_cand_n);
 }
 
 // ---- octave 0, level 0 from the input image -----------------------------------------------------
@@ -664,9 +640,8 @@ int launch_march(const Partition& part, const float* src, float* dst, float* dog
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl_choice() ? 1 : 0;
-    static const int own = [] { const char* e = getenv("POPSIFT_B200_OWNED"); return e && e[0] == '0' ? 0 : 1; }();
     return cudaLaunchKernelEx(&cfg, march_level_kernel<R, NEXT, CAND>, map, src, dst, dog, next0, o.w, o.h, o.pitch, next_pitch,
-                              part, t, sink, own) == cudaSuccess ? 1 : -2;
+                              part, t, sink) == cudaSuccess ? 1 : -2;
 }
 
 template <int R>
