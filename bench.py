@@ -211,9 +211,9 @@ class ClockSampler:
 
 # one `ncu --set full --clock-control none` capture of tools/one_frame.py 3840 2160 5 1 (round 1, after the
 # last kernel change); per frame / per octave-0 level launch
-NCU_SOURCE = "profiles/r01_ncu_full_frame_4k.csv"
-NCU_PYRAMID_DRAM_BYTES = 2215795712
-NCU_LEVEL_DRAM_BYTES = 367469568
+NCU_SOURCE = "profiles/r02_ncu_full_frame_4k.csv"
+NCU_PYRAMID_DRAM_BYTES = 2216593408
+NCU_LEVEL_DRAM_BYTES = 367803546
 
 
 def measured_peak():
@@ -415,7 +415,7 @@ def run_ours(args, rank, world, local_rank):
                      "peak": peak, "unit": "GB/s", "frac": alg_bytes_frame / (pyr * 1e-3) / 1e9 / peak, "peak_source": peak_src,
                      "algorithmic_bytes": alg_bytes_frame, "ms": pyr,
                      # dram__bytes_read.sum + dram__bytes_write.sum of the 26 pyramid launches of one frame, one
-                     # `ncu --set full` capture (profiles/r01_ncu_full_frame_4k.csv); below the algorithmic bytes
+                     # `ncu --set full` capture (profiles/r02_ncu_full_frame_4k.csv); below the algorithmic bytes
                      # because part of every plane is still dirty in the 126 MB L2 when its consumer starts
                      "traffic": NCU_PYRAMID_DRAM_BYTES, "traffic_source": NCU_SOURCE,
                      "dominant_kernel": {"name": "march_level_kernel (octave 0, levels 1..5: blur + DoG, avg per launch)",

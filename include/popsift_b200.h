@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PS_ABI_VERSION   2
+#define PS_ABI_VERSION   3
 #define PS_MAX_OCTAVES   20   /* reference sift_conf.h:12  MAX_OCTAVES   */
 #define PS_GAUSS_ALIGN   32   /* reference sift_constants.h:37            */
 #define PS_GAUSS_LEVELS  12   /* reference sift_constants.h:38            */
@@ -67,7 +67,7 @@ typedef struct ps_config {
     int32_t norm_multi;        /* descriptor scaled by 2^norm_multi                        */
     int32_t max_extrema;       /* 100000 per octave                                        */
     /* ABI 2 */
-    int32_t scaling_mode;      /* PS_SCALE_*  (only DEFAULT is implemented; DIRECT is REJECTED by ps_create)         */
+    int32_t scaling_mode;      /* PS_SCALE_*  (DIRECT: level 0 of every octave straight from the input image)         */
     int32_t filter_max_extrema;/* <= 0: grid filter off (reference sift_conf.cu:30, s_orientation.cu:380-383)        */
     int32_t filter_grid_size;  /* 2: cells per image side (s_filtergrid.cu:125)                                      */
     int32_t filter_sort;       /* PS_FILTER_*                                                                        */
@@ -104,6 +104,11 @@ typedef struct ps_gauss_tables {
     int32_t dd_span0;
     float   peak_threshold;                                /* sift_conf.cu:276-279 */
     float   sigma_k;                                       /* sift_constants.cu:27 */
+    /* ABI 3: the direct-downscaling rows of every octave (gauss_filter.cu:216-238), used by Config::ScaleDirect:
+     * level 0 of octave o is filtered horizontally with row o straight from the input image.  Row 0 == dd_filter0. */
+    float   dd_filter[PS_MAX_OCTAVES * PS_GAUSS_ALIGN];
+    float   dd_sigma[PS_MAX_OCTAVES];
+    int32_t dd_span[PS_MAX_OCTAVES];
 } ps_gauss_tables;
 
 enum { PS_STAGE_H2D = 0, PS_STAGE_PYRAMID = 1, PS_STAGE_EXTREMA = 2, PS_STAGE_ORIENT = 3,

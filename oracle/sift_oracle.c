@@ -51,6 +51,7 @@ void orc_default_config(orc_config* c)
     c->upscale = 1.0f; c->initial_blur = 0.5f; c->has_initial_blur = 1;
     c->sift_mode = ORC_MODE_POPSIFT; c->norm_mode = ORC_NORM_ROOTSIFT; c->norm_multi = 0;
     c->max_extrema = 100000;
+    c->scaling_mode = 0;
 }
 
 int orc_set_threads(int n)
@@ -116,6 +117,12 @@ int orc_compute_tables(const orc_config* c, orc_tables* t)
         float b = sqrtf(fabsf(oct_sigma * oct_sigma - initial_blur * initial_blur));
         t->dd_sigma0 = scalbnf(b, 0);
         blur_row(t->dd_sigma0, &t->dd_span0, t->dd_filter0);
+    }
+    for (int oct = 0; oct < ORC_MAX_OCTAVES; oct++) {       /* gauss_filter.cu:227-238, every row */
+        float oct_sigma = scalbnf(sigma0, oct);
+        float b = sqrtf(fabsf(oct_sigma * oct_sigma - initial_blur * initial_blur));
+        t->dd_sigma[oct] = scalbnf(b, -oct);
+        blur_row(t->dd_sigma[oct], &t->dd_span[oct], &t->dd_filter[oct * ORC_GAUSS_ALIGN]);
     }
     t->peak_threshold = c->threshold * 0.5f * 255.0f / (float)levels; /* sift_conf.cu:276-279 */
     t->sigma_k = powf(2.0f, 1.0f / (float)levels);                    /* sift_constants.cu:27 */
@@ -231,13 +238,15 @@ static inline float tex_any(const orc_ctx* c, const uint8_t* img, const float* f
     return fimg ? orc_tex_f32(fimg, c->w, c->h, rx, ry) : orc_tex_u8(img, c->w, c->h, rx, ry);
 }
 
-static void level0_rows(const orc_ctx* c, const uint8_t* img, const float* fimg, float* dst)
+/* normalizedSource::horiz (s_pyramid_build_ra.cu:17-55) for octave `oct` (0 in the default scaling mode; every octave under
+ * ScaleDirect, s_pyramid_build.cu:97-126,499-508): the dd row of that octave, shift 0.5 unless octave 0 in PopSift / VLFeat mode */
+static void level0_rows(const orc_ctx* c, const uint8_t* img, const float* fimg, float* dst, int oct)
 {
-    const int W0 = c->W[0], H0 = c->H[0];
-    const int span = c->tab.dd_span0;
-    const float* g = c->tab.dd_filter0;
+    const int W0 = c->W[oct], H0 = c->H[oct];
+    const int span = c->tab.dd_span[oct];
+    const float* g = &c->tab.dd_filter[oct * ORC_GAUSS_ALIGN];
     float shift = 0.5f;   /* s_pyramid_build.cu:108-114 */
-    if (c->cfg.sift_mode == ORC_MODE_POPSIFT || c->cfg.sift_mode == ORC_MODE_VLFEAT)
+    if (oct == 0 && (c->cfg.sift_mode == ORC_MODE_POPSIFT || c->cfg.sift_mode == ORC_MODE_VLFEAT))
         shift = 0.5f * powf(2.0f, c->cfg.upscale - 0);
     #pragma omp parallel for schedule(static)
     for (int Y = 0; Y < H0; Y++) {
@@ -307,8 +316,9 @@ static void build_pyramid(orc_ctx* c, const uint8_t* img, const float* fimg)
             const float* g = &c->tab.inc.filter[l * ORC_GAUSS_ALIGN];
             const int span = c->tab.inc.span[l];
             if (l == 0) {
-                if (o == 0) {
-                    level0_rows(c, img, fimg, interm);
+                if (o == 0 || c->cfg.scaling_mode == 1) {
+                    /* ScaleDirect: rows with dd[octave], columns with inc[0] (vert_from_interm(octave, 0), :507) */
+                    level0_rows(c, img, fimg, interm, o);
                     cols_pass(interm, dstp, W, H, g, span);
                 } else {
                     /* s_pyramid_build.cu:50-71 get_by_2_pick_every_second from level L of o-1 */

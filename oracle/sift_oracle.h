@@ -36,6 +36,7 @@ typedef struct orc_config {
     int32_t norm_mode;        /* ORC_NORM_* */
     int32_t norm_multi;       /* 0 */
     int32_t max_extrema;      /* 100000 */
+    int32_t scaling_mode;     /* 0 = ScaleDefault, 1 = ScaleDirect (sift_conf.h; s_pyramid_build.cu:499-514) */
 } orc_config;
 
 typedef struct orc_gauss_table {
@@ -51,6 +52,10 @@ typedef struct orc_tables {
     int32_t dd_span0;
     float   peak_threshold;              /* sift_conf.cu:276-279 */
     float   sigma_k;                     /* sift_constants.cu:27 */
+    /* all rows of the dd table (gauss_filter.cu:216-238), used by ScaleDirect */
+    float   dd_filter[ORC_MAX_OCTAVES * ORC_GAUSS_ALIGN];
+    float   dd_sigma[ORC_MAX_OCTAVES];
+    int32_t dd_span[ORC_MAX_OCTAVES];
 } orc_tables;
 
 /* same layout as popsift::Feature (features.h:23-37), 72 bytes */

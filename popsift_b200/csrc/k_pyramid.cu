@@ -334,11 +334,11 @@ Taps make_taps(const GaussRow& g)
 
 template <typename PIX>
 int launch_level0_any(const PIX* img, size_t img_pitch, int w, int h, float upscale, int sift_mode,
-                      const OctaveView& o0, const GaussRow& dd, const GaussRow& inc0, cudaStream_t st)
+                      const OctaveView& o0, const GaussRow& dd, const GaussRow& inc0, cudaStream_t st, int octave)
 {
     // reference s_pyramid_build.cu:108-114
     float shift = 0.5f;
-    if (sift_mode == PS_MODE_POPSIFT || sift_mode == PS_MODE_VLFEAT) shift = 0.5f * powf(2.0f, upscale);
+    if (octave == 0 && (sift_mode == PS_MODE_POPSIFT || sift_mode == PS_MODE_VLFEAT)) shift = 0.5f * powf(2.0f, upscale);
     // both passes use sigma_inc[0]; the two tables have the same span by construction
     const int R = (dd.span > inc0.span ? dd.span : inc0.span) - 1;
     const Taps a = make_taps(dd), b = make_taps(inc0);
@@ -363,15 +363,15 @@ int launch_level0_any(const PIX* img, size_t img_pitch, int w, int h, float upsc
 int level0_plan_for(int w, int h, int W, int H, float shift, int R) { return level0_plan(w, h, W, H, shift, R); }
 
 int launch_level0_u8(const uint8_t* img, size_t img_pitch, int w, int h, float upscale, int sift_mode,
-                     const OctaveView& o0, const GaussRow& dd, const GaussRow& inc0, cudaStream_t st)
+                     const OctaveView& o0, const GaussRow& dd, const GaussRow& inc0, cudaStream_t st, int octave)
 {
-    return launch_level0_any<uint8_t>(img, img_pitch, w, h, upscale, sift_mode, o0, dd, inc0, st);
+    return launch_level0_any<uint8_t>(img, img_pitch, w, h, upscale, sift_mode, o0, dd, inc0, st, octave);
 }
 
 int launch_level0_f32(const float* img, size_t img_pitch_floats, int w, int h, float upscale, int sift_mode,
-                      const OctaveView& o0, const GaussRow& dd, const GaussRow& inc0, cudaStream_t st)
+                      const OctaveView& o0, const GaussRow& dd, const GaussRow& inc0, cudaStream_t st, int octave)
 {
-    return launch_level0_any<float>(img, img_pitch_floats, w, h, upscale, sift_mode, o0, dd, inc0, st);
+    return launch_level0_any<float>(img, img_pitch_floats, w, h, upscale, sift_mode, o0, dd, inc0, st, octave);
 }
 
 bool blur_level_collects(const GaussRow& g) { return use_march() && march_supports(g.span - 1); }

@@ -80,7 +80,8 @@ struct ps_ctx {
     ps_config cfg{};
     ps_gauss_tables tab{};
     GaussRow rows[PS_GAUSS_LEVELS];
-    GaussRow dd0;
+    GaussRow dd0;                         // first horizontal pass over the input image, octave 0
+    GaussRow dd[kMaxOctaves];             // ... of every octave (Config::ScaleDirect)
     Consts k{};
     int max_w = 0, max_h = 0;
     int max_octaves = 0;
@@ -195,6 +196,7 @@ int run_pyramid(ps_ctx* ctx, Slot& s)
 {
     const int L = ctx->levels;
     const bool fork = fork_choice() && s.num_octaves > 1;
+    const bool direct = ctx->cfg.scaling_mode == PS_SCALE_DIRECT;
     int n = 0, r;
     // the pyramid kernels report the threshold-passing DoG samples when every scanned level runs on the
     // marching kernels (16-bit coordinates in the lists)
@@ -213,8 +215,20 @@ int run_pyramid(ps_ctx* ctx, Slot& s)
     bool forked[Slot::kSides] = {};
     for (int o = 0; o < s.num_octaves; ++o) {
         const bool last = (o + 1 == s.num_octaves);
+        if (direct && o > 0) {
+            if (s.is_float)
+                r = launch_level0_f32(reinterpret_cast<const float*>(s.d_img), (size_t)s.w, s.w, s.h, ctx->cfg.upscale,
+                                      ctx->cfg.sift_mode, s.view.oct[o], ctx->dd[o], ctx->rows[0], s.stream, o);
+            else
+                r = launch_level0_u8(s.d_img, u8_pitch(s.w), s.w, s.h, ctx->cfg.upscale, ctx->cfg.sift_mode, s.view.oct[o],
+                                     ctx->dd[o], ctx->rows[0], s.stream, o);
+            if (r < 0) return ctx->fail(PS_ERR_ARG, "unsupported level-0 filter span %d (octave %d)", ctx->dd[o].span, o);
+            n += r;
+        }
         for (int l = 1; l < L + 3; ++l) {
-            const OctaveView* next = (l == L && !last) ? &s.view.oct[o + 1] : nullptr;
+            // Config::ScaleDirect (s_pyramid_build.cu:499-514): level 0 of EVERY octave comes straight from the input image
+            // (rows: the dd table of the octave, columns: the level-0 table), nothing is decimated from the octave above
+            const OctaveView* next = (l == L && !last && !direct) ? &s.view.oct[o + 1] : nullptr;
             cudaStream_t st = s.stream;
             if (fork && !last && l > L) {
                 const int sd = o % Slot::kSides;
@@ -465,8 +479,8 @@ extern "C" ps_ctx* ps_create(int device, const ps_config* cfg, int max_w, int ma
         const char* why = nullptr;
         if (ctx->cfg.desc_mode < PS_DESC_LOOP || ctx->cfg.desc_mode > PS_DESC_NOTILE)
             why = "ps_create: bad descriptor mode";
-        else if (ctx->cfg.scaling_mode != PS_SCALE_DEFAULT)
-            why = "ps_create: unsupported configuration: direct scaling (Config::ScaleDirect) is not implemented";
+        else if (ctx->cfg.scaling_mode != PS_SCALE_DEFAULT && ctx->cfg.scaling_mode != PS_SCALE_DIRECT)
+            why = "ps_create: bad scaling mode";
         else if (ctx->cfg.sift_mode != PS_MODE_POPSIFT && ctx->cfg.sift_mode != PS_MODE_OPENCV && ctx->cfg.sift_mode != PS_MODE_VLFEAT)
             why = "ps_create: bad sift mode";
         else if (ctx->cfg.filter_max_extrema > 0 && !kGridFilterBuilt)
@@ -485,6 +499,10 @@ extern "C" ps_ctx* ps_create(int device, const ps_config* cfg, int max_w, int ma
     }
     std::memcpy(ctx->dd0.tap, ctx->tab.dd_filter0, sizeof(float) * PS_GAUSS_ALIGN);
     ctx->dd0.span = ctx->tab.dd_span0;
+    for (int o = 0; o < kMaxOctaves && o < PS_MAX_OCTAVES; ++o) {
+        std::memcpy(ctx->dd[o].tap, &ctx->tab.dd_filter[o * PS_GAUSS_ALIGN], sizeof(float) * PS_GAUSS_ALIGN);
+        ctx->dd[o].span = ctx->tab.dd_span[o];
+    }
     ctx->max_w = max_w; ctx->max_h = max_h;
     int32_t W[kMaxOctaves], H[kMaxOctaves];
     ctx->max_octaves = ps_geometry(&ctx->cfg, max_w, max_h, W, H);

@@ -116,10 +116,11 @@ struct GaussRow { float tap[PS_GAUSS_ALIGN]; int span; };
 
 int level0_plan_for(int w, int h, int W, int H, float shift, int R);   // k_pyramid.cu: LEVEL0_* choice for one geometry
 // octave 0, level 0 from the 8-bit or float input image
+// (octave > 0: Config::ScaleDirect, the same pass onto a smaller octave with that octave's dd row and shift 0.5)
 int launch_level0_u8(const uint8_t* img, size_t img_pitch, int w, int h, float upscale, int sift_mode,
-                     const OctaveView& o0, const GaussRow& dd, const GaussRow& inc0, cudaStream_t st);
+                     const OctaveView& o0, const GaussRow& dd, const GaussRow& inc0, cudaStream_t st, int octave = 0);
 int launch_level0_f32(const float* img, size_t img_pitch_floats, int w, int h, float upscale, int sift_mode,
-                      const OctaveView& o0, const GaussRow& dd, const GaussRow& inc0, cudaStream_t st);
+                      const OctaveView& o0, const GaussRow& dd, const GaussRow& inc0, cudaStream_t st, int octave = 0);
 // level l >= 1 of one octave: blur level l-1 -> level l, DoG[l-1] = G[l]-G[l-1]; if next0 != nullptr
 // also writes every second pixel into the next octave's level 0.
 // `sink` (optional) receives the threshold-passing samples of the DoG plane; only honoured when

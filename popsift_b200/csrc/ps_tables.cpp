@@ -104,6 +104,13 @@ extern "C" int ps_gauss_tables_compute(const ps_config* cfg, ps_gauss_tables* ou
         out->dd_sigma0 = std::scalbn(gap, 0);
         fill_kernel(out->dd_sigma0, out->dd_filter0, &out->dd_span0, ocv);
     }
+    // ... and of every octave, for Config::ScaleDirect (gauss_filter.cu:227-238): sqrt(|(sigma0 2^o)^2 - blur_in^2|) / 2^o
+    for (int o = 0; o < PS_MAX_OCTAVES; ++o) {
+        const float so = std::scalbn(s0, o);
+        const float gap = std::sqrt(std::fabs(so * so - blur_in * blur_in));
+        out->dd_sigma[o] = std::scalbn(gap, -o);
+        fill_kernel(out->dd_sigma[o], &out->dd_filter[o * PS_GAUSS_ALIGN], &out->dd_span[o], ocv);
+    }
     out->peak_threshold = cfg->threshold * 0.5f * 255.0f / static_cast<float>(levels);
     out->sigma_k = std::pow(2.0f, 1.0f / static_cast<float>(levels));
     return PS_OK;

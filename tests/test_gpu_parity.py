@@ -522,7 +522,7 @@ def test_grid_filter_1280_and_unsupported_options_are_refused():
     assert feats.getFeatureCount() == len(z["feat"]) and feats.getDescriptorCount() == int(z["n_desc"][0])
     ps.uninit()
     # options whose numerics are not implemented are refused, never silently computed with the default path
-    for setter in (lambda c: c.setGaussMode("fixed9"), lambda c: c.setGaussMode("relative"), lambda c: c.setScalingMode(0)):
+    for setter in (lambda c: c.setGaussMode("fixed9"), lambda c: c.setGaussMode("relative")):
         c = mk_cfg()
         setter(c)
         with pytest.raises(api.PopSiftError):
@@ -730,4 +730,48 @@ def test_level0_planes_bit_exact_vs_live_reference(tmp_path, w, h, seed, extra):
     assert not bad, bad
     rf, rd = ol.read_ref_features(str(tmp_path / "f.bin"))
     assert (feats.getFeatureCount(), feats.getDescriptorCount()) == (len(rf), len(rd))
+    ps.uninit()
+
+
+def test_direct_scaling_vs_oracle_and_live_reference(tmp_path):
+    """Config::ScaleDirect (--direct-scaling; reference s_pyramid_build.cu:499-514): level 0 of every octave straight from
+    the input image with that octave's dd row.  Planes and extrema bit-exact against the oracle; planes of three octaves
+    bit-exact against the live reference's --log dumps and the same features / descriptors."""
+    w, h = 640, 480
+    img = make_frame(w, h, 31)
+    cfg = mk_cfg("vlfeat", "classic")
+    cfg.setScalingMode(0)                      # Config::ScaleDirect
+    ps, feats = run_gpu(img, cfg)
+    o = ol.Oracle(ol.make_config(mode="vlfeat", norm="classic", scaling_mode=1), w, h)
+    o.run(img)
+    bad = []
+    for oc in range(o.num_octaves):
+        for l in range(6):
+            if not np.array_equal(ps.plane(0, oc, l), o.gauss(oc, l)):
+                bad.append(("g", oc, l))
+    assert not bad, bad
+    # the default scaling mode gives different planes from octave 1 on: the option really is exercised
+    ps2, _ = run_gpu(img, mk_cfg("vlfeat", "classic"))
+    assert np.array_equal(ps2.plane(0, 0, 0), ps.plane(0, 0, 0)) and not np.array_equal(ps2.plane(0, 1, 0), ps.plane(0, 1, 0))
+    ps2.uninit()
+    of, od = o.features()
+    assert (feats.getFeatureCount(), feats.getDescriptorCount()) == (len(of), len(od))
+    o.close()
+    if os.path.exists(REF):
+        write_pgm(str(tmp_path / "f.pgm"), img)
+        subprocess.run([REF, "-i", "f.pgm", "-o", "f.bin", "--log", "--mode", "vlfeat", "--norm", "classic", "--direct-scaling"],
+                       cwd=str(tmp_path), check=True, capture_output=True)
+        for oc in range(3):
+            for l in range(6):
+                ref = ol.read_ref_dump(str(tmp_path / "dir-octave-dump" / ("pyramid-o-%d-l-%d.dump" % (oc, l))))
+                assert np.array_equal(ref, ps.plane(0, oc, l)), ("reference plane", oc, l)
+        rf, rd = ol.read_ref_features(str(tmp_path / "f.bin"))
+        assert (feats.getFeatureCount(), feats.getDescriptorCount()) == (len(rf), len(rd))
+        r = compare.report(*feats.keypoints(), *ol.flatten(rf, rd))
+        assert r["f1"] >= F1_MIN and r["desc_l2_max"] < L2_MAX, r
+        # keep the reference's output as a fixture source for the CPU-side oracle test
+        out_dir = os.path.join(ROOT, "gpurun_out")
+        if os.path.isdir(out_dir):
+            import shutil
+            shutil.copy(str(tmp_path / "f.bin"), os.path.join(out_dir, "ref_direct_640.bin"))
     ps.uninit()

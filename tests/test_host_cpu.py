@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(L, name), "libpopsift_b200.so does not export %s" % name
     assert declared == set(api.EXPORTS)
-    assert L.ps_abi_version() == 2
+    assert L.ps_abi_version() == 3
 
 
 def test_struct_sizes_match_reference_layouts():
@@ -66,6 +66,10 @@ def test_gauss_tables_bit_identical_to_oracle(kw):
     assert np.array_equal(np.frombuffer(t.inc_sigma, np.uint32), np.frombuffer(ot.inc.sigma, np.uint32))
     assert np.array_equal(np.frombuffer(t.dd_filter0, np.uint32), np.frombuffer(ot.dd_filter0, np.uint32))
     assert t.dd_span0 == ot.dd_span0
+    # the direct-downscaling rows of every octave (Config::ScaleDirect); row 0 is the classic one
+    assert list(t.dd_span) == list(ot.dd_span) and t.dd_span[0] == t.dd_span0
+    assert np.array_equal(np.frombuffer(t.dd_filter, np.uint32), np.frombuffer(ot.dd_filter, np.uint32))
+    assert np.array_equal(np.frombuffer(t.dd_filter, np.uint32)[:32], np.frombuffer(t.dd_filter0, np.uint32))
     assert t.peak_threshold == ot.peak_threshold and t.sigma_k == ot.sigma_k
 
 
