@@ -143,6 +143,13 @@ def main(src):
             out[tag + "_r16"] = r16[sel][:, xs, :].astype(np.uint16)
             out[tag + "_meta"], out[tag + "_up"] = np.array([w, h, W0, H0, maxoff], np.int32), np.float32(up)
         np.savez_compressed(os.path.join(HERE, "texture_coords.npz"), **out)
+    # ---- Config::ScaleDirect (tools/gpu_round2_p.sh: ref_dump --direct-scaling --log on the 256x192 frame; the 640x480
+    # output is saved by tests/test_gpu_parity.py::test_direct_scaling_vs_oracle_and_live_reference)
+    save_feat(src, "ref_direct_f256.bin", "f256_direct")
+    save_feat(os.path.dirname(src.rstrip("/")), "ref_direct_640.bin", "f640_direct")
+    fn = os.path.join(src, "ref_direct_f256_planes.json")
+    if os.path.exists(fn):
+        json.dump(json.load(open(fn)), open(os.path.join(HERE, "planes_f256_direct.json"), "w"), indent=0)
 
 
 if __name__ == "__main__":
