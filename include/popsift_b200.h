@@ -61,7 +61,7 @@ typedef struct ps_config {
     float   initial_blur;      /* 0.5                                                      */
     int32_t has_initial_blur;  /* 1                                                        */
     int32_t sift_mode;         /* PS_MODE_*                                                */
-    int32_t gauss_mode;        /* PS_GAUSS_*  (VLFEAT_COMPUTE and OPENCV_COMPUTE are implemented; the others are REJECTED by ps_create) */
+    int32_t gauss_mode;        /* PS_GAUSS_*  (VLFEAT_COMPUTE, OPENCV_COMPUTE and VLFEAT_RELATIVE_ALL are implemented; the others are REJECTED by ps_create) */
     int32_t desc_mode;         /* PS_DESC_*   (loop is the fast path; iloop / grid / igrid / notile follow the reference's schemes) */
     int32_t norm_mode;         /* PS_NORM_*                                                */
     int32_t norm_multi;        /* descriptor scaled by 2^norm_multi                        */
@@ -109,6 +109,11 @@ typedef struct ps_gauss_tables {
     float   dd_filter[PS_MAX_OCTAVES * PS_GAUSS_ALIGN];
     float   dd_sigma[PS_MAX_OCTAVES];
     int32_t dd_span[PS_MAX_OCTAVES];
+    /* the absolute rows of octave 0 (gauss_filter.cu:190-199), used by --gauss-mode vlfeat-direct (VLFeat_Relative_All):
+     * every level of octave 0 is filtered straight from the input image with row `level`, horizontally and vertically */
+    float   abs_filter[PS_GAUSS_LEVELS * PS_GAUSS_ALIGN];
+    float   abs_sigma[PS_GAUSS_LEVELS];
+    int32_t abs_span[PS_GAUSS_LEVELS];
 } ps_gauss_tables;
 
 enum { PS_STAGE_H2D = 0, PS_STAGE_PYRAMID = 1, PS_STAGE_EXTREMA = 2, PS_STAGE_ORIENT = 3,

@@ -52,6 +52,7 @@ void orc_default_config(orc_config* c)
     c->sift_mode = ORC_MODE_POPSIFT; c->norm_mode = ORC_NORM_ROOTSIFT; c->norm_multi = 0;
     c->max_extrema = 100000;
     c->scaling_mode = 0;
+    c->gauss_direct = 0;
 }
 
 int orc_set_threads(int n)
@@ -124,6 +125,12 @@ int orc_compute_tables(const orc_config* c, orc_tables* t)
         t->dd_sigma[oct] = scalbnf(b, -oct);
         blur_row(t->dd_sigma[oct], &t->dd_span[oct], &t->dd_filter[oct * ORC_GAUSS_ALIGN]);
     }
+    for (int lvl = 0; lvl < stages; lvl++) {                /* gauss_filter.cu:194-199 */
+        const float sigmaS = sigma0 * powf(2.0f, (float)(lvl) / (float)levels);
+        t->abs_o0.sigma[lvl] = sqrtf(fabsf(sigmaS * sigmaS - initial_blur * initial_blur));
+    }
+    for (int lvl = 0; lvl < ORC_GAUSS_LEVELS; lvl++)
+        blur_row(t->abs_o0.sigma[lvl], &t->abs_o0.span[lvl], &t->abs_o0.filter[lvl * ORC_GAUSS_ALIGN]);
     t->peak_threshold = c->threshold * 0.5f * 255.0f / (float)levels; /* sift_conf.cu:276-279 */
     t->sigma_k = powf(2.0f, 1.0f / (float)levels);                    /* sift_constants.cu:27 */
     return 0;
@@ -240,11 +247,12 @@ static inline float tex_any(const orc_ctx* c, const uint8_t* img, const float* f
 
 /* normalizedSource::horiz (s_pyramid_build_ra.cu:17-55) for octave `oct` (0 in the default scaling mode; every octave under
  * ScaleDirect, s_pyramid_build.cu:97-126,499-508): the dd row of that octave, shift 0.5 unless octave 0 in PopSift / VLFeat mode */
-static void level0_rows(const orc_ctx* c, const uint8_t* img, const float* fimg, float* dst, int oct)
+static void level0_rows(const orc_ctx* c, const uint8_t* img, const float* fimg, float* dst, int oct, int abs_level)
 {
     const int W0 = c->W[oct], H0 = c->H[oct];
-    const int span = c->tab.dd_span[oct];
-    const float* g = &c->tab.dd_filter[oct * ORC_GAUSS_ALIGN];
+    /* abs_level >= 0: normalizedSource::horiz_all (s_pyramid_build_ra.cu:90-129), row `abs_level` of the abs_o0 table */
+    const int span = abs_level >= 0 ? c->tab.abs_o0.span[abs_level] : c->tab.dd_span[oct];
+    const float* g = abs_level >= 0 ? &c->tab.abs_o0.filter[abs_level * ORC_GAUSS_ALIGN] : &c->tab.dd_filter[oct * ORC_GAUSS_ALIGN];
     float shift = 0.5f;   /* s_pyramid_build.cu:108-114 */
     if (oct == 0 && (c->cfg.sift_mode == ORC_MODE_POPSIFT || c->cfg.sift_mode == ORC_MODE_VLFEAT))
         shift = 0.5f * powf(2.0f, c->cfg.upscale - 0);
@@ -315,10 +323,15 @@ static void build_pyramid(orc_ctx* c, const uint8_t* img, const float* fimg)
             float* dstp = c->gauss[o] + P * l;
             const float* g = &c->tab.inc.filter[l * ORC_GAUSS_ALIGN];
             const int span = c->tab.inc.span[l];
-            if (l == 0) {
+            if (o == 0 && c->cfg.gauss_direct && c->cfg.scaling_mode != 1) {
+                /* VLFeat_Relative_All, octave 0 (s_pyramid_build.cu:543-546): horiz_all_from_input_image + vert_all_abs0 */
+                const float* ga = &c->tab.abs_o0.filter[l * ORC_GAUSS_ALIGN];
+                level0_rows(c, img, fimg, interm, 0, l);
+                cols_pass(interm, dstp, W, H, ga, c->tab.abs_o0.span[l]);
+            } else if (l == 0) {
                 if (o == 0 || c->cfg.scaling_mode == 1) {
                     /* ScaleDirect: rows with dd[octave], columns with inc[0] (vert_from_interm(octave, 0), :507) */
-                    level0_rows(c, img, fimg, interm, o);
+                    level0_rows(c, img, fimg, interm, o, -1);
                     cols_pass(interm, dstp, W, H, g, span);
                 } else {
                     /* s_pyramid_build.cu:50-71 get_by_2_pick_every_second from level L of o-1 */

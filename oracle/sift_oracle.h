@@ -37,6 +37,7 @@ typedef struct orc_config {
     int32_t norm_multi;       /* 0 */
     int32_t max_extrema;      /* 100000 */
     int32_t scaling_mode;     /* 0 = ScaleDefault, 1 = ScaleDirect (sift_conf.h; s_pyramid_build.cu:499-514) */
+    int32_t gauss_direct;     /* 1 = --gauss-mode vlfeat-direct (VLFeat_Relative_All, s_pyramid_build.cu:543-546) */
 } orc_config;
 
 typedef struct orc_gauss_table {
@@ -56,6 +57,7 @@ typedef struct orc_tables {
     float   dd_filter[ORC_MAX_OCTAVES * ORC_GAUSS_ALIGN];
     float   dd_sigma[ORC_MAX_OCTAVES];
     int32_t dd_span[ORC_MAX_OCTAVES];
+    orc_gauss_table abs_o0;              /* gauss_filter.cu:190-199: every level of octave 0 from the input image */
 } orc_tables;
 
 /* same layout as popsift::Feature (features.h:23-37), 72 bytes */

@@ -234,6 +234,92 @@ level0_kernel(const PIX* __restrict__ img, size_t img_pitch, int w, int h, float
     }
 }
 
+// Generic form of the level-0 kernel (run-time radii, any span up to 31): rows with `dd` (radius Rr), columns with `inc0`
+// (radius Rc).  Used by --gauss-mode vlfeat-direct (VLFeat_Relative_All, reference s_pyramid_build_ra.cu:90-129 +
+// s_pyramid_build_aa.cu:124-167), whose rows reach 21 taps a side.  exact != 0: every tap at the reference's own coordinate.
+template <typename PIX>
+__global__ void __launch_bounds__(NT)
+level0_generic_kernel(const PIX* __restrict__ img, size_t img_pitch, int w, int h, float shift,
+                      float* __restrict__ dst, int W, int H, int pitch, Taps dd, Taps inc0, int Rr, int Rc, int exact)
+{
+    extern __shared__ float smem[];
+    const int SW = TW + 2 * Rr;
+    const int ROWS = TH + 2 * Rc;
+    float* s = smem;                 // ROWS x SW staged virtual samples (fetch-sharing form only)
+    float* m = smem + ROWS * SW;     // ROWS x TW row-filtered
+    const int x0 = blockIdx.x * TW;
+    const int y0 = blockIdx.y * TH;
+    if (exact) {
+        for (int idx = threadIdx.x; idx < ROWS * TW; idx += NT) {
+            const int j = idx / TW;
+            const int x = idx - j * TW;
+            const TexAxis ty = virt_axis(clampi(y0 - Rc + j, 0, H - 1), shift, H, h);
+            const int X = min(x0 + x, W - 1);
+            const float cx = tex_coord_centre(X, shift, W);
+            float acc = 0.0f;
+            for (int off = Rr; off > 0; --off) {
+                const float v1 = tex_fetch(img, img_pitch, tex_axis(tex_coord_tap(cx, -off, W), w), ty);
+                const float v2 = tex_fetch(img, img_pitch, tex_axis(tex_coord_tap(cx, off, W), w), ty);
+                acc = __fmaf_rn(__fadd_rn(v1, v2), dd.g[off], acc);
+            }
+            acc = __fmaf_rn(tex_fetch(img, img_pitch, tex_axis(cx, w), ty), dd.g[0], acc);
+            m[idx] = __fmul_rn(acc, 255.0f);
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < ROWS * SW; idx += NT) {
+            const int j = idx / SW;
+            const int i = idx - j * SW;
+            s[idx] = tex_fetch(img, img_pitch, virt_axis(x0 - Rr + i, shift, W, w), virt_axis(clampi(y0 - Rc + j, 0, H - 1), shift, H, h));
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < ROWS * TW; idx += NT) {
+            const int j = idx / TW;
+            const int i = idx - j * TW;
+            const float* p = s + j * SW + i + Rr;
+            float acc = 0.0f;
+            for (int off = Rr; off > 0; --off) acc = __fmaf_rn(__fadd_rn(p[-off], p[off]), dd.g[off], acc);
+            acc = __fmaf_rn(p[0], dd.g[0], acc);
+            m[idx] = __fmul_rn(acc, 255.0f);
+        }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < TH * TW; idx += NT) {
+        const int y = idx / TW;
+        const int x = idx - y * TW;
+        const int gx = x0 + x, gy = y0 + y;
+        if (gx >= W || gy >= H) continue;
+        const float* p = m + (y + Rc) * TW + x;
+        float acc = 0.0f;
+        for (int off = Rc; off > 0; --off) {
+            acc = __fmaf_rn(p[-off * TW], inc0.g[off], acc);
+            acc = __fmaf_rn(p[off * TW], inc0.g[off], acc);
+        }
+        dst[(size_t)gy * pitch + gx] = __fmaf_rn(p[0], inc0.g[0], acc);
+    }
+}
+
+// DoG planes of an octave whose levels were not produced by the fused blur + DoG kernels (reference make_dog,
+// s_pyramid_build.cu:74-92): dog[l] = gauss[l + 1] - gauss[l]
+__global__ void dog_planes_kernel(const float* __restrict__ gauss, float* __restrict__ dog, size_t plane, int nplanes, int W, int H, int pitch)
+{
+    const size_t n = (size_t)H * pitch;
+    for (int l = 0; l < nplanes; ++l) {
+        const float* a = gauss + plane * l;
+        const float* b = a + plane;
+        float* d = dog + plane * l;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+            if ((int)(i % (size_t)pitch) < W) d[i] = __fsub_rn(b[i], a[i]);
+    }
+}
+
+// level 0 of the next octave: every second pixel of level L (reference get_by_2_pick_every_second, s_pyramid_build.cu:50-71)
+__global__ void decimate_kernel(const float* __restrict__ src, int Wp, int Hp, int pitch_p, float* __restrict__ dst, int W, int H, int pitch)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W || y >= H) return;
+    dst[(size_t)y * pitch + x] = src[(size_t)clampi(2 * y, 0, Hp - 1) * pitch_p + clampi(2 * x, 0, Wp - 1)];
+}
+
 template <int R>
 constexpr size_t tile_smem() { return sizeof(float) * ((TH + 2 * R) * (TW + 2 * R) + (TH + 2 * R) * TW); }
 
@@ -407,6 +493,46 @@ int launch_blur_level(const OctaveView& o, int level, const GaussRow& g, const O
     blur_level_generic_kernel<<<grid, NT, sm, st>>>(o.gauss + o.plane * (level - 1), o.gauss + o.plane * level,
                                                     o.dog + o.plane * (level - 1), next0, o.w, o.h, o.pitch,
                                                     next_pitch, t, R);
+    return 1;
+}
+
+// --gauss-mode vlfeat-direct: level `level` of octave 0 straight from the input image with `taps` in both directions
+template <typename PIX>
+static int launch_level0_abs_any(const PIX* img, size_t img_pitch, int w, int h, float upscale, int sift_mode,
+                                 const OctaveView& o0, int level, const GaussRow& taps, cudaStream_t st)
+{
+    float shift = 0.5f;
+    if (sift_mode == PS_MODE_POPSIFT || sift_mode == PS_MODE_VLFEAT) shift = 0.5f * powf(2.0f, upscale);
+    const int R = taps.span - 1;
+    if (R < 0 || R >= PS_GAUSS_ALIGN) return -1;
+    const Taps t = make_taps(taps);
+    const int plan = level0_plan(w, h, o0.w, o0.h, shift, R);
+    const size_t sm = sizeof(float) * ((size_t)(TH + 2 * R) * (TW + 2 * R) + (size_t)(TH + 2 * R) * TW);
+    ensure_smem(level0_generic_kernel<PIX>, sm);
+    dim3 grid((o0.w + TW - 1) / TW, (o0.h + TH - 1) / TH);
+    level0_generic_kernel<PIX><<<grid, NT, sm, st>>>(img, img_pitch, w, h, shift, o0.gauss + o0.plane * level, o0.w, o0.h, o0.pitch,
+                                                     t, t, R, R, plan == LEVEL0_PER_TAP ? 1 : 0);
+    return 1;
+}
+int launch_level0_abs_u8(const uint8_t* img, size_t img_pitch, int w, int h, float upscale, int sift_mode,
+                         const OctaveView& o0, int level, const GaussRow& taps, cudaStream_t st)
+{
+    return launch_level0_abs_any<uint8_t>(img, img_pitch, w, h, upscale, sift_mode, o0, level, taps, st);
+}
+int launch_level0_abs_f32(const float* img, size_t img_pitch_floats, int w, int h, float upscale, int sift_mode,
+                          const OctaveView& o0, int level, const GaussRow& taps, cudaStream_t st)
+{
+    return launch_level0_abs_any<float>(img, img_pitch_floats, w, h, upscale, sift_mode, o0, level, taps, st);
+}
+int launch_dog_planes(const OctaveView& o, int nplanes, cudaStream_t st)
+{
+    dog_planes_kernel<<<sm_count() * 8, 256, 0, st>>>(o.gauss, o.dog, o.plane, nplanes, o.w, o.h, o.pitch);
+    return 1;
+}
+int launch_decimate(const OctaveView& prev, int level, const OctaveView& next, cudaStream_t st)
+{
+    dim3 grid((next.w + 127) / 128, next.h);
+    decimate_kernel<<<grid, 128, 0, st>>>(prev.gauss + prev.plane * level, prev.w, prev.h, prev.pitch, next.gauss, next.w, next.h, next.pitch);
     return 1;
 }
 

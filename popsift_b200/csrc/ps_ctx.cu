@@ -82,6 +82,7 @@ struct ps_ctx {
     GaussRow rows[PS_GAUSS_LEVELS];
     GaussRow dd0;                         // first horizontal pass over the input image, octave 0
     GaussRow dd[kMaxOctaves];             // ... of every octave (Config::ScaleDirect)
+    GaussRow abs0[PS_GAUSS_LEVELS];       // octave 0 from the input image, every level (--gauss-mode vlfeat-direct)
     Consts k{};
     int max_w = 0, max_h = 0;
     int max_octaves = 0;
@@ -200,10 +201,27 @@ int run_pyramid(ps_ctx* ctx, Slot& s)
     int n = 0, r;
     // the pyramid kernels report the threshold-passing DoG samples when every scanned level runs on the
     // marching kernels (16-bit coordinates in the lists)
-    bool collects = L <= kMaxLevels;
+    // --gauss-mode vlfeat-direct (VLFeat_Relative_All, s_pyramid_build.cu:543-546; under ScaleDirect the direct-scaling
+    // arm comes first, :499): every level of octave 0 straight from the input image
+    const bool abs_o0 = ctx->cfg.gauss_mode == PS_GAUSS_VLFEAT_RELATIVE_ALL && !direct;
+    bool collects = L <= kMaxLevels && !abs_o0;
     for (int l = 2; l <= L + 1 && collects; ++l) collects = blur_level_collects(ctx->rows[l]);
     for (int o = 0; o < s.num_octaves && collects; ++o) collects = s.view.oct[o].w <= 65535 && s.view.oct[o].h <= 65535;
     s.view.cands_filled = collects ? 1 : 0;
+    if (abs_o0) {
+        for (int l = 0; l < L + 3; ++l) {
+            if (s.is_float)
+                r = launch_level0_abs_f32(reinterpret_cast<const float*>(s.d_img), (size_t)s.w, s.w, s.h, ctx->cfg.upscale,
+                                          ctx->cfg.sift_mode, s.view.oct[0], l, ctx->abs0[l], s.stream);
+            else
+                r = launch_level0_abs_u8(s.d_img, u8_pitch(s.w), s.w, s.h, ctx->cfg.upscale, ctx->cfg.sift_mode, s.view.oct[0], l,
+                                         ctx->abs0[l], s.stream);
+            if (r < 0) return ctx->fail(PS_ERR_ARG, "unsupported filter span %d (octave 0, level %d)", ctx->abs0[l].span, l);
+            n += r;
+        }
+        n += launch_dog_planes(s.view.oct[0], L + 2, s.stream);
+        if (s.num_octaves > 1) n += launch_decimate(s.view.oct[0], L, s.view.oct[1], s.stream);
+    } else {
     if (s.is_float)
         r = launch_level0_f32(reinterpret_cast<const float*>(s.d_img), (size_t)s.w, s.w, s.h, ctx->cfg.upscale,
                               ctx->cfg.sift_mode, s.view.oct[0], ctx->dd0, ctx->rows[0], s.stream);
@@ -212,6 +230,7 @@ int run_pyramid(ps_ctx* ctx, Slot& s)
                              ctx->dd0, ctx->rows[0], s.stream);
     if (r < 0) return ctx->fail(PS_ERR_ARG, "unsupported level-0 filter span %d", ctx->dd0.span);
     n += r;
+    }
     bool forked[Slot::kSides] = {};
     for (int o = 0; o < s.num_octaves; ++o) {
         const bool last = (o + 1 == s.num_octaves);
@@ -225,7 +244,7 @@ int run_pyramid(ps_ctx* ctx, Slot& s)
             if (r < 0) return ctx->fail(PS_ERR_ARG, "unsupported level-0 filter span %d (octave %d)", ctx->dd[o].span, o);
             n += r;
         }
-        for (int l = 1; l < L + 3; ++l) {
+        for (int l = 1; l < L + 3 && !(abs_o0 && o == 0); ++l) {
             // Config::ScaleDirect (s_pyramid_build.cu:499-514): level 0 of EVERY octave comes straight from the input image
             // (rows: the dd table of the octave, columns: the level-0 table), nothing is decimated from the octave above
             const OctaveView* next = (l == L && !last && !direct) ? &s.view.oct[o + 1] : nullptr;
@@ -491,7 +510,7 @@ extern "C" ps_ctx* ps_create(int device, const ps_config* cfg, int max_w, int ma
     }
     if (ps_gauss_tables_compute(&ctx->cfg, &ctx->tab) != PS_OK) {
         delete ctx;
-        return bail("ps_create: unsupported configuration (sigma > 2.0, levels > 12, or a gauss mode other than vlfeat / opencv)", cudaSuccess);
+        return bail("ps_create: unsupported configuration (sigma > 2.0, levels > 12, or a gauss mode other than vlfeat / opencv / vlfeat-direct)", cudaSuccess);
     }
     for (int l = 0; l < PS_GAUSS_LEVELS; ++l) {
         std::memcpy(ctx->rows[l].tap, &ctx->tab.inc_filter[l * PS_GAUSS_ALIGN], sizeof(float) * PS_GAUSS_ALIGN);
@@ -502,6 +521,10 @@ extern "C" ps_ctx* ps_create(int device, const ps_config* cfg, int max_w, int ma
     for (int o = 0; o < kMaxOctaves && o < PS_MAX_OCTAVES; ++o) {
         std::memcpy(ctx->dd[o].tap, &ctx->tab.dd_filter[o * PS_GAUSS_ALIGN], sizeof(float) * PS_GAUSS_ALIGN);
         ctx->dd[o].span = ctx->tab.dd_span[o];
+    }
+    for (int l = 0; l < PS_GAUSS_LEVELS; ++l) {
+        std::memcpy(ctx->abs0[l].tap, &ctx->tab.abs_filter[l * PS_GAUSS_ALIGN], sizeof(float) * PS_GAUSS_ALIGN);
+        ctx->abs0[l].span = ctx->tab.abs_span[l];
     }
     ctx->max_w = max_w; ctx->max_h = max_h;
     int32_t W[kMaxOctaves], H[kMaxOctaves];

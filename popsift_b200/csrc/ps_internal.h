@@ -121,6 +121,14 @@ int launch_level0_u8(const uint8_t* img, size_t img_pitch, int w, int h, float u
                      const OctaveView& o0, const GaussRow& dd, const GaussRow& inc0, cudaStream_t st, int octave = 0);
 int launch_level0_f32(const float* img, size_t img_pitch_floats, int w, int h, float upscale, int sift_mode,
                       const OctaveView& o0, const GaussRow& dd, const GaussRow& inc0, cudaStream_t st, int octave = 0);
+// --gauss-mode vlfeat-direct (VLFeat_Relative_All): one level of octave 0 straight from the input image; the DoG planes and
+// the next octave's level 0 then come from their own small kernels
+int launch_level0_abs_u8(const uint8_t* img, size_t img_pitch, int w, int h, float upscale, int sift_mode,
+                         const OctaveView& o0, int level, const GaussRow& taps, cudaStream_t st);
+int launch_level0_abs_f32(const float* img, size_t img_pitch_floats, int w, int h, float upscale, int sift_mode,
+                          const OctaveView& o0, int level, const GaussRow& taps, cudaStream_t st);
+int launch_dog_planes(const OctaveView& o, int nplanes, cudaStream_t st);
+int launch_decimate(const OctaveView& prev, int level, const OctaveView& next, cudaStream_t st);
 // level l >= 1 of one octave: blur level l-1 -> level l, DoG[l-1] = G[l]-G[l-1]; if next0 != nullptr
 // also writes every second pixel into the next octave's level 0.
 // `sink` (optional) receives the threshold-passing samples of the DoG plane; only honoured when

@@ -81,7 +81,8 @@ extern "C" int ps_gauss_tables_compute(const ps_config* cfg, ps_gauss_tables* ou
     const float s0 = cfg->sigma;
     if (s0 > 2.0f) return PS_ERR_ARG;                 // reference gauss_filter.cu:131-137
     if (levels > PS_GAUSS_LEVELS) return PS_ERR_ARG;  // reference gauss_filter.cu:138-144
-    if (cfg->gauss_mode != PS_GAUSS_VLFEAT_COMPUTE && cfg->gauss_mode != PS_GAUSS_OPENCV_COMPUTE) return PS_ERR_ARG;
+    if (cfg->gauss_mode != PS_GAUSS_VLFEAT_COMPUTE && cfg->gauss_mode != PS_GAUSS_OPENCV_COMPUTE &&
+        cfg->gauss_mode != PS_GAUSS_VLFEAT_RELATIVE_ALL) return PS_ERR_ARG;   // RELATIVE_ALL: the vlfeat span rule (gauss_filter.cu:279-281)
     const bool ocv = cfg->gauss_mode == PS_GAUSS_OPENCV_COMPUTE;
     const int planes = levels + 3;
     const float blur_in = cfg->has_initial_blur ? cfg->initial_blur * std::pow(2.0f, cfg->upscale) : 0.0f;
@@ -111,6 +112,13 @@ extern "C" int ps_gauss_tables_compute(const ps_config* cfg, ps_gauss_tables* ou
         out->dd_sigma[o] = std::scalbn(gap, -o);
         fill_kernel(out->dd_sigma[o], &out->dd_filter[o * PS_GAUSS_ALIGN], &out->dd_span[o], ocv);
     }
+    // octave 0 straight from the input image, every level (gauss_filter.cu:190-199): sqrt(|(sigma0 2^(l/L))^2 - blur_in^2|)
+    for (int l = 0; l < planes; ++l) {
+        const float ss = s0 * std::pow(2.0f, static_cast<float>(l) / static_cast<float>(levels));
+        out->abs_sigma[l] = std::sqrt(std::fabs(ss * ss - blur_in * blur_in));
+    }
+    for (int l = 0; l < PS_GAUSS_LEVELS; ++l)
+        fill_kernel(out->abs_sigma[l], &out->abs_filter[l * PS_GAUSS_ALIGN], &out->abs_span[l], ocv);
     out->peak_threshold = cfg->threshold * 0.5f * 255.0f / static_cast<float>(levels);
     out->sigma_k = std::pow(2.0f, 1.0f / static_cast<float>(levels));
     return PS_OK;

@@ -775,3 +775,46 @@ def test_direct_scaling_vs_oracle_and_live_reference(tmp_path):
             import shutil
             shutil.copy(str(tmp_path / "f.bin"), os.path.join(out_dir, "ref_direct_640.bin"))
     ps.uninit()
+
+
+def test_gauss_mode_vlfeat_direct_vs_oracle_and_live_reference(tmp_path):
+    """--gauss-mode vlfeat-direct (Config::VLFeat_Relative_All; reference s_pyramid_build.cu:543-546, s_pyramid_build_ra.cu:90-129,
+    s_pyramid_build_aa.cu:124-167): every level of octave 0 is filtered straight from the input image with the abs_o0 row of
+    that level (up to 21 taps a side); octaves >= 1 as usual.  Planes bit-exact against the oracle and against the live
+    reference's --log dumps, same features."""
+    w, h = 640, 480
+    img = make_frame(w, h, 33)
+    cfg = mk_cfg("vlfeat", "classic")
+    cfg.setGaussMode("vlfeat-direct")
+    ps, feats = run_gpu(img, cfg)
+    o = ol.Oracle(ol.make_config(mode="vlfeat", norm="classic", gauss_direct=1), w, h)
+    o.run(img)
+    bad = []
+    for oc in range(o.num_octaves):
+        for l in range(6):
+            if not np.array_equal(ps.plane(0, oc, l), o.gauss(oc, l)):
+                bad.append(("g", oc, l))
+        for l in range(5):
+            if not np.array_equal(ps.plane(0, oc, l, dog=True), o.dog(oc, l)):
+                bad.append(("d", oc, l))
+    assert not bad, bad
+    of, od = o.features()
+    assert (feats.getFeatureCount(), feats.getDescriptorCount()) == (len(of), len(od))
+    o.close()
+    if os.path.exists(REF):
+        write_pgm(str(tmp_path / "f.pgm"), img)
+        subprocess.run([REF, "-i", "f.pgm", "-o", "f.bin", "--log", "--mode", "vlfeat", "--norm", "classic", "--gauss-mode", "vlfeat-direct"],
+                       cwd=str(tmp_path), check=True, capture_output=True)
+        for oc in range(2):
+            for l in range(6):
+                ref = ol.read_ref_dump(str(tmp_path / "dir-octave-dump" / ("pyramid-o-%d-l-%d.dump" % (oc, l))))
+                assert np.array_equal(ref, ps.plane(0, oc, l)), ("reference plane", oc, l)
+        rf, rd = ol.read_ref_features(str(tmp_path / "f.bin"))
+        assert (feats.getFeatureCount(), feats.getDescriptorCount()) == (len(rf), len(rd))
+        r = compare.report(*feats.keypoints(), *ol.flatten(rf, rd))
+        assert r["f1"] >= F1_MIN and r["desc_l2_max"] < L2_MAX, r
+        out_dir = os.path.join(ROOT, "gpurun_out")
+        if os.path.isdir(out_dir):
+            import shutil
+            shutil.copy(str(tmp_path / "f.bin"), os.path.join(out_dir, "ref_vlfeat_direct_640.bin"))
+    ps.uninit()

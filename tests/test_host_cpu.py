@@ -70,6 +70,9 @@ def test_gauss_tables_bit_identical_to_oracle(kw):
     assert list(t.dd_span) == list(ot.dd_span) and t.dd_span[0] == t.dd_span0
     assert np.array_equal(np.frombuffer(t.dd_filter, np.uint32), np.frombuffer(ot.dd_filter, np.uint32))
     assert np.array_equal(np.frombuffer(t.dd_filter, np.uint32)[:32], np.frombuffer(t.dd_filter0, np.uint32))
+    # the absolute rows of octave 0 (--gauss-mode vlfeat-direct)
+    assert list(t.abs_span) == list(ot.abs_o0.span)
+    assert np.array_equal(np.frombuffer(t.abs_filter, np.uint32), np.frombuffer(ot.abs_o0.filter, np.uint32))
     assert t.peak_threshold == ot.peak_threshold and t.sigma_k == ot.sigma_k
 
 
