@@ -61,7 +61,7 @@ typedef struct ps_config {
     float   initial_blur;      /* 0.5                                                      */
     int32_t has_initial_blur;  /* 1                                                        */
     int32_t sift_mode;         /* PS_MODE_*                                                */
-    int32_t gauss_mode;        /* PS_GAUSS_*  (VLFEAT_COMPUTE, OPENCV_COMPUTE and VLFEAT_RELATIVE_ALL are implemented; the others are REJECTED by ps_create) */
+    int32_t gauss_mode;        /* PS_GAUSS_*  (FIXED9 / FIXED15 are REJECTED by ps_create) */
     int32_t desc_mode;         /* PS_DESC_*   (loop is the fast path; iloop / grid / igrid / notile follow the reference's schemes) */
     int32_t norm_mode;         /* PS_NORM_*                                                */
     int32_t norm_multi;        /* descriptor scaled by 2^norm_multi                        */
@@ -114,6 +114,10 @@ typedef struct ps_gauss_tables {
     float   abs_filter[PS_GAUSS_LEVELS * PS_GAUSS_ALIGN];
     float   abs_sigma[PS_GAUSS_LEVELS];
     int32_t abs_span[PS_GAUSS_LEVELS];
+    /* the incremental rows transformed for hardware interpolation (gauss_filter.cu:372-405), used by --gauss-mode relative
+     * (= vlfeat-hw-interpolated, VLFeat_Relative): [0] centre weight, odd x: fraction u, even x: pair weight v */
+    float   inc_ifilter[PS_GAUSS_LEVELS * PS_GAUSS_ALIGN];
+    int32_t inc_ispan[PS_GAUSS_LEVELS];
 } ps_gauss_tables;
 
 enum { PS_STAGE_H2D = 0, PS_STAGE_PYRAMID = 1, PS_STAGE_EXTREMA = 2, PS_STAGE_ORIENT = 3,

@@ -53,6 +53,7 @@ void orc_default_config(orc_config* c)
     c->max_extrema = 100000;
     c->scaling_mode = 0;
     c->gauss_direct = 0;
+    c->gauss_relative = 0;
 }
 
 int orc_set_threads(int n)
@@ -76,9 +77,11 @@ static int vlfeat_span(float sigma)
 
 /* gauss_filter.cu:341-371 (computeBlurTable): taps in double, stored float,
  * normalised by a double sum that accumulates 2.0f*val of the *float* tap. */
+static int g_odd_spans = 0;   /* gauss_filter.cu:309-319 vlFeatRelativeSpan: set while the tables of --gauss-mode relative are built */
 static void blur_row(float sig, int* span_out, float* f)
 {
     int spn = vlfeat_span(sig);
+    if (g_odd_spans && (spn & 1) == 0) spn += 1;
     if (spn > ORC_GAUSS_ALIGN - 1) spn = ORC_GAUSS_ALIGN - 1;
     double sum = 1.0;
     f[0] = 1.0f;
@@ -95,6 +98,7 @@ static void blur_row(float sig, int* span_out, float* f)
 int orc_compute_tables(const orc_config* c, orc_tables* t)
 {
     memset(t, 0, sizeof(*t));
+    g_odd_spans = c->gauss_relative ? 1 : 0;
     const int levels = c->levels < 2 ? 2 : c->levels;      /* popsift.cpp:86 */
     const float sigma0 = c->sigma;
     if (sigma0 > 2.0f) return -1;                           /* gauss_filter.cu:131 */
@@ -131,6 +135,20 @@ int orc_compute_tables(const orc_config* c, orc_tables* t)
     }
     for (int lvl = 0; lvl < ORC_GAUSS_LEVELS; lvl++)
         blur_row(t->abs_o0.sigma[lvl], &t->abs_o0.span[lvl], &t->abs_o0.filter[lvl * ORC_GAUSS_ALIGN]);
+    for (int lvl = 0; lvl < ORC_GAUSS_LEVELS; lvl++) {      /* transformBlurTable, gauss_filter.cu:372-405 */
+        int spn = t->inc.span[lvl];
+        if (!(spn & 1)) spn += 1;
+        t->inc_ispan[lvl] = spn;
+        const float* f = &t->inc.filter[lvl * ORC_GAUSS_ALIGN];
+        float* g = &t->inc_ifilter[lvl * ORC_GAUSS_ALIGN];
+        for (int x = 1; x < spn && x + 1 < ORC_GAUSS_ALIGN; x += 2) {
+            const float a = f[x], b = f[x + 1];
+            g[x] = a / (a + b);
+            g[x + 1] = a + b;
+        }
+        g[0] = f[0];
+    }
+    g_odd_spans = 0;
     t->peak_threshold = c->threshold * 0.5f * 255.0f / (float)levels; /* sift_conf.cu:276-279 */
     t->sigma_k = powf(2.0f, 1.0f / (float)levels);                    /* sift_constants.cu:27 */
     return 0;
@@ -311,6 +329,70 @@ static void cols_pass(const float* src, float* dst, int W, int H, const float* g
     }
 }
 
+/* MEASURED on a B200 (`texprobe lcoords`, 270 336 samples incl. the reference's own expression (x -/+ off) + 0.5, 0
+ * mismatches): texel position p = c - 0.5 is rounded half-up to 1/256 and clamped to [0, n-1]; the two texels are blended
+ * with the 8-bit weight like every float texture (exact sum / 256, one rounding, ties away from zero). */
+float orc_tex_lin1d(const float* row, int n, float c)
+{
+    double I = floor(((double)c - 0.5) * 256.0 + 0.5);
+    if (I < 0.0) I = 0.0;
+    if (I > (double)(n - 1) * 256.0) I = (double)(n - 1) * 256.0;
+    const long long Ii = (long long)I;
+    const int i = (int)(Ii >> 8), a = (int)(Ii & 255);
+    const int i1 = i + 1 < n ? i + 1 : n - 1;
+    const long double v = ((long double)(256 - a) * row[i] + (long double)a * row[i1]) / 256.0L;
+    const long double av = v < 0 ? -v : v;
+    float lo = (float)av;
+    if ((long double)lo > av) lo = nextafterf(lo, 0.0f);
+    const float hi = nextafterf(lo, INFINITY);
+    const float r = (av - (long double)lo >= (long double)hi - av) ? hi : lo;
+    return v < 0 ? -r : r;
+}
+
+/* absoluteSourceInterpolated::horiz / vert (s_pyramid_build_ai.cu:17-66; SASS: off = offset + (1 - u), coordinates
+ * (x -/+ off) + 0.5, val = tex + tex, out = fma(val, v, out), centre last): `along_x` selects the direction */
+static void interp_pass(const float* src, float* dst, int W, int H, const float* f, int span, int along_x)
+{
+    #pragma omp parallel for schedule(static)
+    for (int y = 0; y < H; y++) {
+        float* col = NULL;
+        (void)col;
+        for (int x = 0; x < W; x++) {
+            float out = 0.0f;
+            for (int offset = 1; offset <= span; offset += 2) {
+                const float u = f[offset];
+                const float off = (float)offset + (1.0f - u);
+                float t0, t1;
+                if (along_x) {
+                    const float* row = src + (size_t)y * W;
+                    t0 = orc_tex_lin1d(row, W, ((float)x - off) + 0.5f);
+                    t1 = orc_tex_lin1d(row, W, ((float)x + off) + 0.5f);
+                } else {
+                    /* a column: gather it once per call would be faster; the oracle only has to be right */
+                    float tmp[2][2];
+                    for (int k = 0; k < 2; k++) {
+                        const float c = (k == 0 ? ((float)y - off) : ((float)y + off)) + 0.5f;
+                        double I = floor(((double)c - 0.5) * 256.0 + 0.5);
+                        if (I < 0.0) I = 0.0;
+                        if (I > (double)(H - 1) * 256.0) I = (double)(H - 1) * 256.0;
+                        const long long Ii = (long long)I;
+                        const int i = (int)(Ii >> 8);
+                        const int i1 = i + 1 < H ? i + 1 : H - 1;
+                        tmp[k][0] = src[(size_t)i * W + x]; tmp[k][1] = src[(size_t)i1 * W + x];
+                        /* reuse the 1-D blend on a 2-texel row: position inside it = fraction only */
+                        const float cc = (float)((double)(Ii & 255) / 256.0) + 0.5f;
+                        tmp[k][0] = orc_tex_lin1d(tmp[k], 2, cc);
+                    }
+                    t0 = tmp[0][0]; t1 = tmp[1][0];
+                }
+                out = fmaf(t0 + t1, f[offset + 1], out);
+            }
+            const float v3 = src[(size_t)y * W + x];
+            dst[(size_t)y * W + x] = fmaf(v3, f[0], out);
+        }
+    }
+}
+
 /* s_pyramid_build.cu:460-594, default arm :547-575, then make_dog :74-92 */
 static void build_pyramid(orc_ctx* c, const uint8_t* img, const float* fimg)
 {
@@ -328,6 +410,19 @@ static void build_pyramid(orc_ctx* c, const uint8_t* img, const float* fimg)
                 const float* ga = &c->tab.abs_o0.filter[l * ORC_GAUSS_ALIGN];
                 level0_rows(c, img, fimg, interm, 0, l);
                 cols_pass(interm, dstp, W, H, ga, c->tab.abs_o0.span[l]);
+            } else if (c->cfg.gauss_relative && c->cfg.scaling_mode != 1 && !(l == 0 && o > 0)) {
+                /* VLFeat_Relative (s_pyramid_build.cu:515-542): interpolated passes with the transformed incremental row */
+                const float* fi = &c->tab.inc_ifilter[l * ORC_GAUSS_ALIGN];
+                const int ispan = c->tab.inc_ispan[l];
+                if (l == 0) {
+                    float* tmp = (float*)malloc(P * sizeof(float));
+                    level0_rows(c, img, fimg, tmp, 0, -1);
+                    interp_pass(tmp, dstp, W, H, fi, ispan, 0);
+                    free(tmp);
+                } else {
+                    interp_pass(c->gauss[o] + P * (l - 1), interm, W, H, fi, ispan, 1);
+                    interp_pass(interm, dstp, W, H, fi, ispan, 0);
+                }
             } else if (l == 0) {
                 if (o == 0 || c->cfg.scaling_mode == 1) {
                     /* ScaleDirect: rows with dd[octave], columns with inc[0] (vert_from_interm(octave, 0), :507) */

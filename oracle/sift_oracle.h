@@ -38,6 +38,7 @@ typedef struct orc_config {
     int32_t max_extrema;      /* 100000 */
     int32_t scaling_mode;     /* 0 = ScaleDefault, 1 = ScaleDirect (sift_conf.h; s_pyramid_build.cu:499-514) */
     int32_t gauss_direct;     /* 1 = --gauss-mode vlfeat-direct (VLFeat_Relative_All, s_pyramid_build.cu:543-546) */
+    int32_t gauss_relative;   /* 1 = --gauss-mode relative / vlfeat-hw-interpolated (VLFeat_Relative, :515-542) */
 } orc_config;
 
 typedef struct orc_gauss_table {
@@ -45,6 +46,11 @@ typedef struct orc_gauss_table {
     float   sigma[ORC_GAUSS_LEVELS];
     int32_t span[ORC_GAUSS_LEVELS];
 } orc_gauss_table;
+
+/* What tex2DLayered<float> returns for the reference's UNNORMALIZED, linear, clamped float textures (the data and
+ * intermediate planes, sift_octave.cu:243-252,311-325) between the texels of one row: c = the coordinate handed to the
+ * texture unit (readTex has already added 0.5).  Measured with `texprobe lcoords` (tests/golden/texture_lcoords.npz). */
+float orc_tex_lin1d(const float* row, int n, float c);
 
 typedef struct orc_tables {
     orc_gauss_table inc;                 /* gauss_filter.cu:173-188 */
@@ -58,6 +64,9 @@ typedef struct orc_tables {
     float   dd_sigma[ORC_MAX_OCTAVES];
     int32_t dd_span[ORC_MAX_OCTAVES];
     orc_gauss_table abs_o0;              /* gauss_filter.cu:190-199: every level of octave 0 from the input image */
+    /* the incremental rows transformed for hardware interpolation (gauss_filter.cu:372-405) */
+    float   inc_ifilter[ORC_GAUSS_LEVELS * ORC_GAUSS_ALIGN];
+    int32_t inc_ispan[ORC_GAUSS_LEVELS];
 } orc_tables;
 
 /* same layout as popsift::Feature (features.h:23-37), 72 bytes */

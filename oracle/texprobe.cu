@@ -89,9 +89,61 @@ __global__ void coords_kernel(cudaTextureObject_t tex, float* out, int W0, int H
     o[maxoff] = tex2D<float>(tex, read_x, read_y);
 }
 
+// unnormalized-coordinate, linear, clamp, layered float texture exactly as Octave::alloc_data_tex / alloc_interm_tex
+// configure theirs (sift_octave.cu:243-252,311-325); c = the coordinate handed to tex2DLayered (readTex adds 0.5 itself)
+__global__ void lfetch(cudaTextureObject_t tex, const float2* xy, float* out, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = tex2DLayered<float>(tex, xy[i].x, xy[i].y, 0);
+}
+
 int main(int argc, char** argv)
 {
     if (argc < 3) { fprintf(stderr, "usage\n"); return 2; }
+    if (!strcmp(argv[1], "lcoords")) {
+        // texprobe lcoords out.bin : texel (x, y) = 256 if (x + y) odd else 0, so a fetch between a zero texel and its
+        // right (upper) neighbour returns the 8-bit weight itself.  Sweeps of the x coordinate in steps of 1/4096 around several
+        // columns (small and large), the same in y, and the reference's own expression x - off + 0.5 for a few (x, off).
+        const int W = 8192, H = 64;
+        std::vector<float> img(size_t(W) * H);
+        for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) img[size_t(y) * W + x] = ((x + y) & 1) ? 256.0f : 0.0f;
+        cudaChannelFormatDesc cd = cudaCreateChannelDesc<float>();
+        cudaArray_t arr; CK(cudaMalloc3DArray(&arr, &cd, make_cudaExtent(W, H, 1), cudaArrayLayered));
+        cudaMemcpy3DParms cp; memset(&cp, 0, sizeof(cp));
+        cp.srcPtr = make_cudaPitchedPtr(img.data(), W * sizeof(float), W, H);
+        cp.dstArray = arr; cp.extent = make_cudaExtent(W, H, 1); cp.kind = cudaMemcpyHostToDevice;
+        CK(cudaMemcpy3D(&cp));
+        cudaResourceDesc rd; memset(&rd, 0, sizeof(rd)); rd.resType = cudaResourceTypeArray; rd.res.array.array = arr;
+        cudaTextureDesc td; memset(&td, 0, sizeof(td));
+        td.normalizedCoords = 0; td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+        td.readMode = cudaReadModeElementType; td.filterMode = cudaFilterModeLinear;
+        cudaTextureObject_t t; CK(cudaCreateTextureObject(&t, &rd, &td, 0));
+        std::vector<float2> q;
+        const int cols[] = {0, 1, 2, 5, 64, 1000, 2047, 2048, 4095, 4096, 8000, 8190};
+        for (int c : cols) for (int k = -2048; k < 6144; k++) q.push_back(make_float2(float(c) + 0.5f + float(k) / 4096.0f, 10.5f));
+        const int rows[] = {0, 1, 2, 31, 62};
+        for (int r : rows) for (int k = -2048; k < 6144; k++) q.push_back(make_float2(100.5f, float(r) + 0.5f + float(k) / 4096.0f));
+        // the reference's expression: float(x) - off + 0.5f with off = offset + (1 - u), u a float in (0, 1)
+        srand(99);
+        for (int i = 0; i < 65536; i++) {
+            const int x = rand() % 8000 + 40, offset = 1 + 2 * (rand() % 8);
+            const float u = float(rand() % 1000000) / 1000000.0f;
+            const float off = offset + (1.0f - u);
+            q.push_back(make_float2((float(x) - off) + 0.5f, 20.5f));
+            q.push_back(make_float2((float(x) + off) + 0.5f, 20.5f));
+        }
+        float2* dq; float* dout; CK(cudaMalloc(&dq, q.size() * sizeof(float2))); CK(cudaMalloc(&dout, q.size() * 4));
+        CK(cudaMemcpy(dq, q.data(), q.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        lfetch<<<(int(q.size()) + 255) / 256, 256>>>(t, dq, dout, int(q.size()));
+        CK(cudaDeviceSynchronize());
+        std::vector<float> o(q.size()); CK(cudaMemcpy(o.data(), dout, q.size() * 4, cudaMemcpyDeviceToHost));
+        FILE* fp = fopen(argv[2], "wb");
+        int hdr[4] = { W, H, int(q.size()), 0 };
+        fwrite(hdr, 4, 4, fp); fwrite(q.data(), sizeof(float2), q.size(), fp); fwrite(o.data(), 4, o.size(), fp);
+        fclose(fp);
+        printf("texprobe lcoords: %zu samples\n", q.size());
+        return 0;
+    }
     if (!strcmp(argv[1], "pairs")) {
         // image 512 wide x 512 high:
         //   rows 0..255   : row a holds [a, b] pairs at columns (2b, 2b+1)  -> x-fraction 0.5 between them

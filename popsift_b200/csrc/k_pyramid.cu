@@ -496,6 +496,43 @@ int launch_blur_level(const OctaveView& o, int level, const GaussRow& g, const O
     return 1;
 }
 
+// --gauss-mode relative / vlfeat-hw-interpolated (VLFeat_Relative; reference absoluteSourceInterpolated::horiz / vert,
+// s_pyramid_build_ai.cu:17-66): pairs of taps are merged into ONE linearly interpolated fetch of the unnormalized float
+// texture at distance off = offset + (1 - u).  The texture unit's arithmetic there, measured with `texprobe lcoords`
+// (tests/golden/texture_lcoords.npz, oracle orc_tex_lin1d): texel position c - 0.5 rounded half-up to 1/256 and clamped
+// to [0, n-1], then the 8-bit-weight blend of every float texture (tex_blend_f32).  Order from the reference's SASS:
+// off = offset + (1 - u); coordinate (x -/+ off) + 0.5; val = tex(-) + tex(+); out = fma(val, v, out); centre last.
+__device__ __forceinline__ float tex_lin1d(const float* __restrict__ base, long long stride, int n, float c)
+{
+    double I = floor(__fma_rn(__dsub_rn((double)c, 0.5), 256.0, 0.5));
+    I = fmin(fmax(I, 0.0), (double)(n - 1) * 256.0);
+    const long long Ii = (long long)I;
+    const int i = (int)(Ii >> 8), a = (int)(Ii & 255);
+    const int i1 = min(i + 1, n - 1);
+    return tex_blend_f32(__ldg(base + i * stride), __ldg(base + i1 * stride), 0.0f, 0.0f, a, 0);
+}
+
+template <bool ALONG_X>
+__global__ void __launch_bounds__(256)
+interp_pass_kernel(const float* __restrict__ src, float* __restrict__ dst, int W, int H, int pitch, Taps f, int span)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W || y >= H) return;
+    const float* base = ALONG_X ? src + (size_t)y * pitch : src + x;
+    const long long stride = ALONG_X ? 1 : pitch;
+    const int n = ALONG_X ? W : H;
+    const float pos = (float)(ALONG_X ? x : y);
+    float out = 0.0f;
+    for (int offset = 1; offset <= span; offset += 2) {
+        const float u = f.g[offset];
+        const float off = __fadd_rn((float)offset, __fsub_rn(1.0f, u));
+        const float t0 = tex_lin1d(base, stride, n, __fadd_rn(__fsub_rn(pos, off), 0.5f));
+        const float t1 = tex_lin1d(base, stride, n, __fadd_rn(__fadd_rn(pos, off), 0.5f));
+        out = __fmaf_rn(__fadd_rn(t0, t1), f.g[offset + 1], out);
+    }
+    dst[(size_t)y * pitch + x] = __fmaf_rn(__ldg(src + (size_t)y * pitch + x), f.g[0], out);
+}
+
 // --gauss-mode vlfeat-direct: level `level` of octave 0 straight from the input image with `taps` in both directions
 template <typename PIX>
 static int launch_level0_abs_any(const PIX* img, size_t img_pitch, int w, int h, float upscale, int sift_mode,
@@ -508,7 +545,8 @@ static int launch_level0_abs_any(const PIX* img, size_t img_pitch, int w, int h,
     const Taps t = make_taps(taps);
     const int plan = level0_plan(w, h, o0.w, o0.h, shift, R);
     const size_t sm = sizeof(float) * ((size_t)(TH + 2 * R) * (TW + 2 * R) + (size_t)(TH + 2 * R) * TW);
-    ensure_smem(level0_generic_kernel<PIX>, sm);
+    constexpr int RMAX = PS_GAUSS_ALIGN - 1;      // the opt-in is made once per kernel: ask for the largest radius
+    ensure_smem(level0_generic_kernel<PIX>, sizeof(float) * ((size_t)(TH + 2 * RMAX) * (TW + 2 * RMAX) + (size_t)(TH + 2 * RMAX) * TW));
     dim3 grid((o0.w + TW - 1) / TW, (o0.h + TH - 1) / TH);
     level0_generic_kernel<PIX><<<grid, NT, sm, st>>>(img, img_pitch, w, h, shift, o0.gauss + o0.plane * level, o0.w, o0.h, o0.pitch,
                                                      t, t, R, R, plan == LEVEL0_PER_TAP ? 1 : 0);
@@ -534,6 +572,49 @@ int launch_decimate(const OctaveView& prev, int level, const OctaveView& next, c
     dim3 grid((next.w + 127) / 128, next.h);
     decimate_kernel<<<grid, 128, 0, st>>>(prev.gauss + prev.plane * level, prev.w, prev.h, prev.pitch, next.gauss, next.w, next.h, next.pitch);
     return 1;
+}
+
+// one interpolated pass (rows: along_x != 0) over a plane; `f` = the transformed row (gauss_filter.cu:372-405), span its i_span
+int launch_interp_pass(const float* src, float* dst, int W, int H, int pitch, const GaussRow& f, int ispan, int along_x, cudaStream_t st)
+{
+    if (ispan < 1 || ispan >= PS_GAUSS_ALIGN) return -1;
+    const Taps t = make_taps(f);
+    dim3 grid((W + 255) / 256, H);
+    if (along_x) interp_pass_kernel<true><<<grid, 256, 0, st>>>(src, dst, W, H, pitch, t, ispan);
+    else         interp_pass_kernel<false><<<grid, 256, 0, st>>>(src, dst, W, H, pitch, t, ispan);
+    return 1;
+}
+// rows of octave 0 straight from the input image (the first horizontal pass alone) into `dst` (pitch of the octave)
+template <typename PIX>
+static int launch_level0_rows_any(const PIX* img, size_t img_pitch, int w, int h, float upscale, int sift_mode,
+                                  const OctaveView& o0, float* dst, const GaussRow& dd, cudaStream_t st)
+{
+    float shift = 0.5f;
+    if (sift_mode == PS_MODE_POPSIFT || sift_mode == PS_MODE_VLFEAT) shift = 0.5f * powf(2.0f, upscale);
+    const int R = dd.span - 1;
+    if (R < 0 || R >= PS_GAUSS_ALIGN) return -1;
+    const Taps t = make_taps(dd);
+    Taps ident;
+    for (int i = 0; i < PS_GAUSS_ALIGN; ++i) ident.g[i] = 0.0f;
+    ident.g[0] = 1.0f;                            // column pass of radius 0 with weight 1: fma(v, 1, 0) == v
+    const int plan = level0_plan(w, h, o0.w, o0.h, shift, R);
+    const size_t sm = sizeof(float) * ((size_t)TH * (TW + 2 * R) + (size_t)TH * TW);
+    constexpr int RMAX = PS_GAUSS_ALIGN - 1;
+    ensure_smem(level0_generic_kernel<PIX>, sizeof(float) * ((size_t)(TH + 2 * RMAX) * (TW + 2 * RMAX) + (size_t)(TH + 2 * RMAX) * TW));
+    dim3 grid((o0.w + TW - 1) / TW, (o0.h + TH - 1) / TH);
+    level0_generic_kernel<PIX><<<grid, NT, sm, st>>>(img, img_pitch, w, h, shift, dst, o0.w, o0.h, o0.pitch, t, ident, R, 0,
+                                                     plan == LEVEL0_PER_TAP ? 1 : 0);
+    return 1;
+}
+int launch_level0_rows_u8(const uint8_t* img, size_t img_pitch, int w, int h, float upscale, int sift_mode,
+                          const OctaveView& o0, float* dst, const GaussRow& dd, cudaStream_t st)
+{
+    return launch_level0_rows_any<uint8_t>(img, img_pitch, w, h, upscale, sift_mode, o0, dst, dd, st);
+}
+int launch_level0_rows_f32(const float* img, size_t img_pitch_floats, int w, int h, float upscale, int sift_mode,
+                           const OctaveView& o0, float* dst, const GaussRow& dd, cudaStream_t st)
+{
+    return launch_level0_rows_any<float>(img, img_pitch_floats, w, h, upscale, sift_mode, o0, dst, dd, st);
 }
 
 } // namespace psb

@@ -38,6 +38,7 @@ struct Slot {
     uint8_t* h_img = nullptr;      // pinned staging, same size
     // pyramid
     float*  d_planes = nullptr;
+    float*  d_interm = nullptr;    // one octave-0 plane of row-filtered values (--gauss-mode relative only)
     size_t  planes_floats = 0;
     int*    cand_cnt = nullptr;    // candidate counts of all octaves, levels and blocks (inside d_planes)
     size_t  cand_cnt_bytes = 0;
@@ -83,6 +84,7 @@ struct ps_ctx {
     GaussRow dd0;                         // first horizontal pass over the input image, octave 0
     GaussRow dd[kMaxOctaves];             // ... of every octave (Config::ScaleDirect)
     GaussRow abs0[PS_GAUSS_LEVELS];       // octave 0 from the input image, every level (--gauss-mode vlfeat-direct)
+    GaussRow irows[PS_GAUSS_LEVELS];      // incremental rows transformed for interpolated fetches (--gauss-mode relative); span = i_span
     Consts k{};
     int max_w = 0, max_h = 0;
     int max_octaves = 0;
@@ -201,6 +203,37 @@ int run_pyramid(ps_ctx* ctx, Slot& s)
     int n = 0, r;
     // the pyramid kernels report the threshold-passing DoG samples when every scanned level runs on the
     // marching kernels (16-bit coordinates in the lists)
+    // --gauss-mode relative / vlfeat-hw-interpolated (VLFeat_Relative, s_pyramid_build.cu:515-542): every pass merges pairs of
+    // taps into interpolated fetches; simple per-pixel kernels (k_pyramid.cu), DoG and decimation by their own kernels, dense
+    // extrema scan.  (Under ScaleDirect the reference's direct-scaling arm applies, with interpolated passes: not built.)
+    if (ctx->cfg.gauss_mode == PS_GAUSS_VLFEAT_RELATIVE) {
+        if (direct) return ctx->fail(PS_ERR_ARG, "unsupported configuration: --gauss-mode relative together with --direct-scaling");
+        s.view.cands_filled = 0;
+        for (int o = 0; o < s.num_octaves; ++o) {
+            const OctaveView& ov = s.view.oct[o];
+            if (o == 0) {
+                if (s.is_float)
+                    r = launch_level0_rows_f32(reinterpret_cast<const float*>(s.d_img), (size_t)s.w, s.w, s.h, ctx->cfg.upscale,
+                                               ctx->cfg.sift_mode, ov, s.d_interm, ctx->dd0, s.stream);
+                else
+                    r = launch_level0_rows_u8(s.d_img, u8_pitch(s.w), s.w, s.h, ctx->cfg.upscale, ctx->cfg.sift_mode, ov, s.d_interm,
+                                              ctx->dd0, s.stream);
+                if (r < 0) return ctx->fail(PS_ERR_ARG, "unsupported level-0 filter span %d", ctx->dd0.span);
+                n += r;
+                n += launch_interp_pass(s.d_interm, ov.gauss, ov.w, ov.h, ov.pitch, ctx->irows[0], ctx->irows[0].span, 0, s.stream);
+            } else {
+                n += launch_decimate(s.view.oct[o - 1], L, ov, s.stream);
+            }
+            for (int l = 1; l < L + 3; ++l) {
+                n += launch_interp_pass(ov.gauss + ov.plane * (l - 1), s.d_interm, ov.w, ov.h, ov.pitch, ctx->irows[l], ctx->irows[l].span, 1, s.stream);
+                n += launch_interp_pass(s.d_interm, ov.gauss + ov.plane * l, ov.w, ov.h, ov.pitch, ctx->irows[l], ctx->irows[l].span, 0, s.stream);
+            }
+            n += launch_dog_planes(ov, L + 2, s.stream);
+        }
+        ctx->launches += n;
+        PS_CUDA(ctx, cudaGetLastError());
+        return PS_OK;
+    }
     // --gauss-mode vlfeat-direct (VLFeat_Relative_All, s_pyramid_build.cu:543-546; under ScaleDirect the direct-scaling
     // arm comes first, :499): every level of octave 0 straight from the input image
     const bool abs_o0 = ctx->cfg.gauss_mode == PS_GAUSS_VLFEAT_RELATIVE_ALL && !direct;
@@ -459,7 +492,7 @@ extern "C" void ps_destroy(ps_ctx* ctx)
     cudaSetDevice(ctx->device);
     for (Slot& s : ctx->slots) {
         if (s.stream) cudaStreamSynchronize(s.stream);
-        cudaFree(s.d_img); cudaFreeHost(s.h_img); cudaFree(s.d_planes); cudaFree(s.d_iext); cudaFree(s.d_iext_f); cudaFree(s.d_keep); cudaFree(s.d_plan); cudaFree(s.d_ext); cudaFree(s.d_ori_slice);
+        cudaFree(s.d_img); cudaFreeHost(s.h_img); cudaFree(s.d_planes); cudaFree(s.d_interm); cudaFree(s.d_iext); cudaFree(s.d_iext_f); cudaFree(s.d_keep); cudaFree(s.d_plan); cudaFree(s.d_ext); cudaFree(s.d_ori_slice);
         cudaFree(s.d_feat); cudaFree(s.d_desc); cudaFree(s.d_f2e); cudaFree(s.d_ct); cudaFreeHost(s.h_ct);
         cudaFreeHost(s.h_feat); cudaFreeHost(s.h_desc);
         for (auto& e : s.ev) if (e) cudaEventDestroy(e);
@@ -510,7 +543,7 @@ extern "C" ps_ctx* ps_create(int device, const ps_config* cfg, int max_w, int ma
     }
     if (ps_gauss_tables_compute(&ctx->cfg, &ctx->tab) != PS_OK) {
         delete ctx;
-        return bail("ps_create: unsupported configuration (sigma > 2.0, levels > 12, or a gauss mode other than vlfeat / opencv / vlfeat-direct)", cudaSuccess);
+        return bail("ps_create: unsupported configuration (sigma > 2.0, levels > 12, or --gauss-mode fixed9 / fixed15)", cudaSuccess);
     }
     for (int l = 0; l < PS_GAUSS_LEVELS; ++l) {
         std::memcpy(ctx->rows[l].tap, &ctx->tab.inc_filter[l * PS_GAUSS_ALIGN], sizeof(float) * PS_GAUSS_ALIGN);
@@ -525,6 +558,8 @@ extern "C" ps_ctx* ps_create(int device, const ps_config* cfg, int max_w, int ma
     for (int l = 0; l < PS_GAUSS_LEVELS; ++l) {
         std::memcpy(ctx->abs0[l].tap, &ctx->tab.abs_filter[l * PS_GAUSS_ALIGN], sizeof(float) * PS_GAUSS_ALIGN);
         ctx->abs0[l].span = ctx->tab.abs_span[l];
+        std::memcpy(ctx->irows[l].tap, &ctx->tab.inc_ifilter[l * PS_GAUSS_ALIGN], sizeof(float) * PS_GAUSS_ALIGN);
+        ctx->irows[l].span = ctx->tab.inc_ispan[l];
     }
     ctx->max_w = max_w; ctx->max_h = max_h;
     int32_t W[kMaxOctaves], H[kMaxOctaves];
@@ -560,6 +595,11 @@ extern "C" ps_ctx* ps_create(int device, const ps_config* cfg, int max_w, int ma
         PS_TRY(cudaHostAlloc(&s.h_img, (size_t)max_w * max_h * 4, cudaHostAllocDefault));
         PS_TRY(cudaMalloc(&s.d_planes, planes * sizeof(float)));
         s.planes_floats = planes;
+        if (ctx->cfg.gauss_mode == PS_GAUSS_VLFEAT_RELATIVE) {
+            int32_t W0[kMaxOctaves], H0[kMaxOctaves];
+            ps_geometry(&ctx->cfg, max_w, max_h, W0, H0);
+            PS_TRY(cudaMalloc(&s.d_interm, sizeof(float) * (size_t)((W0[0] + 31) / 32 * 32 + 32) * (size_t)H0[0]));
+        }
         PS_TRY(cudaMalloc(&s.d_iext, sizeof(InitialExtremum) * (size_t)ctx->max_octaves * k.max_extrema));
         if (ctx->cfg.filter_max_extrema > 0) {
             PS_TRY(cudaMalloc(&s.d_iext_f, sizeof(InitialExtremum) * (size_t)ctx->max_octaves * k.max_extrema));

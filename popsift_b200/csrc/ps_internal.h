@@ -128,6 +128,12 @@ int launch_level0_abs_u8(const uint8_t* img, size_t img_pitch, int w, int h, flo
 int launch_level0_abs_f32(const float* img, size_t img_pitch_floats, int w, int h, float upscale, int sift_mode,
                           const OctaveView& o0, int level, const GaussRow& taps, cudaStream_t st);
 int launch_dog_planes(const OctaveView& o, int nplanes, cudaStream_t st);
+// --gauss-mode relative (VLFeat_Relative): the first horizontal pass alone, and one interpolated pass over a plane
+int launch_level0_rows_u8(const uint8_t* img, size_t img_pitch, int w, int h, float upscale, int sift_mode,
+                          const OctaveView& o0, float* dst, const GaussRow& dd, cudaStream_t st);
+int launch_level0_rows_f32(const float* img, size_t img_pitch_floats, int w, int h, float upscale, int sift_mode,
+                           const OctaveView& o0, float* dst, const GaussRow& dd, cudaStream_t st);
+int launch_interp_pass(const float* src, float* dst, int W, int H, int pitch, const GaussRow& f, int ispan, int along_x, cudaStream_t st);
 int launch_decimate(const OctaveView& prev, int level, const OctaveView& next, cudaStream_t st);
 // level l >= 1 of one octave: blur level l-1 -> level l, DoG[l-1] = G[l]-G[l-1]; if next0 != nullptr
 // also writes every second pixel into the next octave's level 0.

@@ -16,23 +16,27 @@ namespace {
 
 // Half-width (including the centre tap) of the kernel for one sigma: VLFeat's rule (reference gauss_filter.cu:301-307)
 // or OpenCV's (--gauss-mode opencv, gauss_filter.cu:320-327).  Everything else about the two modes is identical.
-int kernel_span(float sigma, bool opencv)
+// mode: 0 = VLFeat rule, 1 = OpenCV rule, 2 = VLFeat rule rounded up to the next odd span (--gauss-mode relative /
+// vlfeat-hw-interpolated: the taps are consumed in pairs, gauss_filter.cu:309-319)
+int kernel_span(float sigma, int mode)
 {
+    const bool opencv = mode == 1;
     if (opencv) {
         int span = static_cast<int>(std::roundf(2.0f * 4.0f * sigma + 1.0f)) | 1;
         span >>= 1;
         span += 1;
         return std::min(span, PS_GAUSS_ALIGN - 1);
     }
-    const int s = static_cast<int>(std::ceil(4.0f * sigma) + 1.0f);
+    int s = std::min(static_cast<int>(std::ceil(4.0f * sigma) + 1.0f), PS_GAUSS_ALIGN - 1);
+    if (mode == 2 && (s & 1) == 0) s += 1;
     return std::min(s, PS_GAUSS_ALIGN - 1);
 }
 
 // One normalised half-kernel.  The taps are evaluated in double, stored as float; the
 // normaliser is a double that accumulates twice the *stored float* tap.
-void fill_kernel(float sigma, float* taps, int32_t* span_out, bool opencv)
+void fill_kernel(float sigma, float* taps, int32_t* span_out, int mode)
 {
-    const int span = kernel_span(sigma, opencv);
+    const int span = kernel_span(sigma, mode);
     std::fill(taps, taps + PS_GAUSS_ALIGN, 0.0f);
     taps[0] = 1.0f;
     double norm = 1.0;
@@ -82,8 +86,9 @@ extern "C" int ps_gauss_tables_compute(const ps_config* cfg, ps_gauss_tables* ou
     if (s0 > 2.0f) return PS_ERR_ARG;                 // reference gauss_filter.cu:131-137
     if (levels > PS_GAUSS_LEVELS) return PS_ERR_ARG;  // reference gauss_filter.cu:138-144
     if (cfg->gauss_mode != PS_GAUSS_VLFEAT_COMPUTE && cfg->gauss_mode != PS_GAUSS_OPENCV_COMPUTE &&
-        cfg->gauss_mode != PS_GAUSS_VLFEAT_RELATIVE_ALL) return PS_ERR_ARG;   // RELATIVE_ALL: the vlfeat span rule (gauss_filter.cu:279-281)
-    const bool ocv = cfg->gauss_mode == PS_GAUSS_OPENCV_COMPUTE;
+        cfg->gauss_mode != PS_GAUSS_VLFEAT_RELATIVE_ALL && cfg->gauss_mode != PS_GAUSS_VLFEAT_RELATIVE) return PS_ERR_ARG;
+    // span rule (gauss_filter.cu:274-296): RELATIVE_ALL uses the vlfeat rule, RELATIVE the odd one
+    const int ocv = cfg->gauss_mode == PS_GAUSS_OPENCV_COMPUTE ? 1 : cfg->gauss_mode == PS_GAUSS_VLFEAT_RELATIVE ? 2 : 0;
     const int planes = levels + 3;
     const float blur_in = cfg->has_initial_blur ? cfg->initial_blur * std::pow(2.0f, cfg->upscale) : 0.0f;
 
@@ -119,6 +124,21 @@ extern "C" int ps_gauss_tables_compute(const ps_config* cfg, ps_gauss_tables* ou
     }
     for (int l = 0; l < PS_GAUSS_LEVELS; ++l)
         fill_kernel(out->abs_sigma[l], &out->abs_filter[l * PS_GAUSS_ALIGN], &out->abs_span[l], ocv);
+    // pairs of taps merged into one linearly interpolated fetch (GaussTable::transformBlurTable, gauss_filter.cu:372-405):
+    // odd entries = the fraction u = a / (a + b), even entries = the weight v = a + b of the pair
+    for (int l = 0; l < PS_GAUSS_LEVELS; ++l) {
+        int spn = out->inc_span[l];
+        if (!(spn & 1)) spn += 1;
+        out->inc_ispan[l] = spn;
+        float* f = &out->inc_filter[l * PS_GAUSS_ALIGN];
+        float* g = &out->inc_ifilter[l * PS_GAUSS_ALIGN];
+        g[0] = f[0];
+        for (int x = 1; x < spn && x + 1 < PS_GAUSS_ALIGN; x += 2) {
+            const float a = f[x], b = f[x + 1];
+            g[x] = a / (a + b);
+            g[x + 1] = a + b;
+        }
+    }
     out->peak_threshold = cfg->threshold * 0.5f * 255.0f / static_cast<float>(levels);
     out->sigma_k = std::pow(2.0f, 1.0f / static_cast<float>(levels));
     return PS_OK;

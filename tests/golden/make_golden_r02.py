@@ -147,6 +147,11 @@ def main(src):
     # output is saved by tests/test_gpu_parity.py::test_direct_scaling_vs_oracle_and_live_reference)
     save_feat(src, "ref_direct_f256.bin", "f256_direct")
     save_feat(os.path.dirname(src.rstrip("/")), "ref_direct_640.bin", "f640_direct")
+    # --gauss-mode vlfeat-direct (tools/gpu_round2_r.sh)
+    save_feat(src, "ref_vlfeat_direct_f256.bin", "f256_vlfeat_direct")
+    fn = os.path.join(src, "ref_vlfeat_direct_f256_planes.json")
+    if os.path.exists(fn):
+        json.dump(json.load(open(fn)), open(os.path.join(HERE, "planes_f256_vlfeat_direct.json"), "w"), indent=0)
     fn = os.path.join(src, "ref_direct_f256_planes.json")
     if os.path.exists(fn):
         json.dump(json.load(open(fn)), open(os.path.join(HERE, "planes_f256_direct.json"), "w"), indent=0)

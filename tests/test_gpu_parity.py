@@ -522,7 +522,7 @@ def test_grid_filter_1280_and_unsupported_options_are_refused():
     assert feats.getFeatureCount() == len(z["feat"]) and feats.getDescriptorCount() == int(z["n_desc"][0])
     ps.uninit()
     # options whose numerics are not implemented are refused, never silently computed with the default path
-    for setter in (lambda c: c.setGaussMode("fixed9"), lambda c: c.setGaussMode("relative")):
+    for setter in (lambda c: c.setGaussMode("fixed9"), lambda c: c.setGaussMode("fixed15")):
         c = mk_cfg()
         setter(c)
         with pytest.raises(api.PopSiftError):
@@ -817,4 +817,47 @@ def test_gauss_mode_vlfeat_direct_vs_oracle_and_live_reference(tmp_path):
         if os.path.isdir(out_dir):
             import shutil
             shutil.copy(str(tmp_path / "f.bin"), os.path.join(out_dir, "ref_vlfeat_direct_640.bin"))
+    ps.uninit()
+
+
+def test_gauss_mode_relative_vs_oracle_and_live_reference(tmp_path):
+    """--gauss-mode relative = vlfeat-hw-interpolated (Config::VLFeat_Relative; reference s_pyramid_build.cu:515-542,
+    s_pyramid_build_ai.cu:17-66): pairs of taps merged into linearly interpolated fetches of the unnormalized float texture
+    (8-bit weights, position rounded half-up to 1/256 -- tests/golden/texture_lcoords.npz).  Planes bit-exact against the
+    oracle and against the live reference's --log dumps, same features."""
+    w, h = 640, 480
+    img = make_frame(w, h, 35)
+    cfg = mk_cfg("vlfeat", "classic")
+    cfg.setGaussMode("relative")
+    ps, feats = run_gpu(img, cfg)
+    o = ol.Oracle(ol.make_config(mode="vlfeat", norm="classic", gauss_relative=1), w, h)
+    o.run(img)
+    bad = []
+    for oc in range(o.num_octaves):
+        for l in range(6):
+            if not np.array_equal(ps.plane(0, oc, l), o.gauss(oc, l)):
+                bad.append(("g", oc, l, int((ps.plane(0, oc, l) != o.gauss(oc, l)).sum())))
+        for l in range(5):
+            if not np.array_equal(ps.plane(0, oc, l, dog=True), o.dog(oc, l)):
+                bad.append(("d", oc, l))
+    assert not bad, bad
+    of, od = o.features()
+    assert (feats.getFeatureCount(), feats.getDescriptorCount()) == (len(of), len(od))
+    o.close()
+    if os.path.exists(REF):
+        write_pgm(str(tmp_path / "f.pgm"), img)
+        subprocess.run([REF, "-i", "f.pgm", "-o", "f.bin", "--log", "--mode", "vlfeat", "--norm", "classic", "--gauss-mode", "relative"],
+                       cwd=str(tmp_path), check=True, capture_output=True)
+        refbad = []
+        for oc in range(3):
+            for l in range(6):
+                ref = ol.read_ref_dump(str(tmp_path / "dir-octave-dump" / ("pyramid-o-%d-l-%d.dump" % (oc, l))))
+                mine = ps.plane(0, oc, l)
+                if not np.array_equal(ref, mine):
+                    refbad.append((oc, l, int((ref != mine).sum()), float(np.abs(ref - mine).max())))
+        assert not refbad, refbad
+        rf, rd = ol.read_ref_features(str(tmp_path / "f.bin"))
+        assert (feats.getFeatureCount(), feats.getDescriptorCount()) == (len(rf), len(rd))
+        r = compare.report(*feats.keypoints(), *ol.flatten(rf, rd))
+        assert r["f1"] >= F1_MIN and r["desc_l2_max"] < L2_MAX, r
     ps.uninit()

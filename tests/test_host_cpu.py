@@ -34,7 +34,7 @@ def test_struct_sizes_match_reference_layouts():
 
 
 CFGS = [dict(), dict(downsampling=0), dict(levels=4), dict(sigma=1.2, levels=5), dict(initial_blur=0.0),
-        dict(downsampling=-2), dict(levels=2, sigma=2.0)]
+        dict(downsampling=-2), dict(levels=2, sigma=2.0), dict(gauss_relative=1), dict(gauss_relative=1, levels=4, sigma=1.3)]
 
 
 def _mk(kw):
@@ -48,6 +48,8 @@ def _mk(kw):
         c.setSigma(o["sigma"])
     if "initial_blur" in o:
         c.setInitialBlur(o["initial_blur"])
+    if o.get("gauss_relative"):
+        c.setGaussMode("relative")
     oc = ol.make_config(**{k: v for k, v in kw.items() if k != "initial_blur"})
     if "initial_blur" in kw:
         oc.initial_blur = kw["initial_blur"]
@@ -70,6 +72,9 @@ def test_gauss_tables_bit_identical_to_oracle(kw):
     assert list(t.dd_span) == list(ot.dd_span) and t.dd_span[0] == t.dd_span0
     assert np.array_equal(np.frombuffer(t.dd_filter, np.uint32), np.frombuffer(ot.dd_filter, np.uint32))
     assert np.array_equal(np.frombuffer(t.dd_filter, np.uint32)[:32], np.frombuffer(t.dd_filter0, np.uint32))
+    # the rows transformed for interpolated fetches (--gauss-mode relative)
+    assert list(t.inc_ispan) == list(ot.inc_ispan)
+    assert np.array_equal(np.frombuffer(t.inc_ifilter, np.uint32), np.frombuffer(ot.inc_ifilter, np.uint32))
     # the absolute rows of octave 0 (--gauss-mode vlfeat-direct)
     assert list(t.abs_span) == list(ot.abs_o0.span)
     assert np.array_equal(np.frombuffer(t.abs_filter, np.uint32), np.frombuffer(ot.abs_o0.filter, np.uint32))
