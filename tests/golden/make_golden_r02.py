@@ -147,6 +147,21 @@ def main(src):
     # output is saved by tests/test_gpu_parity.py::test_direct_scaling_vs_oracle_and_live_reference)
     save_feat(src, "ref_direct_f256.bin", "f256_direct")
     save_feat(os.path.dirname(src.rstrip("/")), "ref_direct_640.bin", "f640_direct")
+    # --gauss-mode relative (tools/gpu_round2_t.sh), the unnormalized linear float texture probe (tools/gpu_round2_s.sh)
+    save_feat(src, "ref_relative_f256.bin", "f256_relative")
+    save_feat(os.path.dirname(src.rstrip("/")), "ref_vlfeat_direct_640.bin", "f640_vlfeat_direct")
+    fn = os.path.join(src, "ref_relative_f256_planes.json")
+    if os.path.exists(fn):
+        json.dump(json.load(open(fn)), open(os.path.join(HERE, "planes_f256_relative.json"), "w"), indent=0)
+    fn = os.path.join(src, "tex_lcoords.bin")
+    if os.path.exists(fn):
+        import struct
+        data = open(fn, "rb").read()
+        W, H, n, _ = struct.unpack_from("4i", data, 0)
+        q = np.frombuffer(data, np.float32, 2 * n, 16).reshape(n, 2)
+        o = np.frombuffer(data, np.float32, n, 16 + 8 * n)
+        sel = np.r_[np.arange(0, 17 * 8192, 5), np.arange(17 * 8192, n, 3)]
+        np.savez_compressed(os.path.join(HERE, "texture_lcoords.npz"), W=np.int32(W), H=np.int32(H), xy=q[sel], out=o[sel])
     # --gauss-mode vlfeat-direct (tools/gpu_round2_r.sh)
     save_feat(src, "ref_vlfeat_direct_f256.bin", "f256_vlfeat_direct")
     fn = os.path.join(src, "ref_vlfeat_direct_f256_planes.json")
