@@ -61,7 +61,7 @@ typedef struct ps_config {
     float   initial_blur;      /* 0.5                                                      */
     int32_t has_initial_blur;  /* 1                                                        */
     int32_t sift_mode;         /* PS_MODE_*                                                */
-    int32_t gauss_mode;        /* PS_GAUSS_*  (FIXED9 / FIXED15 are REJECTED by ps_create) */
+    int32_t gauss_mode;        /* PS_GAUSS_*  (all six; FIXED9 / FIXED15 need levels == 3 like the reference) */
     int32_t desc_mode;         /* PS_DESC_*   (loop is the fast path; iloop / grid / igrid / notile follow the reference's schemes) */
     int32_t norm_mode;         /* PS_NORM_*                                                */
     int32_t norm_multi;        /* descriptor scaled by 2^norm_multi                        */
@@ -118,6 +118,11 @@ typedef struct ps_gauss_tables {
      * (= vlfeat-hw-interpolated, VLFeat_Relative): [0] centre weight, odd x: fraction u, even x: pair weight v */
     float   inc_ifilter[PS_GAUSS_LEVELS * PS_GAUSS_ALIGN];
     int32_t inc_ispan[PS_GAUSS_LEVELS];
+    /* the absolute rows of octaves >= 1 (gauss_filter.cu:200-214): level l straight from level 0 of the same octave; used by
+     * --gauss-mode fixed9 / fixed15 */
+    float   absn_filter[PS_GAUSS_LEVELS * PS_GAUSS_ALIGN];
+    float   absn_sigma[PS_GAUSS_LEVELS];
+    int32_t absn_span[PS_GAUSS_LEVELS];
 } ps_gauss_tables;
 
 enum { PS_STAGE_H2D = 0, PS_STAGE_PYRAMID = 1, PS_STAGE_EXTREMA = 2, PS_STAGE_ORIENT = 3,

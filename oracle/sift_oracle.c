@@ -54,6 +54,7 @@ void orc_default_config(orc_config* c)
     c->scaling_mode = 0;
     c->gauss_direct = 0;
     c->gauss_relative = 0;
+    c->gauss_fixed = 0;
 }
 
 int orc_set_threads(int n)
@@ -77,11 +78,13 @@ static int vlfeat_span(float sigma)
 
 /* gauss_filter.cu:341-371 (computeBlurTable): taps in double, stored float,
  * normalised by a double sum that accumulates 2.0f*val of the *float* tap. */
+static int g_fixed_span = 0;  /* gauss_filter.cu:289-292: 5 (fixed9) or 8 (fixed15) while those modes' tables are built */
 static int g_odd_spans = 0;   /* gauss_filter.cu:309-319 vlFeatRelativeSpan: set while the tables of --gauss-mode relative are built */
 static void blur_row(float sig, int* span_out, float* f)
 {
     int spn = vlfeat_span(sig);
     if (g_odd_spans && (spn & 1) == 0) spn += 1;
+    if (g_fixed_span) spn = g_fixed_span;
     if (spn > ORC_GAUSS_ALIGN - 1) spn = ORC_GAUSS_ALIGN - 1;
     double sum = 1.0;
     f[0] = 1.0f;
@@ -99,6 +102,7 @@ int orc_compute_tables(const orc_config* c, orc_tables* t)
 {
     memset(t, 0, sizeof(*t));
     g_odd_spans = c->gauss_relative ? 1 : 0;
+    g_fixed_span = c->gauss_fixed == 4 ? 5 : c->gauss_fixed == 7 ? 8 : 0;
     const int levels = c->levels < 2 ? 2 : c->levels;      /* popsift.cpp:86 */
     const float sigma0 = c->sigma;
     if (sigma0 > 2.0f) return -1;                           /* gauss_filter.cu:131 */
@@ -148,7 +152,14 @@ int orc_compute_tables(const orc_config* c, orc_tables* t)
         }
         g[0] = f[0];
     }
+    for (int lvl = 1; lvl < stages; lvl++) {                /* gauss_filter.cu:208-212 */
+        const float sigmaS = sigma0 * powf(2.0f, (float)(lvl) / (float)levels);
+        t->abs_oN.sigma[lvl] = sqrtf(sigmaS * sigmaS - sigma0 * sigma0);
+    }
+    for (int lvl = 0; lvl < ORC_GAUSS_LEVELS; lvl++)
+        blur_row(t->abs_oN.sigma[lvl], &t->abs_oN.span[lvl], &t->abs_oN.filter[lvl * ORC_GAUSS_ALIGN]);
     g_odd_spans = 0;
+    g_fixed_span = 0;
     t->peak_threshold = c->threshold * 0.5f * 255.0f / (float)levels; /* sift_conf.cu:276-279 */
     t->sigma_k = powf(2.0f, 1.0f / (float)levels);                    /* sift_constants.cu:27 */
     return 0;
@@ -393,6 +404,66 @@ static void interp_pass(const float* src, float* dst, int W, int H, const float*
     }
 }
 
+/* --gauss-mode fixed9 / fixed15 (s_pyramid_fixed.cu): every level is filtered VERTICALLY first, then horizontally (warp
+ * shuffles in the reference), with a fixed half width S = 4 / 7 and -- from the reference's SASS, all four kernels --
+ * this accumulation order: acc = pair_1 * f[1]; acc = fma(centre, f[0], acc); acc = fma(pair_i, f[i], acc) for i = 2..S. */
+static float fixed_acc(const float* v, const float* f, int S)
+{
+    float acc = (v[S - 1] + v[S + 1]) * f[1];
+    acc = fmaf(v[S], f[0], acc);
+    for (int i = 2; i <= S; i++) acc = fmaf(v[S - i] + v[S + i], f[i], acc);
+    return acc;
+}
+
+/* octave 0 (relativeTexAddress::octave_fixed, s_pyramid_fixed.cu:127-202): vertical taps are fetches of the input texture at
+ * ((col + tshift) * rcp(W), fma(-/+i, rcp(H), (row + tshift) * rcp(H))) -- products with the correctly rounded reciprocal,
+ * not divisions; columns left / right of the octave are fetched at their own (clamping) coordinates; result * 255 */
+static void fixed_octave0_level(const orc_ctx* c, const uint8_t* img, const float* fimg, float* dst, const float* f, int S)
+{
+    const int W = c->W[0], H = c->H[0];
+    const float mul_w = 1.0f / (float)W, mul_h = 1.0f / (float)H;
+    const float tshift = 0.5f * powf(2.0f, c->cfg.upscale);
+    const int VW = W + 2 * S;
+    float* V = (float*)malloc((size_t)VW * H * sizeof(float));
+    #pragma omp parallel for schedule(static)
+    for (int y = 0; y < H; y++) {
+        const float ypos = ((float)y + tshift) * mul_h;
+        for (int k = 0; k < VW; k++) {
+            const float xpos = ((float)(k - S) + tshift) * mul_w;
+            float v[2 * 7 + 1];
+            for (int i = -S; i <= S; i++) v[S + i] = tex_any(c, img, fimg, xpos, fmaf((float)i, mul_h, ypos));
+            V[(size_t)y * VW + k] = fixed_acc(v, f, S);
+        }
+    }
+    #pragma omp parallel for schedule(static)
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++)
+            dst[(size_t)y * W + x] = fixed_acc(&V[(size_t)y * VW + x], f, S) * 255.0f;
+    free(V);
+}
+
+/* octaves >= 1 (absoluteTexAddress::octave_fixed, s_pyramid_fixed.cu:46-120): levels 1.. from level 0 of the same octave,
+ * point texture with clamp addressing */
+static void fixed_octaveN_level(const float* src, float* dst, int W, int H, const float* f, int S)
+{
+    float* V = (float*)malloc((size_t)W * H * sizeof(float));
+    #pragma omp parallel for schedule(static)
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            float v[2 * 7 + 1];
+            for (int i = -S; i <= S; i++) v[S + i] = src[(size_t)clampi(y + i, 0, H - 1) * W + x];
+            V[(size_t)y * W + x] = fixed_acc(v, f, S);
+        }
+    #pragma omp parallel for schedule(static)
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            float v[2 * 7 + 1];
+            for (int i = -S; i <= S; i++) v[S + i] = V[(size_t)y * W + clampi(x + i, 0, W - 1)];
+            dst[(size_t)y * W + x] = fixed_acc(v, f, S);
+        }
+    free(V);
+}
+
 /* s_pyramid_build.cu:460-594, default arm :547-575, then make_dog :74-92 */
 static void build_pyramid(orc_ctx* c, const uint8_t* img, const float* fimg)
 {
@@ -405,7 +476,12 @@ static void build_pyramid(orc_ctx* c, const uint8_t* img, const float* fimg)
             float* dstp = c->gauss[o] + P * l;
             const float* g = &c->tab.inc.filter[l * ORC_GAUSS_ALIGN];
             const int span = c->tab.inc.span[l];
-            if (o == 0 && c->cfg.gauss_direct && c->cfg.scaling_mode != 1) {
+            if (c->cfg.gauss_fixed && c->cfg.scaling_mode != 1 && !(o > 0 && l == 0)) {
+                /* Fixed9 / Fixed15 (s_pyramid_build.cu:487-498): make_octave */
+                const int S = c->cfg.gauss_fixed;
+                if (o == 0) fixed_octave0_level(c, img, fimg, dstp, &c->tab.abs_o0.filter[l * ORC_GAUSS_ALIGN], S);
+                else        fixed_octaveN_level(c->gauss[o], dstp, W, H, &c->tab.abs_oN.filter[l * ORC_GAUSS_ALIGN], S);
+            } else if (o == 0 && c->cfg.gauss_direct && c->cfg.scaling_mode != 1) {
                 /* VLFeat_Relative_All, octave 0 (s_pyramid_build.cu:543-546): horiz_all_from_input_image + vert_all_abs0 */
                 const float* ga = &c->tab.abs_o0.filter[l * ORC_GAUSS_ALIGN];
                 level0_rows(c, img, fimg, interm, 0, l);

@@ -39,6 +39,7 @@ typedef struct orc_config {
     int32_t scaling_mode;     /* 0 = ScaleDefault, 1 = ScaleDirect (sift_conf.h; s_pyramid_build.cu:499-514) */
     int32_t gauss_direct;     /* 1 = --gauss-mode vlfeat-direct (VLFeat_Relative_All, s_pyramid_build.cu:543-546) */
     int32_t gauss_relative;   /* 1 = --gauss-mode relative / vlfeat-hw-interpolated (VLFeat_Relative, :515-542) */
+    int32_t gauss_fixed;      /* 4 = --gauss-mode fixed9, 7 = fixed15 (Fixed9 / Fixed15: s_pyramid_fixed.cu), 0 = off */
 } orc_config;
 
 typedef struct orc_gauss_table {
@@ -67,6 +68,7 @@ typedef struct orc_tables {
     /* the incremental rows transformed for hardware interpolation (gauss_filter.cu:372-405) */
     float   inc_ifilter[ORC_GAUSS_LEVELS * ORC_GAUSS_ALIGN];
     int32_t inc_ispan[ORC_GAUSS_LEVELS];
+    orc_gauss_table abs_oN;              /* gauss_filter.cu:200-214: levels >= 1 from level 0 of the same octave */
 } orc_tables;
 
 /* same layout as popsift::Feature (features.h:23-37), 72 bytes */

@@ -43,7 +43,8 @@ class PsGaussTables(C.Structure):
                 ("peak_threshold", C.c_float), ("sigma_k", C.c_float),
                 ("dd_filter", C.c_float * (20 * 32)), ("dd_sigma", C.c_float * 20), ("dd_span", C.c_int32 * 20),
                 ("abs_filter", C.c_float * (12 * 32)), ("abs_sigma", C.c_float * 12), ("abs_span", C.c_int32 * 12),
-                ("inc_ifilter", C.c_float * (12 * 32)), ("inc_ispan", C.c_int32 * 12)]
+                ("inc_ifilter", C.c_float * (12 * 32)), ("inc_ispan", C.c_int32 * 12),
+                ("absn_filter", C.c_float * (12 * 32)), ("absn_sigma", C.c_float * 12), ("absn_span", C.c_int32 * 12)]
 
 
 FEATURE_DTYPE = np.dtype([("octave", "<i4"), ("x", "<f4"), ("y", "<f4"), ("sigma", "<f4"), ("num_ori", "<i4"),

@@ -533,6 +533,58 @@ interp_pass_kernel(const float* __restrict__ src, float* __restrict__ dst, int W
     dst[(size_t)y * pitch + x] = __fmaf_rn(__ldg(src + (size_t)y * pitch + x), f.g[0], out);
 }
 
+// --gauss-mode fixed9 / fixed15 (reference s_pyramid_fixed.cu): every level is filtered VERTICALLY first, then horizontally,
+// with a fixed half width S = 4 / 7.  Accumulation order from the reference's SASS (all four octave_fixed kernels):
+// acc = pair_1 * f[1]; acc = fma(centre, f[0], acc); acc = fma(pair_i, f[i], acc) for i = 2..S.
+__device__ __forceinline__ float fixed_acc(const float* v /* 2S+1 values, centre at v[S] */, int stride, const Taps& f, int S)
+{
+    float acc = __fmul_rn(__fadd_rn(v[(S - 1) * stride], v[(S + 1) * stride]), f.g[1]);
+    acc = __fmaf_rn(v[S * stride], f.g[0], acc);
+    for (int i = 2; i <= S; ++i) acc = __fmaf_rn(__fadd_rn(v[(S - i) * stride], v[(S + i) * stride]), f.g[i], acc);
+    return acc;
+}
+
+// vertical pass of octave 0 (relativeTexAddress::octave_fixed_vert, s_pyramid_fixed.cu:127-146) for the virtual columns
+// -S .. W-1+S: fetches of the input texture at ((col + tshift) * rcp(W), fma(-/+i, rcp(H), (row + tshift) * rcp(H)))
+template <typename PIX>
+__global__ void __launch_bounds__(256)
+fixed_vert0_kernel(const PIX* __restrict__ img, size_t img_pitch, int w, int h, float tshift, float* __restrict__ V, int vpitch,
+                   int W, int H, Taps f, int S)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (k >= W + 2 * S || y >= H) return;
+    const float mul_w = __frcp_rn((float)W), mul_h = __frcp_rn((float)H);
+    const float xpos = __fmul_rn(__fadd_rn((float)(k - S), tshift), mul_w);
+    const float ypos = __fmul_rn(__fadd_rn((float)y, tshift), mul_h);
+    const TexAxis tx = tex_axis(xpos, w);
+    float v[2 * 7 + 1];
+    for (int i = -S; i <= S; ++i) v[S + i] = tex_fetch(img, img_pitch, tx, tex_axis(__fmaf_rn((float)i, mul_h, ypos), h));
+    V[(size_t)y * vpitch + k] = fixed_acc(v, 1, f, S);
+}
+
+// vertical pass of octaves >= 1 (absoluteTexAddress::octave_fixed_vert, s_pyramid_fixed.cu:46-66): from level 0 of the octave,
+// clamp addressing; also for the virtual columns -S .. W-1+S (= the clamped columns)
+__global__ void __launch_bounds__(256)
+fixed_vertN_kernel(const float* __restrict__ src, int pitch, float* __restrict__ V, int vpitch, int W, int H, Taps f, int S)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (k >= W + 2 * S || y >= H) return;
+    const int x = clampi(k - S, 0, W - 1);
+    float v[2 * 7 + 1];
+    for (int i = -S; i <= S; ++i) v[S + i] = __ldg(src + (size_t)clampi(y + i, 0, H - 1) * pitch + x);
+    V[(size_t)y * vpitch + k] = fixed_acc(v, 1, f, S);
+}
+
+// horizontal pass (octave_fixed_horiz, s_pyramid_fixed.cu:24-44: shuffles there, the row of vertical results here)
+__global__ void __launch_bounds__(256)
+fixed_horiz_kernel(const float* __restrict__ V, int vpitch, float* __restrict__ dst, int pitch, int W, int H, Taps f, int S, int times255)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W || y >= H) return;
+    const float out = fixed_acc(V + (size_t)y * vpitch + x, 1, f, S);
+    dst[(size_t)y * pitch + x] = times255 ? __fmul_rn(out, 255.0f) : out;
+}
+
 // --gauss-mode vlfeat-direct: level `level` of octave 0 straight from the input image with `taps` in both directions
 template <typename PIX>
 static int launch_level0_abs_any(const PIX* img, size_t img_pitch, int w, int h, float upscale, int sift_mode,
@@ -615,6 +667,37 @@ int launch_level0_rows_f32(const float* img, size_t img_pitch_floats, int w, int
                            const OctaveView& o0, float* dst, const GaussRow& dd, cudaStream_t st)
 {
     return launch_level0_rows_any<float>(img, img_pitch_floats, w, h, upscale, sift_mode, o0, dst, dd, st);
+}
+
+// --gauss-mode fixed9 / fixed15: one level of an octave; `scratch` holds (W + 2S rounded up to 32) x H floats
+int launch_fixed_level0_u8(const uint8_t* img, size_t img_pitch, int w, int h, float upscale, const OctaveView& o0, int level,
+                           const GaussRow& taps, int S, float* scratch, cudaStream_t st)
+{
+    const Taps t = make_taps(taps);
+    const int vpitch = (o0.w + 2 * S + 31) / 32 * 32;
+    dim3 gv((o0.w + 2 * S + 255) / 256, o0.h), gh((o0.w + 255) / 256, o0.h);
+    fixed_vert0_kernel<uint8_t><<<gv, 256, 0, st>>>(img, img_pitch, w, h, 0.5f * powf(2.0f, upscale), scratch, vpitch, o0.w, o0.h, t, S);
+    fixed_horiz_kernel<<<gh, 256, 0, st>>>(scratch, vpitch, o0.gauss + o0.plane * level, o0.pitch, o0.w, o0.h, t, S, 1);
+    return 2;
+}
+int launch_fixed_level0_f32(const float* img, size_t img_pitch_floats, int w, int h, float upscale, const OctaveView& o0, int level,
+                            const GaussRow& taps, int S, float* scratch, cudaStream_t st)
+{
+    const Taps t = make_taps(taps);
+    const int vpitch = (o0.w + 2 * S + 31) / 32 * 32;
+    dim3 gv((o0.w + 2 * S + 255) / 256, o0.h), gh((o0.w + 255) / 256, o0.h);
+    fixed_vert0_kernel<float><<<gv, 256, 0, st>>>(img, img_pitch_floats, w, h, 0.5f * powf(2.0f, upscale), scratch, vpitch, o0.w, o0.h, t, S);
+    fixed_horiz_kernel<<<gh, 256, 0, st>>>(scratch, vpitch, o0.gauss + o0.plane * level, o0.pitch, o0.w, o0.h, t, S, 1);
+    return 2;
+}
+int launch_fixed_levelN(const OctaveView& o, int level, const GaussRow& taps, int S, float* scratch, cudaStream_t st)
+{
+    const Taps t = make_taps(taps);
+    const int vpitch = (o.w + 2 * S + 31) / 32 * 32;
+    dim3 gv((o.w + 2 * S + 255) / 256, o.h), gh((o.w + 255) / 256, o.h);
+    fixed_vertN_kernel<<<gv, 256, 0, st>>>(o.gauss, o.pitch, scratch, vpitch, o.w, o.h, t, S);
+    fixed_horiz_kernel<<<gh, 256, 0, st>>>(scratch, vpitch, o.gauss + o.plane * level, o.pitch, o.w, o.h, t, S, 0);
+    return 2;
 }
 
 } // namespace psb

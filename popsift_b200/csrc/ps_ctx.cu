@@ -84,6 +84,7 @@ struct ps_ctx {
     GaussRow dd0;                         // first horizontal pass over the input image, octave 0
     GaussRow dd[kMaxOctaves];             // ... of every octave (Config::ScaleDirect)
     GaussRow abs0[PS_GAUSS_LEVELS];       // octave 0 from the input image, every level (--gauss-mode vlfeat-direct)
+    GaussRow absn[PS_GAUSS_LEVELS];       // levels >= 1 of an octave from its level 0 (--gauss-mode fixed9 / fixed15, octaves >= 1)
     GaussRow irows[PS_GAUSS_LEVELS];      // incremental rows transformed for interpolated fetches (--gauss-mode relative); span = i_span
     Consts k{};
     int max_w = 0, max_h = 0;
@@ -203,6 +204,31 @@ int run_pyramid(ps_ctx* ctx, Slot& s)
     int n = 0, r;
     // the pyramid kernels report the threshold-passing DoG samples when every scanned level runs on the
     // marching kernels (16-bit coordinates in the lists)
+    // --gauss-mode fixed9 / fixed15 (Fixed9 / Fixed15, s_pyramid_build.cu:487-498 + s_pyramid_fixed.cu): every level straight from
+    // the input image (octave 0) or from level 0 of its octave, vertical pass first, fixed half width 4 / 7
+    if (ctx->cfg.gauss_mode == PS_GAUSS_FIXED9 || ctx->cfg.gauss_mode == PS_GAUSS_FIXED15) {
+        const int S = ctx->cfg.gauss_mode == PS_GAUSS_FIXED9 ? 4 : 7;
+        if (direct) return ctx->fail(PS_ERR_ARG, "unsupported configuration: --gauss-mode fixed9 / fixed15 together with --direct-scaling");
+        if (L != 3) return ctx->fail(PS_ERR_ARG, "unsupported configuration: --gauss-mode fixed9 / fixed15 needs levels == 3 (reference s_pyramid_fixed.cu:271-289)");
+        s.view.cands_filled = 0;
+        for (int o = 0; o < s.num_octaves; ++o) {
+            const OctaveView& ov = s.view.oct[o];
+            if (o == 0) {
+                for (int l = 0; l < L + 3; ++l)
+                    n += s.is_float ? launch_fixed_level0_f32(reinterpret_cast<const float*>(s.d_img), (size_t)s.w, s.w, s.h, ctx->cfg.upscale, ov, l,
+                                                              ctx->abs0[l], S, s.d_interm, s.stream)
+                                    : launch_fixed_level0_u8(s.d_img, u8_pitch(s.w), s.w, s.h, ctx->cfg.upscale, ov, l, ctx->abs0[l], S,
+                                                             s.d_interm, s.stream);
+            } else {
+                n += launch_decimate(s.view.oct[o - 1], L, ov, s.stream);
+                for (int l = 1; l < L + 3; ++l) n += launch_fixed_levelN(ov, l, ctx->absn[l], S, s.d_interm, s.stream);
+            }
+            n += launch_dog_planes(ov, L + 2, s.stream);
+        }
+        ctx->launches += n;
+        PS_CUDA(ctx, cudaGetLastError());
+        return PS_OK;
+    }
     // --gauss-mode relative / vlfeat-hw-interpolated (VLFeat_Relative, s_pyramid_build.cu:515-542): every pass merges pairs of
     // taps into interpolated fetches; simple per-pixel kernels (k_pyramid.cu), DoG and decimation by their own kernels, dense
     // extrema scan.  (Under ScaleDirect the reference's direct-scaling arm applies, with interpolated passes: not built.)
@@ -533,6 +559,11 @@ extern "C" ps_ctx* ps_create(int device, const ps_config* cfg, int max_w, int ma
             why = "ps_create: bad descriptor mode";
         else if (ctx->cfg.scaling_mode != PS_SCALE_DEFAULT && ctx->cfg.scaling_mode != PS_SCALE_DIRECT)
             why = "ps_create: bad scaling mode";
+        else if (ctx->cfg.scaling_mode == PS_SCALE_DIRECT &&
+                 (ctx->cfg.gauss_mode == PS_GAUSS_VLFEAT_RELATIVE || ctx->cfg.gauss_mode == PS_GAUSS_FIXED9 || ctx->cfg.gauss_mode == PS_GAUSS_FIXED15))
+            why = "ps_create: unsupported configuration: --direct-scaling together with --gauss-mode relative / fixed9 / fixed15 is not implemented";
+        else if ((ctx->cfg.gauss_mode == PS_GAUSS_FIXED9 || ctx->cfg.gauss_mode == PS_GAUSS_FIXED15) && std::max(2, ctx->cfg.levels) != 3)
+            why = "ps_create: unsupported configuration: --gauss-mode fixed9 / fixed15 needs levels == 3 (reference s_pyramid_fixed.cu:271-289)";
         else if (ctx->cfg.sift_mode != PS_MODE_POPSIFT && ctx->cfg.sift_mode != PS_MODE_OPENCV && ctx->cfg.sift_mode != PS_MODE_VLFEAT)
             why = "ps_create: bad sift mode";
         else if (ctx->cfg.filter_max_extrema > 0 && !kGridFilterBuilt)
@@ -543,7 +574,7 @@ extern "C" ps_ctx* ps_create(int device, const ps_config* cfg, int max_w, int ma
     }
     if (ps_gauss_tables_compute(&ctx->cfg, &ctx->tab) != PS_OK) {
         delete ctx;
-        return bail("ps_create: unsupported configuration (sigma > 2.0, levels > 12, or --gauss-mode fixed9 / fixed15)", cudaSuccess);
+        return bail("ps_create: unsupported configuration (sigma > 2.0 or levels > 12)", cudaSuccess);
     }
     for (int l = 0; l < PS_GAUSS_LEVELS; ++l) {
         std::memcpy(ctx->rows[l].tap, &ctx->tab.inc_filter[l * PS_GAUSS_ALIGN], sizeof(float) * PS_GAUSS_ALIGN);
@@ -560,6 +591,8 @@ extern "C" ps_ctx* ps_create(int device, const ps_config* cfg, int max_w, int ma
         ctx->abs0[l].span = ctx->tab.abs_span[l];
         std::memcpy(ctx->irows[l].tap, &ctx->tab.inc_ifilter[l * PS_GAUSS_ALIGN], sizeof(float) * PS_GAUSS_ALIGN);
         ctx->irows[l].span = ctx->tab.inc_ispan[l];
+        std::memcpy(ctx->absn[l].tap, &ctx->tab.absn_filter[l * PS_GAUSS_ALIGN], sizeof(float) * PS_GAUSS_ALIGN);
+        ctx->absn[l].span = ctx->tab.absn_span[l];
     }
     ctx->max_w = max_w; ctx->max_h = max_h;
     int32_t W[kMaxOctaves], H[kMaxOctaves];
@@ -595,7 +628,7 @@ extern "C" ps_ctx* ps_create(int device, const ps_config* cfg, int max_w, int ma
         PS_TRY(cudaHostAlloc(&s.h_img, (size_t)max_w * max_h * 4, cudaHostAllocDefault));
         PS_TRY(cudaMalloc(&s.d_planes, planes * sizeof(float)));
         s.planes_floats = planes;
-        if (ctx->cfg.gauss_mode == PS_GAUSS_VLFEAT_RELATIVE) {
+        if (ctx->cfg.gauss_mode == PS_GAUSS_VLFEAT_RELATIVE || ctx->cfg.gauss_mode == PS_GAUSS_FIXED9 || ctx->cfg.gauss_mode == PS_GAUSS_FIXED15) {
             int32_t W0[kMaxOctaves], H0[kMaxOctaves];
             ps_geometry(&ctx->cfg, max_w, max_h, W0, H0);
             PS_TRY(cudaMalloc(&s.d_interm, sizeof(float) * (size_t)((W0[0] + 31) / 32 * 32 + 32) * (size_t)H0[0]));

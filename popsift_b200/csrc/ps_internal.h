@@ -133,6 +133,12 @@ int launch_level0_rows_u8(const uint8_t* img, size_t img_pitch, int w, int h, fl
                           const OctaveView& o0, float* dst, const GaussRow& dd, cudaStream_t st);
 int launch_level0_rows_f32(const float* img, size_t img_pitch_floats, int w, int h, float upscale, int sift_mode,
                            const OctaveView& o0, float* dst, const GaussRow& dd, cudaStream_t st);
+// --gauss-mode fixed9 / fixed15 (s_pyramid_fixed.cu): one level of octave 0 from the input image / of an octave >= 1 from its level 0
+int launch_fixed_level0_u8(const uint8_t* img, size_t img_pitch, int w, int h, float upscale, const OctaveView& o0, int level,
+                           const GaussRow& taps, int S, float* scratch, cudaStream_t st);
+int launch_fixed_level0_f32(const float* img, size_t img_pitch_floats, int w, int h, float upscale, const OctaveView& o0, int level,
+                            const GaussRow& taps, int S, float* scratch, cudaStream_t st);
+int launch_fixed_levelN(const OctaveView& o, int level, const GaussRow& taps, int S, float* scratch, cudaStream_t st);
 int launch_interp_pass(const float* src, float* dst, int W, int H, int pitch, const GaussRow& f, int ispan, int along_x, cudaStream_t st);
 int launch_decimate(const OctaveView& prev, int level, const OctaveView& next, cudaStream_t st);
 // level l >= 1 of one octave: blur level l-1 -> level l, DoG[l-1] = G[l]-G[l-1]; if next0 != nullptr

@@ -20,6 +20,8 @@ namespace {
 // vlfeat-hw-interpolated: the taps are consumed in pairs, gauss_filter.cu:309-319)
 int kernel_span(float sigma, int mode)
 {
+    if (mode == 3) return 5;     // --gauss-mode fixed9  (gauss_filter.cu:289-290)
+    if (mode == 4) return 8;     // --gauss-mode fixed15 (gauss_filter.cu:291-292)
     const bool opencv = mode == 1;
     if (opencv) {
         int span = static_cast<int>(std::roundf(2.0f * 4.0f * sigma + 1.0f)) | 1;
@@ -86,9 +88,11 @@ extern "C" int ps_gauss_tables_compute(const ps_config* cfg, ps_gauss_tables* ou
     if (s0 > 2.0f) return PS_ERR_ARG;                 // reference gauss_filter.cu:131-137
     if (levels > PS_GAUSS_LEVELS) return PS_ERR_ARG;  // reference gauss_filter.cu:138-144
     if (cfg->gauss_mode != PS_GAUSS_VLFEAT_COMPUTE && cfg->gauss_mode != PS_GAUSS_OPENCV_COMPUTE &&
-        cfg->gauss_mode != PS_GAUSS_VLFEAT_RELATIVE_ALL && cfg->gauss_mode != PS_GAUSS_VLFEAT_RELATIVE) return PS_ERR_ARG;
-    // span rule (gauss_filter.cu:274-296): RELATIVE_ALL uses the vlfeat rule, RELATIVE the odd one
-    const int ocv = cfg->gauss_mode == PS_GAUSS_OPENCV_COMPUTE ? 1 : cfg->gauss_mode == PS_GAUSS_VLFEAT_RELATIVE ? 2 : 0;
+        cfg->gauss_mode != PS_GAUSS_VLFEAT_RELATIVE_ALL && cfg->gauss_mode != PS_GAUSS_VLFEAT_RELATIVE &&
+        cfg->gauss_mode != PS_GAUSS_FIXED9 && cfg->gauss_mode != PS_GAUSS_FIXED15) return PS_ERR_ARG;
+    // span rule (gauss_filter.cu:274-296): RELATIVE_ALL uses the vlfeat rule, RELATIVE the odd one, FIXED9 / FIXED15 constants
+    const int ocv = cfg->gauss_mode == PS_GAUSS_OPENCV_COMPUTE ? 1 : cfg->gauss_mode == PS_GAUSS_VLFEAT_RELATIVE ? 2 :
+                    cfg->gauss_mode == PS_GAUSS_FIXED9 ? 3 : cfg->gauss_mode == PS_GAUSS_FIXED15 ? 4 : 0;
     const int planes = levels + 3;
     const float blur_in = cfg->has_initial_blur ? cfg->initial_blur * std::pow(2.0f, cfg->upscale) : 0.0f;
 
@@ -124,6 +128,14 @@ extern "C" int ps_gauss_tables_compute(const ps_config* cfg, ps_gauss_tables* ou
     }
     for (int l = 0; l < PS_GAUSS_LEVELS; ++l)
         fill_kernel(out->abs_sigma[l], &out->abs_filter[l * PS_GAUSS_ALIGN], &out->abs_span[l], ocv);
+    // levels 1.. of any octave straight from its level 0 (gauss_filter.cu:208-214): sqrt((sigma0 2^(l/L))^2 - sigma0^2); used by
+    // the fixed-span modes for octaves >= 1
+    for (int l = 1; l < planes; ++l) {
+        const float ss = s0 * std::pow(2.0f, static_cast<float>(l) / static_cast<float>(levels));
+        out->absn_sigma[l] = std::sqrt(ss * ss - s0 * s0);
+    }
+    for (int l = 0; l < PS_GAUSS_LEVELS; ++l)
+        fill_kernel(out->absn_sigma[l], &out->absn_filter[l * PS_GAUSS_ALIGN], &out->absn_span[l], ocv);
     // pairs of taps merged into one linearly interpolated fetch (GaussTable::transformBlurTable, gauss_filter.cu:372-405):
     // odd entries = the fraction u = a / (a + b), even entries = the weight v = a + b of the pair
     for (int l = 0; l < PS_GAUSS_LEVELS; ++l) {

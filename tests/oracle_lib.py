@@ -24,7 +24,7 @@ class OrcConfig(C.Structure):
                 ("edge_limit", C.c_float), ("threshold", C.c_float), ("upscale", C.c_float),
                 ("initial_blur", C.c_float), ("has_initial_blur", C.c_int32),
                 ("sift_mode", C.c_int32), ("norm_mode", C.c_int32), ("norm_multi", C.c_int32),
-                ("max_extrema", C.c_int32), ("scaling_mode", C.c_int32), ("gauss_direct", C.c_int32), ("gauss_relative", C.c_int32)]
+                ("max_extrema", C.c_int32), ("scaling_mode", C.c_int32), ("gauss_direct", C.c_int32), ("gauss_relative", C.c_int32), ("gauss_fixed", C.c_int32)]
 
 
 class OrcGaussTable(C.Structure):
@@ -35,7 +35,8 @@ class OrcTables(C.Structure):
     _fields_ = [("inc", OrcGaussTable), ("dd_filter0", C.c_float * 32), ("dd_sigma0", C.c_float),
                 ("dd_span0", C.c_int32), ("peak_threshold", C.c_float), ("sigma_k", C.c_float),
                 ("dd_filter", C.c_float * (20 * 32)), ("dd_sigma", C.c_float * 20), ("dd_span", C.c_int32 * 20),
-                ("abs_o0", OrcGaussTable), ("inc_ifilter", C.c_float * (12 * 32)), ("inc_ispan", C.c_int32 * 12)]
+                ("abs_o0", OrcGaussTable), ("inc_ifilter", C.c_float * (12 * 32)), ("inc_ispan", C.c_int32 * 12),
+                ("abs_oN", OrcGaussTable)]
 
 
 FEATURE_DTYPE = np.dtype([("octave", "<i4"), ("x", "<f4"), ("y", "<f4"), ("sigma", "<f4"),

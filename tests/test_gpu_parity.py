@@ -522,7 +522,8 @@ def test_grid_filter_1280_and_unsupported_options_are_refused():
     assert feats.getFeatureCount() == len(z["feat"]) and feats.getDescriptorCount() == int(z["n_desc"][0])
     ps.uninit()
     # options whose numerics are not implemented are refused, never silently computed with the default path
-    for setter in (lambda c: c.setGaussMode("fixed9"), lambda c: c.setGaussMode("fixed15")):
+    for setter in (lambda c: (c.setGaussMode("fixed9"), c.setLevels(4)), lambda c: (c.setGaussMode("relative"), c.setScalingMode(0)),
+                   lambda c: (c.setGaussMode("fixed15"), c.setScalingMode(0))):
         c = mk_cfg()
         setter(c)
         with pytest.raises(api.PopSiftError):
@@ -860,4 +861,51 @@ def test_gauss_mode_relative_vs_oracle_and_live_reference(tmp_path):
         assert (feats.getFeatureCount(), feats.getDescriptorCount()) == (len(rf), len(rd))
         r = compare.report(*feats.keypoints(), *ol.flatten(rf, rd))
         assert r["f1"] >= F1_MIN and r["desc_l2_max"] < L2_MAX, r
+    ps.uninit()
+
+
+@pytest.mark.parametrize("name,S", [("fixed9", 4), ("fixed15", 7)])
+def test_gauss_mode_fixed_vs_oracle_and_live_reference(tmp_path, name, S):
+    """--gauss-mode fixed9 / fixed15 (Config::Fixed9 / Fixed15; reference s_pyramid_fixed.cu): every level filtered vertically
+    first, then horizontally, with a fixed half width of 4 / 7 taps and the accumulation order of the reference's SASS; octave
+    0 straight from the input texture (products with the rounded reciprocal of the extent), octaves >= 1 from their level 0.
+    Planes bit-exact against the oracle and against the live reference's --log dumps, same features."""
+    w, h = 640, 480
+    img = make_frame(w, h, 37)
+    cfg = mk_cfg("vlfeat", "classic")
+    cfg.setGaussMode(name)
+    ps, feats = run_gpu(img, cfg)
+    o = ol.Oracle(ol.make_config(mode="vlfeat", norm="classic", gauss_fixed=S), w, h)
+    o.run(img)
+    bad = []
+    for oc in range(o.num_octaves):
+        for l in range(6):
+            if not np.array_equal(ps.plane(0, oc, l), o.gauss(oc, l)):
+                bad.append(("g", oc, l, int((ps.plane(0, oc, l) != o.gauss(oc, l)).sum())))
+        for l in range(5):
+            if not np.array_equal(ps.plane(0, oc, l, dog=True), o.dog(oc, l)):
+                bad.append(("d", oc, l))
+    assert not bad, bad
+    of, od = o.features()
+    assert (feats.getFeatureCount(), feats.getDescriptorCount()) == (len(of), len(od))
+    o.close()
+    if os.path.exists(REF):
+        write_pgm(str(tmp_path / "f.pgm"), img)
+        subprocess.run([REF, "-i", "f.pgm", "-o", "f.bin", "--log", "--mode", "vlfeat", "--norm", "classic", "--gauss-mode", name],
+                       cwd=str(tmp_path), check=True, capture_output=True)
+        refbad = []
+        for oc in range(3):
+            for l in range(6):
+                ref = ol.read_ref_dump(str(tmp_path / "dir-octave-dump" / ("pyramid-o-%d-l-%d.dump" % (oc, l))))
+                mine = ps.plane(0, oc, l)
+                if not np.array_equal(ref, mine):
+                    d = ref != mine
+                    ys, xs = np.nonzero(d)
+                    refbad.append((oc, l, int(d.sum()), float(np.abs(ref - mine).max()), (int(xs.min()), int(xs.max())), (int(ys.min()), int(ys.max()))))
+        assert not refbad, refbad
+        rf, rd = ol.read_ref_features(str(tmp_path / "f.bin"))
+        assert (feats.getFeatureCount(), feats.getDescriptorCount()) == (len(rf), len(rd))
+        if len(rd):
+            r = compare.report(*feats.keypoints(), *ol.flatten(rf, rd))
+            assert r["f1"] >= F1_MIN and r["desc_l2_max"] < L2_MAX, r
     ps.uninit()

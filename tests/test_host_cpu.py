@@ -34,7 +34,8 @@ def test_struct_sizes_match_reference_layouts():
 
 
 CFGS = [dict(), dict(downsampling=0), dict(levels=4), dict(sigma=1.2, levels=5), dict(initial_blur=0.0),
-        dict(downsampling=-2), dict(levels=2, sigma=2.0), dict(gauss_relative=1), dict(gauss_relative=1, levels=4, sigma=1.3)]
+        dict(downsampling=-2), dict(levels=2, sigma=2.0), dict(gauss_relative=1), dict(gauss_relative=1, levels=4, sigma=1.3),
+        dict(gauss_fixed=4), dict(gauss_fixed=7)]
 
 
 def _mk(kw):
@@ -50,6 +51,8 @@ def _mk(kw):
         c.setInitialBlur(o["initial_blur"])
     if o.get("gauss_relative"):
         c.setGaussMode("relative")
+    if o.get("gauss_fixed"):
+        c.setGaussMode("fixed9" if o["gauss_fixed"] == 4 else "fixed15")
     oc = ol.make_config(**{k: v for k, v in kw.items() if k != "initial_blur"})
     if "initial_blur" in kw:
         oc.initial_blur = kw["initial_blur"]
@@ -72,6 +75,9 @@ def test_gauss_tables_bit_identical_to_oracle(kw):
     assert list(t.dd_span) == list(ot.dd_span) and t.dd_span[0] == t.dd_span0
     assert np.array_equal(np.frombuffer(t.dd_filter, np.uint32), np.frombuffer(ot.dd_filter, np.uint32))
     assert np.array_equal(np.frombuffer(t.dd_filter, np.uint32)[:32], np.frombuffer(t.dd_filter0, np.uint32))
+    # levels >= 1 from level 0 of the same octave (--gauss-mode fixed9 / fixed15)
+    assert list(t.absn_span) == list(ot.abs_oN.span)
+    assert np.array_equal(np.frombuffer(t.absn_filter, np.uint32), np.frombuffer(ot.abs_oN.filter, np.uint32))
     # the rows transformed for interpolated fetches (--gauss-mode relative)
     assert list(t.inc_ispan) == list(ot.inc_ispan)
     assert np.array_equal(np.frombuffer(t.inc_ifilter, np.uint32), np.frombuffer(ot.inc_ifilter, np.uint32))
