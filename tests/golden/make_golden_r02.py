@@ -162,6 +162,12 @@ def main(src):
         o = np.frombuffer(data, np.float32, n, 16 + 8 * n)
         sel = np.r_[np.arange(0, 17 * 8192, 5), np.arange(17 * 8192, n, 3)]
         np.savez_compressed(os.path.join(HERE, "texture_lcoords.npz"), W=np.int32(W), H=np.int32(H), xy=q[sel], out=o[sel])
+    # --gauss-mode fixed9 / fixed15 (tools/gpu_round2_u.sh)
+    for m in ("fixed9", "fixed15"):
+        save_feat(src, "ref_%s_f256.bin" % m, "f256_%s" % m)
+        fn = os.path.join(src, "ref_%s_f256_planes.json" % m)
+        if os.path.exists(fn):
+            json.dump(json.load(open(fn)), open(os.path.join(HERE, "planes_f256_%s.json" % m), "w"), indent=0)
     # --gauss-mode vlfeat-direct (tools/gpu_round2_r.sh)
     save_feat(src, "ref_vlfeat_direct_f256.bin", "f256_vlfeat_direct")
     fn = os.path.join(src, "ref_vlfeat_direct_f256_planes.json")
