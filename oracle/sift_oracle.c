@@ -476,7 +476,7 @@ static void build_pyramid(orc_ctx* c, const uint8_t* img, const float* fimg)
             float* dstp = c->gauss[o] + P * l;
             const float* g = &c->tab.inc.filter[l * ORC_GAUSS_ALIGN];
             const int span = c->tab.inc.span[l];
-            if (c->cfg.gauss_fixed && c->cfg.scaling_mode != 1 && !(o > 0 && l == 0)) {
+            if (c->cfg.gauss_fixed && !(o > 0 && l == 0)) {
                 /* Fixed9 / Fixed15 (s_pyramid_build.cu:487-498): make_octave */
                 const int S = c->cfg.gauss_fixed;
                 if (o == 0) fixed_octave0_level(c, img, fimg, dstp, &c->tab.abs_o0.filter[l * ORC_GAUSS_ALIGN], S);
@@ -486,13 +486,13 @@ static void build_pyramid(orc_ctx* c, const uint8_t* img, const float* fimg)
                 const float* ga = &c->tab.abs_o0.filter[l * ORC_GAUSS_ALIGN];
                 level0_rows(c, img, fimg, interm, 0, l);
                 cols_pass(interm, dstp, W, H, ga, c->tab.abs_o0.span[l]);
-            } else if (c->cfg.gauss_relative && c->cfg.scaling_mode != 1 && !(l == 0 && o > 0)) {
+            } else if (c->cfg.gauss_relative && !(l == 0 && o > 0 && c->cfg.scaling_mode != 1)) {
                 /* VLFeat_Relative (s_pyramid_build.cu:515-542): interpolated passes with the transformed incremental row */
                 const float* fi = &c->tab.inc_ifilter[l * ORC_GAUSS_ALIGN];
                 const int ispan = c->tab.inc_ispan[l];
                 if (l == 0) {
                     float* tmp = (float*)malloc(P * sizeof(float));
-                    level0_rows(c, img, fimg, tmp, 0, -1);
+                    level0_rows(c, img, fimg, tmp, o, -1);      /* o > 0 only under ScaleDirect (s_pyramid_build.cu:499-508) */
                     interp_pass(tmp, dstp, W, H, fi, ispan, 0);
                     free(tmp);
                 } else {

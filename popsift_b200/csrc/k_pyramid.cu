@@ -639,10 +639,10 @@ int launch_interp_pass(const float* src, float* dst, int W, int H, int pitch, co
 // rows of octave 0 straight from the input image (the first horizontal pass alone) into `dst` (pitch of the octave)
 template <typename PIX>
 static int launch_level0_rows_any(const PIX* img, size_t img_pitch, int w, int h, float upscale, int sift_mode,
-                                  const OctaveView& o0, float* dst, const GaussRow& dd, cudaStream_t st)
+                                  const OctaveView& o0, float* dst, const GaussRow& dd, cudaStream_t st, int octave)
 {
     float shift = 0.5f;
-    if (sift_mode == PS_MODE_POPSIFT || sift_mode == PS_MODE_VLFEAT) shift = 0.5f * powf(2.0f, upscale);
+    if (octave == 0 && (sift_mode == PS_MODE_POPSIFT || sift_mode == PS_MODE_VLFEAT)) shift = 0.5f * powf(2.0f, upscale);
     const int R = dd.span - 1;
     if (R < 0 || R >= PS_GAUSS_ALIGN) return -1;
     const Taps t = make_taps(dd);
@@ -659,14 +659,14 @@ static int launch_level0_rows_any(const PIX* img, size_t img_pitch, int w, int h
     return 1;
 }
 int launch_level0_rows_u8(const uint8_t* img, size_t img_pitch, int w, int h, float upscale, int sift_mode,
-                          const OctaveView& o0, float* dst, const GaussRow& dd, cudaStream_t st)
+                          const OctaveView& o0, float* dst, const GaussRow& dd, cudaStream_t st, int octave)
 {
-    return launch_level0_rows_any<uint8_t>(img, img_pitch, w, h, upscale, sift_mode, o0, dst, dd, st);
+    return launch_level0_rows_any<uint8_t>(img, img_pitch, w, h, upscale, sift_mode, o0, dst, dd, st, octave);
 }
 int launch_level0_rows_f32(const float* img, size_t img_pitch_floats, int w, int h, float upscale, int sift_mode,
-                           const OctaveView& o0, float* dst, const GaussRow& dd, cudaStream_t st)
+                           const OctaveView& o0, float* dst, const GaussRow& dd, cudaStream_t st, int octave)
 {
-    return launch_level0_rows_any<float>(img, img_pitch_floats, w, h, upscale, sift_mode, o0, dst, dd, st);
+    return launch_level0_rows_any<float>(img, img_pitch_floats, w, h, upscale, sift_mode, o0, dst, dd, st, octave);
 }
 
 // --gauss-mode fixed9 / fixed15: one level of an octave; `scratch` holds (W + 2S rounded up to 32) x H floats

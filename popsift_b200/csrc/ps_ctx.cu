@@ -208,7 +208,6 @@ int run_pyramid(ps_ctx* ctx, Slot& s)
     // the input image (octave 0) or from level 0 of its octave, vertical pass first, fixed half width 4 / 7
     if (ctx->cfg.gauss_mode == PS_GAUSS_FIXED9 || ctx->cfg.gauss_mode == PS_GAUSS_FIXED15) {
         const int S = ctx->cfg.gauss_mode == PS_GAUSS_FIXED9 ? 4 : 7;
-        if (direct) return ctx->fail(PS_ERR_ARG, "unsupported configuration: --gauss-mode fixed9 / fixed15 together with --direct-scaling");
         if (L != 3) return ctx->fail(PS_ERR_ARG, "unsupported configuration: --gauss-mode fixed9 / fixed15 needs levels == 3 (reference s_pyramid_fixed.cu:271-289)");
         s.view.cands_filled = 0;
         for (int o = 0; o < s.num_octaves; ++o) {
@@ -220,7 +219,17 @@ int run_pyramid(ps_ctx* ctx, Slot& s)
                                     : launch_fixed_level0_u8(s.d_img, u8_pitch(s.w), s.w, s.h, ctx->cfg.upscale, ov, l, ctx->abs0[l], S,
                                                              s.d_interm, s.stream);
             } else {
-                n += launch_decimate(s.view.oct[o - 1], L, ov, s.stream);
+                if (direct) {
+                    // ScaleDirect (s_pyramid_build.cu:478-486): level 0 straight from the input image (rows dd[o], columns inc[0])
+                    r = s.is_float ? launch_level0_f32(reinterpret_cast<const float*>(s.d_img), (size_t)s.w, s.w, s.h, ctx->cfg.upscale,
+                                                       ctx->cfg.sift_mode, ov, ctx->dd[o], ctx->rows[0], s.stream, o)
+                                   : launch_level0_u8(s.d_img, u8_pitch(s.w), s.w, s.h, ctx->cfg.upscale, ctx->cfg.sift_mode, ov,
+                                                      ctx->dd[o], ctx->rows[0], s.stream, o);
+                    if (r < 0) return ctx->fail(PS_ERR_ARG, "unsupported level-0 filter span %d (octave %d)", ctx->dd[o].span, o);
+                    n += r;
+                } else {
+                    n += launch_decimate(s.view.oct[o - 1], L, ov, s.stream);
+                }
                 for (int l = 1; l < L + 3; ++l) n += launch_fixed_levelN(ov, l, ctx->absn[l], S, s.d_interm, s.stream);
             }
             n += launch_dog_planes(ov, L + 2, s.stream);
@@ -231,20 +240,20 @@ int run_pyramid(ps_ctx* ctx, Slot& s)
     }
     // --gauss-mode relative / vlfeat-hw-interpolated (VLFeat_Relative, s_pyramid_build.cu:515-542): every pass merges pairs of
     // taps into interpolated fetches; simple per-pixel kernels (k_pyramid.cu), DoG and decimation by their own kernels, dense
-    // extrema scan.  (Under ScaleDirect the reference's direct-scaling arm applies, with interpolated passes: not built.)
+    // extrema scan.
     if (ctx->cfg.gauss_mode == PS_GAUSS_VLFEAT_RELATIVE) {
-        if (direct) return ctx->fail(PS_ERR_ARG, "unsupported configuration: --gauss-mode relative together with --direct-scaling");
         s.view.cands_filled = 0;
         for (int o = 0; o < s.num_octaves; ++o) {
             const OctaveView& ov = s.view.oct[o];
-            if (o == 0) {
+            if (o == 0 || direct) {
+                // (ScaleDirect, s_pyramid_build.cu:499-508: level 0 of every octave from the input image, dd row of the octave)
                 if (s.is_float)
                     r = launch_level0_rows_f32(reinterpret_cast<const float*>(s.d_img), (size_t)s.w, s.w, s.h, ctx->cfg.upscale,
-                                               ctx->cfg.sift_mode, ov, s.d_interm, ctx->dd0, s.stream);
+                                               ctx->cfg.sift_mode, ov, s.d_interm, ctx->dd[o], s.stream, o);
                 else
                     r = launch_level0_rows_u8(s.d_img, u8_pitch(s.w), s.w, s.h, ctx->cfg.upscale, ctx->cfg.sift_mode, ov, s.d_interm,
-                                              ctx->dd0, s.stream);
-                if (r < 0) return ctx->fail(PS_ERR_ARG, "unsupported level-0 filter span %d", ctx->dd0.span);
+                                              ctx->dd[o], s.stream, o);
+                if (r < 0) return ctx->fail(PS_ERR_ARG, "unsupported level-0 filter span %d (octave %d)", ctx->dd[o].span, o);
                 n += r;
                 n += launch_interp_pass(s.d_interm, ov.gauss, ov.w, ov.h, ov.pitch, ctx->irows[0], ctx->irows[0].span, 0, s.stream);
             } else {
@@ -559,9 +568,6 @@ extern "C" ps_ctx* ps_create(int device, const ps_config* cfg, int max_w, int ma
             why = "ps_create: bad descriptor mode";
         else if (ctx->cfg.scaling_mode != PS_SCALE_DEFAULT && ctx->cfg.scaling_mode != PS_SCALE_DIRECT)
             why = "ps_create: bad scaling mode";
-        else if (ctx->cfg.scaling_mode == PS_SCALE_DIRECT &&
-                 (ctx->cfg.gauss_mode == PS_GAUSS_VLFEAT_RELATIVE || ctx->cfg.gauss_mode == PS_GAUSS_FIXED9 || ctx->cfg.gauss_mode == PS_GAUSS_FIXED15))
-            why = "ps_create: unsupported configuration: --direct-scaling together with --gauss-mode relative / fixed9 / fixed15 is not implemented";
         else if ((ctx->cfg.gauss_mode == PS_GAUSS_FIXED9 || ctx->cfg.gauss_mode == PS_GAUSS_FIXED15) && std::max(2, ctx->cfg.levels) != 3)
             why = "ps_create: unsupported configuration: --gauss-mode fixed9 / fixed15 needs levels == 3 (reference s_pyramid_fixed.cu:271-289)";
         else if (ctx->cfg.sift_mode != PS_MODE_POPSIFT && ctx->cfg.sift_mode != PS_MODE_OPENCV && ctx->cfg.sift_mode != PS_MODE_VLFEAT)

@@ -130,9 +130,9 @@ int launch_level0_abs_f32(const float* img, size_t img_pitch_floats, int w, int 
 int launch_dog_planes(const OctaveView& o, int nplanes, cudaStream_t st);
 // --gauss-mode relative (VLFeat_Relative): the first horizontal pass alone, and one interpolated pass over a plane
 int launch_level0_rows_u8(const uint8_t* img, size_t img_pitch, int w, int h, float upscale, int sift_mode,
-                          const OctaveView& o0, float* dst, const GaussRow& dd, cudaStream_t st);
+                          const OctaveView& o0, float* dst, const GaussRow& dd, cudaStream_t st, int octave = 0);
 int launch_level0_rows_f32(const float* img, size_t img_pitch_floats, int w, int h, float upscale, int sift_mode,
-                           const OctaveView& o0, float* dst, const GaussRow& dd, cudaStream_t st);
+                           const OctaveView& o0, float* dst, const GaussRow& dd, cudaStream_t st, int octave = 0);
 // --gauss-mode fixed9 / fixed15 (s_pyramid_fixed.cu): one level of octave 0 from the input image / of an octave >= 1 from its level 0
 int launch_fixed_level0_u8(const uint8_t* img, size_t img_pitch, int w, int h, float upscale, const OctaveView& o0, int level,
                            const GaussRow& taps, int S, float* scratch, cudaStream_t st);

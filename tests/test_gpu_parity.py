@@ -522,8 +522,7 @@ def test_grid_filter_1280_and_unsupported_options_are_refused():
     assert feats.getFeatureCount() == len(z["feat"]) and feats.getDescriptorCount() == int(z["n_desc"][0])
     ps.uninit()
     # options whose numerics are not implemented are refused, never silently computed with the default path
-    for setter in (lambda c: (c.setGaussMode("fixed9"), c.setLevels(4)), lambda c: (c.setGaussMode("relative"), c.setScalingMode(0)),
-                   lambda c: (c.setGaussMode("fixed15"), c.setScalingMode(0))):
+    for setter in (lambda c: (c.setGaussMode("fixed9"), c.setLevels(4)), lambda c: (c.setGaussMode("fixed15"), c.setLevels(2))):
         c = mk_cfg()
         setter(c)
         with pytest.raises(api.PopSiftError):
@@ -908,4 +907,39 @@ def test_gauss_mode_fixed_vs_oracle_and_live_reference(tmp_path, name, S):
         if len(rd):
             r = compare.report(*feats.keypoints(), *ol.flatten(rf, rd))
             assert r["f1"] >= F1_MIN and r["desc_l2_max"] < L2_MAX, r
+    ps.uninit()
+
+
+@pytest.mark.parametrize("name,okw", [("relative", dict(gauss_relative=1)), ("fixed9", dict(gauss_fixed=4)), ("fixed15", dict(gauss_fixed=7)),
+                                      ("vlfeat-direct", dict(gauss_direct=1))])
+def test_direct_scaling_with_every_gauss_mode(tmp_path, name, okw):
+    """--direct-scaling combined with the other Gauss modes (the ScaleDirect arms of build_pyramid, s_pyramid_build.cu:478-514:
+    level 0 of every octave from the input image, then the mode's own passes; under vlfeat-direct the direct-scaling arm wins).
+    Planes bit-exact against the oracle and the live reference, same features."""
+    w, h = 512, 384
+    img = make_frame(w, h, 39)
+    cfg = mk_cfg("vlfeat", "classic")
+    cfg.setGaussMode(name)
+    cfg.setScalingMode(0)
+    ps, feats = run_gpu(img, cfg)
+    o = ol.Oracle(ol.make_config(mode="vlfeat", norm="classic", scaling_mode=1, **okw), w, h)
+    o.run(img)
+    bad = [("g", oc, l) for oc in range(o.num_octaves) for l in range(6) if not np.array_equal(ps.plane(0, oc, l), o.gauss(oc, l))]
+    assert not bad, bad
+    of, od = o.features()
+    assert (feats.getFeatureCount(), feats.getDescriptorCount()) == (len(of), len(od))
+    o.close()
+    if os.path.exists(REF):
+        write_pgm(str(tmp_path / "f.pgm"), img)
+        subprocess.run([REF, "-i", "f.pgm", "-o", "f.bin", "--log", "--mode", "vlfeat", "--norm", "classic", "--gauss-mode", name, "--direct-scaling"],
+                       cwd=str(tmp_path), check=True, capture_output=True)
+        refbad = []
+        for oc in range(3):
+            for l in range(6):
+                ref = ol.read_ref_dump(str(tmp_path / "dir-octave-dump" / ("pyramid-o-%d-l-%d.dump" % (oc, l))))
+                if not np.array_equal(ref, ps.plane(0, oc, l)):
+                    refbad.append((oc, l, int((ref != ps.plane(0, oc, l)).sum())))
+        assert not refbad, refbad
+        rf, rd = ol.read_ref_features(str(tmp_path / "f.bin"))
+        assert (feats.getFeatureCount(), feats.getDescriptorCount()) == (len(rf), len(rd))
     ps.uninit()
