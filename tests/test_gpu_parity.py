@@ -943,3 +943,24 @@ def test_direct_scaling_with_every_gauss_mode(tmp_path, name, okw):
         rf, rd = ol.read_ref_features(str(tmp_path / "f.bin"))
         assert (feats.getFeatureCount(), feats.getDescriptorCount()) == (len(rf), len(rd))
     ps.uninit()
+
+
+@pytest.mark.parametrize("name,okw,direct", [("relative", dict(gauss_relative=1), False), ("fixed15", dict(gauss_fixed=7), False),
+                                             ("vlfeat-direct", dict(gauss_direct=1), False), ("vlfeat", dict(), True)])
+def test_float_images_with_the_other_pyramid_modes(name, okw, direct):
+    """PopSift::FloatImages through the other pyramid modes (they read the input through the same float texture model):
+    planes bit-exact against the oracle, same feature / descriptor counts."""
+    w, h = 320, 240
+    img = make_frame(w, h, 41).astype(np.float32) / np.float32(256.0)
+    cfg = mk_cfg("vlfeat", "classic")
+    cfg.setGaussMode(name)
+    if direct:
+        cfg.setScalingMode(0)
+    ps, feats = _run_gpu_float(img, cfg)
+    o = ol.Oracle(ol.make_config(mode="vlfeat", norm="classic", scaling_mode=1 if direct else 0, **okw), w, h)
+    o.run(img)
+    bad = [(oc, l) for oc in range(o.num_octaves) for l in range(6) if not np.array_equal(ps.plane(0, oc, l), o.gauss(oc, l))]
+    assert not bad, bad
+    of, od = o.features()
+    assert (feats.getFeatureCount(), feats.getDescriptorCount()) == (len(of), len(od))
+    ps.uninit(); o.close()
