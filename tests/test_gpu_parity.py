@@ -964,3 +964,22 @@ def test_float_images_with_the_other_pyramid_modes(name, okw, direct):
     of, od = o.features()
     assert (feats.getFeatureCount(), feats.getDescriptorCount()) == (len(of), len(od))
     ps.uninit(); o.close()
+
+
+@pytest.mark.parametrize("name", ["relative", "fixed15", "vlfeat-direct"])
+def test_other_pyramid_modes_through_the_graph_replay(name):
+    """The first frame of a geometry is issued directly, the second is captured as a CUDA graph, later ones replay it: the
+    other pyramid modes (their own kernel sequences) give the same planes and features on every one of four frames."""
+    w, h = 384, 288
+    img = make_frame(w, h, 43)
+    cfg = mk_cfg("vlfeat", "classic")
+    cfg.setGaussMode(name)
+    ps = api.PopSift(cfg, max_width=w, max_height=h, slots=1)
+    first = None
+    for k in range(4):
+        f = ps.enqueue(w, h, img).get()
+        cur = (f.getFeatureCount(), f.getDescriptorCount(), hashlib.sha256(ps.plane(0, 1, 3).tobytes()).hexdigest())
+        if first is None:
+            first = cur
+        assert cur == first, (k, cur, first)
+    ps.uninit()
