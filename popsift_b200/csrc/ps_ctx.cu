@@ -631,6 +631,8 @@ extern "C" ps_ctx* ps_create(int device, const ps_config* cfg, int max_w, int ma
         for (auto& ev : s.ev_fork) PS_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         for (auto& ev : s.ev_join) PS_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         PS_TRY(cudaMalloc(&s.d_img, (size_t)max_w * max_h * 4));
+        // the padding bytes between an image row and its pitch are read (never used) by the level-0 kernel's 4-byte copies
+        PS_TRY(cudaMemset(s.d_img, 0, (size_t)max_w * max_h * 4));
         PS_TRY(cudaHostAlloc(&s.h_img, (size_t)max_w * max_h * 4, cudaHostAllocDefault));
         PS_TRY(cudaMalloc(&s.d_planes, planes * sizeof(float)));
         s.planes_floats = planes;
