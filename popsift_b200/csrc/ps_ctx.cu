@@ -635,6 +635,9 @@ extern "C" ps_ctx* ps_create(int device, const ps_config* cfg, int max_w, int ma
         PS_TRY(cudaMemset(s.d_img, 0, (size_t)max_w * max_h * 4));
         PS_TRY(cudaHostAlloc(&s.h_img, (size_t)max_w * max_h * 4, cudaHostAllocDefault));
         PS_TRY(cudaMalloc(&s.d_planes, planes * sizeof(float)));
+        // once, so that the extrema kernel's speculative read of a candidate list beyond its count (k_extrema.cu, `prepare`)
+        // and the padding columns of the planes are defined memory
+        PS_TRY(cudaMemset(s.d_planes, 0, planes * sizeof(float)));
         s.planes_floats = planes;
         if (ctx->cfg.gauss_mode == PS_GAUSS_VLFEAT_RELATIVE || ctx->cfg.gauss_mode == PS_GAUSS_FIXED9 || ctx->cfg.gauss_mode == PS_GAUSS_FIXED15) {
             int32_t W0[kMaxOctaves], H0[kMaxOctaves];
