@@ -7,11 +7,15 @@
 #include <chrono>
 #include <condition_variable>
 #include <cstdlib>
+#include <cstdint>
 #include <cstring>
 #include <map>
 #include <mutex>
 #include <thread>
 #include <vector>
+#if defined(__x86_64__) || defined(_M_X64)
+#include <emmintrin.h>
+#endif
 
 namespace popsift { namespace detail {
 
@@ -72,12 +76,38 @@ inline PinnedPool& pinned_pool()
 // helper threads in parallel (POPSIFT_B200_COPY_THREADS, default 4; 1 = plain memcpy).  A caller enqueues its images back to
 // back, so a helper spins for a short while after a copy before it goes to sleep on the condition variable: waking a
 // sleeping thread costs more than the copy it is woken for.
+// One chunk of the copy.  The destination is a page-locked block that the GPU's copy engine reads next and the CPU never
+// does: streaming (non-temporal) stores skip the read-for-ownership of every destination line -- a third less host-memory
+// traffic per image, which is what bounds eight GPUs' worth of pageable frames -- and keep the frame out of the caches.
+inline void stream_copy(unsigned char* dst, const unsigned char* src, size_t n)
+{
+#if defined(__x86_64__) || defined(_M_X64)
+    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0 && n >= 4096) {
+        const size_t blocks = n / 64;
+        for (size_t b = 0; b < blocks; ++b) {
+            const __m128i v0 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + 4 * b);
+            const __m128i v1 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + 4 * b + 1);
+            const __m128i v2 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + 4 * b + 2);
+            const __m128i v3 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + 4 * b + 3);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + 4 * b, v0);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + 4 * b + 1, v1);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + 4 * b + 2, v2);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + 4 * b + 3, v3);
+        }
+        _mm_sfence();
+        if (n > blocks * 64) std::memcpy(dst + blocks * 64, src + blocks * 64, n - blocks * 64);
+        return;
+    }
+#endif
+    std::memcpy(dst, src, n);
+}
+
 class ParallelCopy {
 public:
     void copy(void* dst, const void* src, size_t n)
     {
         const int parts = threads_;
-        if (parts <= 1 || n < (size_t)(2u << 20)) { std::memcpy(dst, src, n); return; }
+        if (parts <= 1 || n < (size_t)(2u << 20)) { stream_copy(static_cast<unsigned char*>(dst), static_cast<const unsigned char*>(src), n); return; }
         std::lock_guard<std::mutex> one_at_a_time(call_mu_);
         start_helpers();
         const size_t chunk = ((n + parts - 1) / parts + 4095) & ~(size_t)4095;
@@ -88,7 +118,7 @@ public:
             std::lock_guard<std::mutex> g(mu_);
             cv_.notify_all();
         }
-        std::memcpy(dst, src, std::min(chunk, n));                       // part 0 on the calling thread
+        stream_copy(dst_, src_, std::min(chunk, n));                     // part 0 on the calling thread
         for (unsigned spins = 0; pending_.load(std::memory_order_acquire) != 0; ++spins)
             if (spins > 2000) std::this_thread::yield();
     }
@@ -128,7 +158,7 @@ private:
                     }
                     seen = generation_.load(std::memory_order_acquire);
                     const size_t off = chunk_ * (size_t)k;
-                    if (off < n_) std::memcpy(dst_ + off, src_ + off, std::min(chunk_, n_ - off));
+                    if (off < n_) stream_copy(dst_ + off, src_ + off, std::min(chunk_, n_ - off));
                     pending_.fetch_sub(1, std::memory_order_release);
                 }
             }).detach();
