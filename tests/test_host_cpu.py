@@ -368,3 +368,26 @@ def test_level0_plan_follows_the_texture_coordinate_model():
         got = L.ps_debug_level0_plan(w, h, W, H, shift, 4)
         assert got == want, (w, h, up, got, want)
         assert (got != 2) == shared(w, W, shift, 4), (w, h, up)
+
+
+def test_shipped_sass_uses_tma_and_tcgen05():
+    """The claims of DESIGN.md about the hardware paths, checked on the built library itself (cuobjdump, no GPU needed):
+    every column-marching level kernel stages its rows with the TMA unit (UTMALDG + mbarrier SYNCS), its column pass is packed
+    FFMA2, and the matcher issues tcgen05 MMAs (UTCHMMA) with TMEM loads (LDTM)."""
+    import shutil
+    import sys as _sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    lib = os.path.join(ROOT, "popsift_b200", "lib", "libpopsift_b200.so")
+    if not os.path.exists(lib):
+        pytest.skip("library not built")
+    _sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sass_hist
+    k = sass_hist.histogram(lib)
+    level = {n: c for n, c in k.items() if "march_level_kernel" in n}
+    assert len(level) >= 50
+    for n, c in level.items():
+        assert c["UTMALDG"] > 0 and c["SYNCS"] > 0 and c["FFMA2"] > 0, n
+        assert c["LDGSTS"] == 0, n                       # no cp.async staging left in the level kernels
+    tc = {n: c for n, c in k.items() if "match_tc_kernel" in n}
+    assert tc and all(c["UTCHMMA"] > 0 and c["LDTM"] > 0 and c["UTMALDG"] > 0 for c in tc.values())
