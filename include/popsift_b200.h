@@ -138,6 +138,9 @@ int  ps_abi_version(void);
 void ps_config_default(ps_config* cfg);
 /* replaces init_filter + init_constants (reference gauss_filter.cu:127-257, sift_constants.cu:22-53) */
 int  ps_gauss_tables_compute(const ps_config* cfg, ps_gauss_tables* out);
+/* replaces the printout of Config::setPrintGaussTables() / --print-gauss-tables (gauss_filter.cu:24-121,146-161,247-256): the
+ * same text, from this library's tables.  Returns the text length; writes at most cap - 1 characters + 0 into buf (may be NULL) */
+int  ps_format_gauss_tables(const ps_config* cfg, char* buf, size_t cap);
 /* replaces PopSift::private_apply_scale_factor + Pyramid ctor geometry
  * (reference popsift.cpp:109-126, sift_pyramid.cu:129-134); returns #octaves or <0 */
 int  ps_geometry(const ps_config* cfg, int w, int h, int32_t* W, int32_t* H);

@@ -58,7 +58,7 @@ EXPORTS = ["ps_abi_version", "ps_config_default", "ps_gauss_tables_compute", "ps
            "ps_sync", "ps_debug_plane", "ps_debug_extrema", "ps_slot_geometry", "ps_set_timing", "ps_stage_ms",
            "ps_launch_count", "ps_slot_stream", "ps_run_pyramid_only", "ps_run_level_only", "ps_host_alloc", "ps_host_free",
            "ps_download_dev", "ps_dev_alloc", "ps_dev_free", "ps_dev_to_host", "ps_wait_input", "ps_match", "ps_pointer_device", "ps_host_to_dev",
-           "ps_debug_level0_plan"]
+           "ps_debug_level0_plan", "ps_format_gauss_tables"]
 
 _lib = None
 
@@ -94,6 +94,7 @@ def load_library():
     L.ps_debug_plane.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     L.ps_debug_extrema.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     L.ps_debug_level0_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int]
+    L.ps_format_gauss_tables.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
     L.ps_slot_geometry.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.ps_set_timing.argtypes = [C.c_void_p, C.c_int]
     L.ps_stage_ms.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
@@ -205,6 +206,16 @@ class Config:
         """Config::ScaleDirect = 0, Config::ScaleDefault = 1 (reference sift_conf.h:75-80)"""
         self._c.scaling_mode = int(m)
     def setPrintGaussTables(self): self._print_gauss_tables = True
+
+    def gauss_tables_text(self) -> str:
+        """what the reference prints under setPrintGaussTables() (gauss_filter.cu:24-121,146-161)"""
+        L = load_library()
+        n = L.ps_format_gauss_tables(C.byref(self._c), None, 0)
+        if n < 0:
+            raise PopSiftError("unsupported configuration (sigma > 2.0 or levels > 12)")
+        buf = C.create_string_buffer(n + 1)
+        L.ps_format_gauss_tables(C.byref(self._c), buf, n + 1)
+        return buf.value.decode()
 
     def setInitialBlur(self, blur):
         self._c.has_initial_blur = 0 if blur == 0.0 else 1      # reference sift_conf.cu:246-255

@@ -19,12 +19,14 @@
 
 #include <algorithm>
 #include <condition_variable>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <iostream>
 #include <mutex>
 #include <sstream>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -90,6 +92,7 @@ struct PopSift::Pipe
     bool                      octaves_fixed = false;
     bool                      log_all = false;      // Config::LogMode::All, fixed when the context is created
     int                       log_levels = 3;
+    bool                      tables_printed = false; // --print-gauss-tables: once per PopSift
     float                     log_upscale = 1.0f;
 };
 
@@ -166,6 +169,7 @@ PopSift::PopSift(ImageMode imode, int device) : _pipe(new Pipe), _image_mode(imo
                 if (p->ctx) { ps_destroy(p->ctx); p->ctx = nullptr; }
                 ps_config c;
                 int slots;
+                bool print_tables = false;
                 {
                     // _config and slots are written by configure()/setSlots() on caller threads: read (and fix
                     // the octave count) under the same mutex; from here on configure() refuses changes
@@ -182,8 +186,20 @@ PopSift::PopSift(ImageMode imode, int device) : _pipe(new Pipe), _image_mode(imo
                     p->log_all = _config.getLogMode() == Config::All;
                     p->log_levels = std::max(2, _config.levels);
                     p->log_upscale = _config.getUpscaleFactor();
+                    print_tables = _config.ifPrintGaussTables() && !p->tables_printed;
+                    p->tables_printed = p->tables_printed || print_tables;
                 }
                 p->ctx_w = std::max(w, p->ctx_w); p->ctx_h = std::max(h, p->ctx_h);
+                if (print_tables) {
+                    // Config::setPrintGaussTables() (reference gauss_filter.cu:24-121,146-161,247-256): once, when the tables are built
+                    const int n = ps_format_gauss_tables(&c, nullptr, 0);
+                    if (n > 0) {
+                        std::string txt((size_t)n + 1, '\0');
+                        ps_format_gauss_tables(&c, &txt[0], txt.size());
+                        std::fputs(txt.c_str(), stdout);
+                        std::fflush(stdout);
+                    }
+                }
                 p->ctx = ps_create(_device, &c, p->ctx_w, p->ctx_h, slots);
                 p->in_slot.assign(slots, nullptr);
                 p->next_slot = 0;

@@ -10,7 +10,10 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdarg>
+#include <cstdio>
 #include <cstring>
+#include <string>
 
 namespace {
 
@@ -176,4 +179,54 @@ extern "C" int ps_geometry(const ps_config* cfg, int w, int h, int32_t* W, int32
         oh = static_cast<int>(std::ceil(oh / 2.0f));
     }
     return n;
+}
+
+// The text the reference prints under Config::setPrintGaussTables() / --print-gauss-tables (init_filter's header,
+// gauss_filter.cu:146-161, and print_gauss_filter_symbol(10), gauss_filter.cu:24-121), from the tables of this library.
+// Returns the length of the text (without the terminating 0); writes at most cap - 1 characters + 0 into buf.
+extern "C" int ps_format_gauss_tables(const ps_config* cfg, char* buf, size_t cap)
+{
+    ps_gauss_tables t;
+    if (!cfg || ps_gauss_tables_compute(cfg, &t) != PS_OK) return PS_ERR_ARG;
+    std::string out;
+    auto add = [&](const char* fmt, ...) {
+        char tmp[256];
+        va_list ap;
+        va_start(ap, fmt);
+        std::vsnprintf(tmp, sizeof(tmp), fmt, ap);
+        va_end(ap);
+        out += tmp;
+    };
+    const int stages = std::max(2, cfg->levels) + 3, columns = 10;
+    add("\nUpscaling factor: %f (i.e. original image is scaled by a factor of %f)\n\nSigma computations\n"
+        "    Initial sigma is %f\n    Input blurriness is assumed to be %f (scaled to %f)\n",
+        cfg->upscale, std::pow(2.0f, cfg->upscale), cfg->sigma, cfg->initial_blur, cfg->initial_blur * std::pow(2.0f, cfg->upscale));
+    auto table = [&](const float* filter, const float* sigma, const int32_t* span, int rows, bool split_sigma) {
+        for (int l = 0; l < rows; ++l) {
+            if (split_sigma) { add("      %d %d ", l, 2 * span[l] - 1); add("%2.6f: ", sigma[l]); }
+            else add("      %d %d %2.6f: ", l, 2 * span[l] - 1, sigma[l]);
+            const int m = std::min(span[l], columns);
+            for (int x = 0; x < m; ++x) add("%0.8f ", filter[l * PS_GAUSS_ALIGN + x]);
+            add(m < span[l] ? "...\n" : "\n");
+        }
+    };
+    add("\nGauss tables\n      level span sigma : center value -> edge value\n    relative sigma\n");
+    table(t.inc_filter, t.inc_sigma, t.inc_span, stages, true);
+    add("\n\nGauss tables for hardware interpolation\n"
+        "      level span sigma : center value -> ( interpolation value, multiplier ) [one edge value] \n");
+    table(t.inc_ifilter, t.inc_sigma, t.inc_ispan, stages, true);
+    add("\n\nGauss tables\n      level span sigma : center value -> edge value\n"
+        "      absolute filters octave 0 (compute level 0, all other levels directly from level 0)\n");
+    table(t.abs_filter, t.abs_sigma, t.abs_span, stages, false);
+    add("\n      absolute filters other octaves\n      (level 0 via downscaling, all other levels directly from level 0)\n");
+    table(t.absn_filter, t.absn_sigma, t.absn_span, stages, false);
+    add("\n    level 0-filters for direct downscaling\n");
+    table(t.dd_filter, t.dd_sigma, t.dd_span, PS_MAX_OCTAVES, false);
+    add("\n");
+    if (buf && cap > 0) {
+        const size_t n = std::min(out.size(), cap - 1);
+        std::memcpy(buf, out.data(), n);
+        buf[n] = 0;
+    }
+    return (int)out.size();
 }

@@ -391,3 +391,26 @@ def test_shipped_sass_uses_tma_and_tcgen05():
         assert c["LDGSTS"] == 0, n                       # no cp.async staging left in the level kernels
     tc = {n: c for n, c in k.items() if "match_tc_kernel" in n}
     assert tc and all(c["UTCHMMA"] > 0 and c["LDTM"] > 0 and c["UTMALDG"] > 0 for c in tc.values())
+
+
+def test_print_gauss_tables_text():
+    """Config::setPrintGaussTables() / --print-gauss-tables: the reference's printout (header of init_filter and
+    print_gauss_filter_symbol(10), gauss_filter.cu:24-121,146-161) rebuilt from this library's tables -- same sections, same
+    row format `level taps sigma: values`, values to 8 decimals, rows longer than 10 columns end with `...`."""
+    c = api.Config()
+    txt = c.gauss_tables_text()
+    assert txt.startswith("\nUpscaling factor: 1.000000 (i.e. original image is scaled by a factor of 2.000000)\n")
+    assert "    Initial sigma is 1.600000\n    Input blurriness is assumed to be 0.500000 (scaled to 1.000000)\n" in txt
+    for head in ("Gauss tables\n      level span sigma : center value -> edge value\n    relative sigma\n",
+                 "Gauss tables for hardware interpolation\n", "      absolute filters octave 0 (compute level 0, all other levels directly from level 0)\n",
+                 "      absolute filters other octaves\n", "    level 0-filters for direct downscaling\n"):
+        assert head in txt, head
+    t = c.gauss_tables()
+    # first incremental row: "      0 11 1.248999: 0.32525530 ..." (span 6 -> 11 taps, 6 values)
+    row0 = [ln for ln in txt.splitlines() if ln.startswith("      0 %d " % (2 * t.inc_span[0] - 1))][0]
+    vals = row0.split(": ")[1].split()
+    assert len(vals) == t.inc_span[0] and vals[0] == "%0.8f" % t.inc_filter[0] and row0.split()[2] == "%2.6f:" % t.inc_sigma[0]
+    # level 5 has 14 taps a side: only 10 printed
+    row5 = [ln for ln in txt.splitlines() if ln.startswith("      5 %d " % (2 * t.inc_span[5] - 1))][0]
+    assert row5.endswith("...") and len(row5.split(": ")[1].split()) == 11
+    assert txt.count("\n") > 6 * 4 + 20       # four tables of levels + 3 rows and the 20 rows of the dd table
